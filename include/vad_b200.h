@@ -1,0 +1,117 @@
+/*
+ * vad_b200.h — C ABI of the B200-native anomaly-scoring hot path.
+ *
+ * The reference (KuldeepChoksi/video-anomaly-detection) has no FFI: its hot path is the Python class API of
+ * models/autoencoder.py and models/video_autoencoder.py.  This library is what the drop-in Python classes
+ * (video-anomaly-detection_b200/models/*.py) bind with ctypes; every entry point names the reference lines it
+ * replaces.  Conventions:
+ *   - extern "C", plain pointers and sizes only; all data pointers are DEVICE pointers owned by the caller.
+ *   - nothing here allocates device memory or synchronises; work is enqueued on `stream`.
+ *   - return value: 0 = ok, negative = argument / configuration error (see vad_error_string), positive = cudaError_t.
+ *   - activations between layers are bf16 NHWC ("pixel-major"); model inputs / outputs are fp32 NCHW like the reference.
+ */
+#ifndef VAD_B200_H_
+#define VAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vad_stream_t; /* cudaStream_t */
+
+/* ---- error codes --------------------------------------------------------------------------------------------- */
+#define VAD_OK 0
+#define VAD_ERR_ARG (-1)          /* null pointer / bad size */
+#define VAD_ERR_SHAPE (-2)        /* H or W not a multiple of 16, channel count unsupported */
+#define VAD_ERR_UNSUPPORTED (-3)  /* no kernel instantiation for this (K-chunk, N-tile, epilogue) */
+#define VAD_ERR_DRIVER (-4)       /* cuTensorMapEncodeTiled unavailable / failed */
+#define VAD_ERR_WORKSPACE (-5)    /* workspace too small */
+
+const char* vad_error_string(int code);
+int vad_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+unsigned long long vad_launch_count(void);
+
+/* ---- one convolution-as-GEMM layer ----------------------------------------------------------------------------
+ * Implicit-GEMM on tcgen05/TMEM fed by TMA.  M = B*H*W input pixels (tiles of 128), N = n_total, K = ntaps*(c0+c1).
+ *   ntaps = 9 : nn.Conv2d(k=3, padding=1)            reference models/autoencoder.py:39-76,107-137,
+ *                                                     models/video_autoencoder.py:46-52,193-211
+ *   ntaps = 1 : nn.ConvTranspose2d(k=2, stride=2) as a GEMM with N = 4*Cout (column = (di*2+dj)*Cout + co)
+ *               reference models/autoencoder.py:104-134, models/video_autoencoder.py:244-259;
+ *               or a 1x1 conv (video_autoencoder.py:311-312 `proj`).
+ * BatchNorm (eval) must already be folded into weight/bias by the caller (host-side prepare step).
+ */
+enum vad_epilogue {
+  VAD_EPI_STORE = 0,            /* y = act(acc + bias) -> bf16 NHWC [B,H,W,n_total]                                   */
+  VAD_EPI_POOL = 1,             /* y = act(maxpool2x2(acc) + bias) -> bf16 NHWC [B,H/2,W/2,n_total]                   */
+  VAD_EPI_CONVT = 2,            /* pixel-shuffle store: bf16 NHWC [B,2H,2W,n_total/4], y = act(acc + bias)            */
+  VAD_EPI_LSTM = 3,             /* ConvLSTM gate update (video_autoencoder.py:72-83): c' , h' ; N tile = 4 gates x 32  */
+  VAD_EPI_TANH_SCORE = 4,       /* conv 3x3 -> 3 ch: recon = tanh(acc+bias); fused (x-recon)^2 reduction              */
+  VAD_EPI_CONVT_TANH_SCORE = 5  /* convT k2s2 -> 3 ch: recon = tanh(acc+bias); fused (x-recon)^2 reduction            */
+};
+
+typedef struct vad_conv_desc {
+  /* A operand: one or two bf16 NHWC sources viewed as [B][T][H][W][C] (second source = ConvLSTM hidden state) */
+  const void* src0;
+  const void* src1;
+  int c0, c1;   /* channels per source; multiples of 32 (c1 = 0: no second source) */
+  int T0, T1;   /* T extent of each source buffer (1 for plain frame batches) */
+  int t0, t1;   /* time index read from each source */
+  int B, H, W;  /* frames and INPUT spatial size */
+  int ntaps;    /* 9 or 1 */
+  /* B operand */
+  const void* weight; /* bf16 [n_total][ntaps*w_ctap], K index = tap*w_ctap + channel (source 0 first) */
+  const float* bias;  /* fp32 [n_total] */
+  int w_ctap;         /* weight columns per tap (0 = c0+c1); lets ConvLSTM step 0 skip the h half (c1 = 0) */
+  int n_total;        /* multiple of 16 */
+  int cout;           /* real output channels (CONVT: n_total/4; *_SCORE: 3) */
+  int epilogue;       /* enum vad_epilogue */
+  float slope;        /* act(v) = v > 0 ? v : v*slope   (0.2 LeakyReLU, 0 ReLU, 1 identity) */
+  /* outputs */
+  void* out;                  /* bf16; STORE/POOL/CONVT/LSTM(h') */
+  long long out_frame_stride; /* elements between consecutive frames b in `out` */
+  int out_cpitch;             /* elements between consecutive pixels in `out` */
+  float* c_state;             /* LSTM: fp32 [B,H,W,hid] cell state, updated in place */
+  int lstm_first;             /* LSTM: 1 = step 0 (c_prev = 0, c_state not read) */
+  const float* x;             /* *_SCORE: fp32 [B,3,Ho,Wo] model input */
+  float* recon;               /* *_SCORE: optional fp32 [B,3,Ho,Wo] */
+  float* heat;                /* *_SCORE: optional fp32 [B,Ho,Wo] per-pixel channel-mean squared error */
+  float* partials;            /* *_SCORE: fp32 [m_tiles][4] per-tile (sum of squares, min, max, -) */
+} vad_conv_desc;
+
+int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
+/* number of 128-pixel tiles (rows of `partials`) a *_SCORE layer produces for (B,H,W) input */
+int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles);
+
+/* ---- first layer: fp32 NCHW (3 ch) -> bf16 NHWC, conv3x3 + folded BN + LeakyReLU (+ 2x2 max-pool) --------------
+ * reference models/autoencoder.py:39-41 (enc1.0, no pool), models/video_autoencoder.py:193-196 (encoder.0, pool) */
+int vad_first_conv(const float* x, const float* weight /* fp32 [27][cout], k = (ky*3+kx)*3+ci */,
+                   const float* bias, int cout, float slope, int pool, int B, int H, int W, void* out_bf16_nhwc,
+                   vad_stream_t stream);
+
+/* ---- scoring reduction ----------------------------------------------------------------------------------------
+ * reference models/autoencoder.py:214-221, models/video_autoencoder.py:371-384, evaluate_video.py:56 (min/max) */
+/* finalize per-tile partials of a fused *_SCORE layer: score[f] = sum/(3*H*W), minmax[f] = {min,max} of the map */
+int vad_score_finalize(const float* partials, int frames, int tiles_per_frame, int H, int W, float* score,
+                       float* minmax /* nullable [frames][2] */, vad_stream_t stream);
+/* standalone (unfused) scoring pass: x, recon fp32 [N,3,H,W]; scratch >= vad_score_scratch_bytes(N,H,W) */
+size_t vad_score_scratch_bytes(int frames, int H, int W);
+int vad_score(const float* x, const float* recon, int frames, int H, int W, float* score, float* minmax,
+              float* heat, void* scratch, vad_stream_t stream);
+
+/* ---- layout helpers -------------------------------------------------------------------------------------------- */
+/* bf16 NHWC [N,H,W,C] -> fp32 NCHW [N,C,H,W]  (get_latent: models/autoencoder.py:195-197) */
+int vad_nhwc_bf16_to_nchw_f32(const void* src, int N, int H, int W, int C, float* dst, vad_stream_t stream);
+/* fp32 NCHW -> bf16 NHWC (entry for ConvLSTM / encoder / decoder sub-module calls on fp32 tensors) */
+int vad_nchw_f32_to_nhwc_bf16(const float* src, int N, int C, int H, int W, void* dst, vad_stream_t stream);
+/* per-frame heat-map normalisation to uint8: (e-min)/(max-min+1e-8)*255, truncation — evaluate_video.py:56-57 */
+int vad_heatmap_u8(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
+                   vad_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAD_B200_H_ */

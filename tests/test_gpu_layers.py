@@ -1,0 +1,249 @@
+"""GPU parity of each fused layer kernel against a plain torch fp32 reference of the same op.
+
+Operands are rounded to bf16 first (that is what the kernels consume); accumulation is fp32 on both sides, so the
+tolerance only has to cover the bf16 rounding of the OUTPUT (<= 2^-8 relative) plus accumulation-order noise.
+Everything goes through the C ABI (ctypes -> libvad_b200.so).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+OUT_RTOL = 1.0 / 128  # bf16 output rounding (2^-8) with margin
+OUT_ATOL = 2e-2
+
+
+def _mods():
+    from models import _engine as eng
+    from models import _native as nat
+    from models import _prepare as prep
+    return eng, nat, prep
+
+
+def _rand_nhwc(B, H, W, C, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(B, H, W, C, generator=g) * scale).to(torch.bfloat16)
+    return x.to(dev)
+
+
+def _nchw(x_nhwc):
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def _assert_close(got, ref, what, rtol=OUT_RTOL, atol=OUT_ATOL):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} elements off; max err {float(err.max()):.4g} "
+                           f"at ref {float(ref.flatten()[err.argmax()]):.4g}; ref rms {float(ref.pow(2).mean().sqrt()):.4g}")
+
+
+CONV_CASES = [
+    # (cin, cout, B, H, W)
+    (32, 32, 2, 32, 32),
+    (32, 64, 2, 16, 48),
+    (64, 64, 3, 16, 16),
+    (64, 128, 2, 24, 40),     # partial tiles in H and W
+    (128, 128, 5, 8, 8),      # two frames per tile, odd frame count
+    (128, 256, 2, 16, 16),
+    (256, 256, 2, 32, 32),
+    (128, 128, 1, 6, 10),     # H, W not powers of two, smaller than a tile
+]
+
+
+@pytest.mark.parametrize("cin,cout,B,H,W", CONV_CASES)
+@pytest.mark.parametrize("pool", [False, True])
+def test_conv3x3(cuda_device, cin, cout, B, H, W, pool):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(cin * 1000 + cout + H)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    packed = prep.pack_conv3x3(w.double(), b.double())
+    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    x = _rand_nhwc(B, H, W, cin, dev, seed=H * W)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = torch.full((B, Ho, Wo, cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    eng._conv(packed, x, B, H, W, out, 0.2, pool=pool, what="test conv")
+    torch.cuda.synchronize()
+    ref = F.conv2d(_nchw(x), w.to(torch.bfloat16).float().to(dev), b.to(dev), padding=1)
+    ref = F.leaky_relu(ref, 0.2)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    _assert_close(out, _nhwc(ref), f"conv3x3 {cin}->{cout} B{B} {H}x{W} pool={pool}")
+
+
+@pytest.mark.parametrize("cin,cout,B,H,W", [(256, 128, 2, 16, 16), (128, 64, 2, 8, 24), (64, 32, 3, 16, 16),
+                                           (32, 32, 2, 32, 32), (128, 128, 3, 4, 4)])
+def test_convt2x2(cuda_device, cin, cout, B, H, W):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(cin + cout)
+    w = torch.randn(cin, cout, 2, 2, generator=g) * (2.0 / cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    packed = prep.pack_convt2x2(w.double(), b.double())
+    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    x = _rand_nhwc(B, H, W, cin, dev, seed=7)
+    out = torch.full((B, 2 * H, 2 * W, cout), float("nan"), dtype=torch.bfloat16, device=dev)
+    eng._convt(packed, x, B, H, W, out, 0.0, what="test convT")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv_transpose2d(_nchw(x), w.to(torch.bfloat16).float().to(dev), b.to(dev), stride=2))
+    _assert_close(out, _nhwc(ref), f"convT {cin}->{cout} B{B} {H}x{W}")
+
+
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 64), (3, 16, 16), (1, 48, 80)])
+def test_first_conv(cuda_device, pool, B, H, W):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(32, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    b = torch.randn(32, generator=g) * 0.1
+    fw = prep.pack_first_conv(w.double(), b.double())
+    fw.w, fw.bias = fw.w.to(dev), fw.bias.to(dev)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    out = torch.full((B, Ho, Wo, 32), float("nan"), dtype=torch.bfloat16, device=dev)
+    eng._first_conv(fw, x, B, H, W, pool, out)
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(F.conv2d(x, w.to(dev), b.to(dev), padding=1), 0.2)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    _assert_close(out, _nhwc(ref), f"first conv pool={pool}", atol=1e-3)
+
+
+@pytest.mark.parametrize("B,T,H,W", [(2, 3, 8, 8), (3, 2, 6, 10)])
+def test_convlstm_sequence(cuda_device, B, T, H, W):
+    """ConvLSTM over a short sequence vs the torch formulation of video_autoencoder.py:64-85 (one layer)."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    cin = hid = 128
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(4 * hid, cin + hid, 3, 3, generator=g) * (1.0 / (9 * (cin + hid))) ** 0.5
+    b = torch.randn(4 * hid, generator=g) * 0.1
+    packed = {"lstm.0": prep.pack_lstm(w.double(), b.double(), hid), "lstm_layers": 1}
+    packed["lstm.0"].w, packed["lstm.0"].bias = packed["lstm.0"].w.to(dev), packed["lstm.0"].bias.to(dev)
+    ve = eng.VideoEngine(packed)
+    seq = _rand_nhwc(B * T, H, W, cin, dev, seed=3).view(B, T, H, W, cin)
+    out = ve.convlstm(seq, B, T, H, W)
+    torch.cuda.synchronize()
+    wq = w.to(torch.bfloat16).float().to(dev)
+    h = torch.zeros(B, hid, H, W, device=dev)
+    c = torch.zeros_like(h)
+    xs = seq.float().permute(0, 1, 4, 2, 3)
+    for t in range(T):
+        # the kernel feeds h back as bf16 (it is the next step's MMA operand)
+        gates = F.conv2d(torch.cat([xs[:, t], h.to(torch.bfloat16).float()], 1), wq, b.to(dev), padding=1)
+        gi, gf, gg, go = torch.split(gates, hid, 1)
+        c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+        h = torch.sigmoid(go) * torch.tanh(c)
+        _assert_close(out[:, t], _nhwc(h), f"convlstm h at t={t}", atol=1e-2)
+    cst = ve.bufs.get("c0", (B, H, W, hid), torch.float32, dev)
+    _assert_close(cst, _nhwc(c), "convlstm final c", rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 48)])
+def test_last_conv_tanh_score(cuda_device, B, H, W):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(13)
+    w = torch.randn(3, 32, 3, 3, generator=g) * (1.0 / 288) ** 0.5
+    b = torch.randn(3, generator=g) * 0.1
+    packed = prep.pack_conv3x3(w.double(), b.double(), pad_n_to=16)
+    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    a = _rand_nhwc(B, H, W, 32, dev, seed=17)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
+    tiles = nat.m_tiles(B, H, W, True)
+    partials = torch.zeros(tiles, 4, device=dev)
+    recon = torch.full((B, 3, H, W), float("nan"), device=dev)
+    heat = torch.full((B, H, W), float("nan"), device=dev)
+    eng._gemm_layer(packed, a, B, H, W, nat.EPI_TANH_SCORE, 1.0, None, x=x, recon=recon, heat=heat, partials=partials)
+    score, minmax = eng._finalize(partials, B, tiles // B, H, W, None, dev)
+    torch.cuda.synchronize()
+    ref = torch.tanh(F.conv2d(_nchw(a), w.to(torch.bfloat16).float().to(dev), b.to(dev), padding=1))
+    err = ((x - ref) ** 2).mean(1)
+    _assert_close(recon, ref, "recon", rtol=1e-4, atol=1e-4)
+    _assert_close(heat, err, "heat", rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(score, err.mean((1, 2)), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(minmax[:, 0], err.amin((1, 2)), rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(minmax[:, 1], err.amax((1, 2)), rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (3, 8, 24), (2, 8, 8)])
+def test_last_convt_tanh_score(cuda_device, B, H, W):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(19)
+    w = torch.randn(32, 3, 2, 2, generator=g) * (1.0 / 32) ** 0.5
+    b = torch.randn(3, generator=g) * 0.1
+    packed = prep.pack_convt2x2(w.double(), b.double(), pad_n_to=16)
+    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    a = _rand_nhwc(B, H, W, 32, dev, seed=23)
+    Ho, Wo = 2 * H, 2 * W
+    x = (torch.rand(B, 3, Ho, Wo, generator=g) * 2 - 1).to(dev)
+    tiles = nat.m_tiles(B, H, W, True)
+    partials = torch.zeros(tiles, 4, device=dev)
+    recon = torch.full((B, 3, Ho, Wo), float("nan"), device=dev)
+    heat = torch.full((B, Ho, Wo), float("nan"), device=dev)
+    eng._gemm_layer(packed, a, B, H, W, nat.EPI_CONVT_TANH_SCORE, 1.0, None, x=x, recon=recon, heat=heat,
+                    partials=partials)
+    score, minmax = eng._finalize(partials, B, tiles // B, Ho, Wo, None, dev)
+    torch.cuda.synchronize()
+    ref = torch.tanh(F.conv_transpose2d(_nchw(a), w.to(torch.bfloat16).float().to(dev), b.to(dev), stride=2))
+    err = ((x - ref) ** 2).mean(1)
+    _assert_close(recon, ref, "recon", rtol=1e-4, atol=1e-4)
+    _assert_close(heat, err, "heat", rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(score, err.mean((1, 2)), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(minmax[:, 0], err.amin((1, 2)), rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(minmax[:, 1], err.amax((1, 2)), rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,H,W", [(5, 64, 64), (2, 256, 256), (3, 16, 48)])
+def test_standalone_score_and_heatmap_u8(cuda_device, N, H, W):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    lib = nat.load()
+    g = torch.Generator().manual_seed(29)
+    x = (torch.rand(N, 3, H, W, generator=g) * 2 - 1).to(dev)
+    r = (torch.rand(N, 3, H, W, generator=g) * 2 - 1).to(dev)
+    score = torch.empty(N, device=dev)
+    minmax = torch.empty(N, 2, device=dev)
+    heat = torch.empty(N, H, W, device=dev)
+    scratch = torch.empty(lib.vad_score_scratch_bytes(N, H, W), dtype=torch.uint8, device=dev)
+    nat.check(lib.vad_score(x.data_ptr(), r.data_ptr(), N, H, W, score.data_ptr(), minmax.data_ptr(), heat.data_ptr(),
+                            scratch.data_ptr(), nat.stream_ptr()), "vad_score")
+    u8 = torch.empty(N, H, W, dtype=torch.uint8, device=dev)
+    nat.check(lib.vad_heatmap_u8(heat.data_ptr(), minmax.data_ptr(), N, H, W, u8.data_ptr(), nat.stream_ptr()),
+              "vad_heatmap_u8")
+    torch.cuda.synchronize()
+    err = ((x - r) ** 2).mean(1)
+    torch.testing.assert_close(heat, err, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(score, err.mean((1, 2)), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(minmax[:, 0], heat.amin((1, 2)), rtol=0, atol=0)
+    torch.testing.assert_close(minmax[:, 1], heat.amax((1, 2)), rtol=0, atol=0)
+    # evaluate_video.py:56-57 on the kernel's own heat map
+    e = heat.cpu().numpy()
+    import numpy as np
+    ref_u8 = np.stack([(((m - m.min()) / (m.max() - m.min() + 1e-8)) * 255).astype(np.uint8) for m in e])
+    diff = np.abs(ref_u8.astype(np.int32) - u8.cpu().numpy().astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+def test_layout_round_trip(cuda_device):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    lib = nat.load()
+    x = torch.randn(3, 40, 6, 10, device=dev)
+    nhwc = torch.empty(3, 6, 10, 40, dtype=torch.bfloat16, device=dev)
+    back = torch.empty_like(x)
+    nat.check(lib.vad_nchw_f32_to_nhwc_bf16(x.data_ptr(), 3, 40, 6, 10, nhwc.data_ptr(), nat.stream_ptr()), "to nhwc")
+    nat.check(lib.vad_nhwc_bf16_to_nchw_f32(nhwc.data_ptr(), 3, 6, 10, 40, back.data_ptr(), nat.stream_ptr()), "to nchw")
+    torch.cuda.synchronize()
+    assert torch.equal(nhwc, x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert torch.equal(back, x.to(torch.bfloat16).float())

@@ -1,0 +1,514 @@
+// C-ABI entry points of libvad_b200.so (see include/vad_b200.h) and the small CUDA-core kernels around the
+// tcgen05 GEMM: first 3-channel convolution, standalone scoring pass, score finalisation, layout helpers.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "vad_internal.h"
+#include "vad_ptx.cuh"
+
+namespace vad {
+
+// ------------------------------------------------------------------------------------------------ bookkeeping
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int floor_log2(int v) {
+  int l = 0;
+  while ((2 << l) <= v) ++l;
+  return l;
+}
+static int ceil_log2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// 128 accumulator rows = TN frames x TH rows x TW columns (powers of two; partial tiles are zero-filled by TMA on
+// load and masked on store).  Score layers force TN = 1 so that every tile lies inside one frame.
+TileGeom pick_tile_geometry(int B, int H, int W, bool single_frame_tiles) {
+  TileGeom g;
+  g.lgTW = floor_log2(W) < 4 ? floor_log2(W) : 4;
+  const int rem = 7 - g.lgTW;
+  int lgTH = floor_log2(H);
+  const int cap = (g.lgTW == 4) ? 3 : rem;
+  g.lgTH = lgTH < cap ? lgTH : cap;
+  int lgTN = rem - g.lgTH;
+  if (single_frame_tiles) lgTN = 0;
+  const int need = ceil_log2(B);
+  g.lgTN = lgTN < need ? lgTN : need;
+  g.tiles_w = (W + (1 << g.lgTW) - 1) >> g.lgTW;
+  g.tiles_h = (H + (1 << g.lgTH) - 1) >> g.lgTH;
+  g.tiles_b = (B + (1 << g.lgTN) - 1) >> g.lgTN;
+  return g;
+}
+
+static int encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int T, int B, int CK,
+                          const TileGeom& g) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return VAD_ERR_DRIVER;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)T * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)CK, 1u << g.lgTW, 1u << g.lgTH, 1u, 1u << g.lgTN};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VAD_OK : VAD_ERR_DRIVER;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* base, int K, int N, int CK, int BN) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return VAD_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)CK, (cuuint32_t)BN};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VAD_OK : VAD_ERR_DRIVER;
+}
+
+// ------------------------------------------------------------------------------------------------ first conv
+// fp32 NCHW 3-channel input -> bf16 NHWC, conv3x3 pad 1 + folded BN + LeakyReLU (+ 2x2 max-pool).
+// K = 27 is too thin for the tensor pipe to matter and the layer is HBM-bound; CUDA cores.
+template <int COUT, bool POOL>
+__global__ void __launch_bounds__(256) first_conv_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                                                         const float* __restrict__ bias, float slope, int B, int H,
+                                                         int W, __nv_bfloat16* __restrict__ out, int tiles_x,
+                                                         int tiles_y) {
+  // One thread = one conv output pixel of a 32x8 tile.  POOL: the four pixels of a 2x2 window sit in four
+  // adjacent lanes (max by two shuffles); each of them then stores a quarter of the pooled pixel's channels.
+  constexpr int TX = 32, TY = 8;
+  constexpr int IW = TX + 2, IH = TY + 2;
+  static_assert(COUT == 32, "pooled store splits 32 channels over 4 lanes");
+  __shared__ float s_in[3][IH][IW + 1];
+  __shared__ float4 s_w[27][COUT / 4];
+  __shared__ float s_b[COUT];
+
+  const int tile = blockIdx.x;
+  const int tx_i = tile % tiles_x;
+  const int ty_i = (tile / tiles_x) % tiles_y;
+  const int f = tile / (tiles_x * tiles_y);
+  const int x0 = tx_i * TX, y0 = ty_i * TY;  // conv-resolution tile origin
+  const float* xf = x + static_cast<long long>(f) * 3 * H * W;
+
+  for (int i = threadIdx.x; i < 27 * (COUT / 4); i += 256)
+    s_w[i / (COUT / 4)][i % (COUT / 4)] = reinterpret_cast<const float4*>(wgt)[i];
+  if (threadIdx.x < COUT) s_b[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * IH * IW; i += 256) {
+    const int c = i / (IH * IW);
+    const int rem = i - c * (IH * IW);
+    const int iy = rem / IW, ix = rem - iy * IW;
+    const int gy = y0 - 1 + iy, gx = x0 - 1 + ix;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(xf + (static_cast<long long>(c) * H + gy) * W + gx);
+    s_in[c][iy][ix] = v;
+  }
+  __syncthreads();
+
+  int px, py, sub = 0;
+  if constexpr (POOL) {
+    const int quad = threadIdx.x >> 2;
+    sub = threadIdx.x & 3;
+    px = 2 * (quad & 15) + (sub & 1);
+    py = 2 * (quad >> 4) + (sub >> 1);
+  } else {
+    px = threadIdx.x & 31;
+    py = threadIdx.x >> 5;
+  }
+  float acc[COUT];
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = s_in[ci][py + ky][px + kx];
+        const int k = (ky * 3 + kx) * 3 + ci;
+#pragma unroll
+        for (int j4 = 0; j4 < COUT / 4; ++j4) {
+          const float4 w4 = s_w[k][j4];
+          acc[4 * j4 + 0] = fmaf(v, w4.x, acc[4 * j4 + 0]);
+          acc[4 * j4 + 1] = fmaf(v, w4.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(v, w4.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(v, w4.w, acc[4 * j4 + 3]);
+        }
+      }
+  if constexpr (POOL) {
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+      acc[j] = fmaxf(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], 1));
+      acc[j] = fmaxf(acc[j], __shfl_xor_sync(0xffffffffu, acc[j], 2));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < COUT; ++j) {
+    const float v = acc[j] + s_b[j];
+    acc[j] = v > 0.f ? v : v * slope;
+  }
+  const int gy = y0 + py, gx = x0 + px;
+  if (gy < H && gx < W) {
+    if constexpr (POOL) {
+      const int Ho = H >> 1, Wo = W >> 1;
+      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<long long>(f) * Ho + (gy >> 1)) * Wo + (gx >> 1)) * COUT +
+                                            sub * 8);
+      uint4 val;
+      if (sub == 0) val = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      else if (sub == 1) val = make_uint4(pack_bf16x2(acc[8], acc[9]), pack_bf16x2(acc[10], acc[11]), pack_bf16x2(acc[12], acc[13]), pack_bf16x2(acc[14], acc[15]));
+      else if (sub == 2) val = make_uint4(pack_bf16x2(acc[16], acc[17]), pack_bf16x2(acc[18], acc[19]), pack_bf16x2(acc[20], acc[21]), pack_bf16x2(acc[22], acc[23]));
+      else val = make_uint4(pack_bf16x2(acc[24], acc[25]), pack_bf16x2(acc[26], acc[27]), pack_bf16x2(acc[28], acc[29]), pack_bf16x2(acc[30], acc[31]));
+      *dst = val;
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<long long>(f) * H + gy) * W + gx) * COUT);
+#pragma unroll
+      for (int j8 = 0; j8 < COUT / 8; ++j8)
+        dst[j8] = make_uint4(pack_bf16x2(acc[j8 * 8 + 0], acc[j8 * 8 + 1]), pack_bf16x2(acc[j8 * 8 + 2], acc[j8 * 8 + 3]),
+                             pack_bf16x2(acc[j8 * 8 + 4], acc[j8 * 8 + 5]), pack_bf16x2(acc[j8 * 8 + 6], acc[j8 * 8 + 7]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scoring kernels
+// Standalone pass: one block reduces a contiguous pixel range of one frame; float4 streaming loads of the three
+// channel planes of x and recon; writes optional heat map; per-block (sum, min, max) partial.
+__global__ void __launch_bounds__(256) score_partial_kernel(const float* __restrict__ x,
+                                                            const float* __restrict__ recon, long long plane,
+                                                            int blocks_per_frame, long long chunk,
+                                                            float* __restrict__ heat, float* __restrict__ partials) {
+  const int f = blockIdx.x / blocks_per_frame;
+  const int bi = blockIdx.x % blocks_per_frame;
+  const long long p0 = bi * chunk;
+  long long p1 = p0 + chunk;
+  if (p1 > plane) p1 = plane;
+  const float* xf = x + static_cast<long long>(f) * 3 * plane;
+  const float* rf = recon + static_cast<long long>(f) * 3 * plane;
+  float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
+  for (long long p = p0 + threadIdx.x * 4LL; p < p1; p += 256 * 4) {
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(xf + c * plane + p));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(rf + c * plane + p));
+      const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+      e.x += d0 * d0; e.y += d1 * d1; e.z += d2 * d2; e.w += d3 * d3;
+    }
+    ssum += (e.x + e.y) + (e.z + e.w);
+    smin = fminf(smin, fminf(fminf(e.x, e.y), fminf(e.z, e.w)));
+    smax = fmaxf(smax, fmaxf(fmaxf(e.x, e.y), fmaxf(e.z, e.w)));
+    if (heat) {
+      const float k = 1.f / 3.f;
+      __stcs(reinterpret_cast<float4*>(heat + static_cast<long long>(f) * plane + p),
+             make_float4(e.x * k, e.y * k, e.z * k, e.w * k));
+    }
+  }
+  __shared__ float red[8][3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[warp][0] = ssum; red[warp][1] = smin; red[warp][2] = smax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f, mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < 8; ++i) { s += red[i][0]; mn = fminf(mn, red[i][1]); mx = fmaxf(mx, red[i][2]); }
+    *reinterpret_cast<float4*>(partials + static_cast<long long>(blockIdx.x) * 4) =
+        make_float4(s, mn * (1.f / 3.f), mx * (1.f / 3.f), 0.f);
+  }
+}
+
+// One warp per frame folds that frame's tile partials in a fixed order (bitwise reproducible run to run).
+__global__ void __launch_bounds__(128) score_finalize_kernel(const float* __restrict__ partials, int frames,
+                                                             int tiles_per_frame, float inv_count,
+                                                             float* __restrict__ score, float* __restrict__ minmax) {
+  const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  const float4* p = reinterpret_cast<const float4*>(partials) + static_cast<long long>(f) * tiles_per_frame;
+  float s = 0.f, mn = INFINITY, mx = -INFINITY;
+  for (int i = lane; i < tiles_per_frame; i += 32) {
+    const float4 v = p[i];
+    s += v.x;
+    mn = fminf(mn, v.y);
+    mx = fmaxf(mx, v.z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+    score[f] = s * inv_count;
+    if (minmax) { minmax[2 * f] = mn; minmax[2 * f + 1] = mx; }
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, long long total, int HW, int C,
+                                    float* __restrict__ dst) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;  // index in NCHW order
+  if (i >= total) return;
+  const long long n = i / (static_cast<long long>(C) * HW);
+  const long long rem = i - n * C * HW;
+  const int c = static_cast<int>(rem / HW);
+  const int p = static_cast<int>(rem - static_cast<long long>(c) * HW);
+  dst[i] = __bfloat162float(src[(n * HW + p) * C + c]);
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, long long total, int HW, int C,
+                                    __nv_bfloat16* __restrict__ dst) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;  // index in NHWC order
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long np = i / C;
+  const long long n = np / HW;
+  const int p = static_cast<int>(np - n * HW);
+  dst[i] = __float2bfloat16_rn(src[(n * C + c) * HW + p]);
+}
+
+__global__ void heatmap_u8_kernel(const float* __restrict__ heat, const float* __restrict__ minmax, long long plane,
+                                  long long total, uint8_t* __restrict__ out) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i >= total) return;
+  const long long f = i / plane;
+  const float mn = minmax[2 * f], mx = minmax[2 * f + 1];
+  const float norm = (heat[i] - mn) / (mx - mn + 1e-8f);
+  out[i] = static_cast<uint8_t>(norm * 255.f);
+}
+
+}  // namespace vad
+
+// ================================================================================================ C ABI
+using namespace vad;
+
+extern "C" {
+
+const char* vad_error_string(int code) {
+  switch (code) {
+    case VAD_OK: return "ok";
+    case VAD_ERR_ARG: return "bad argument (null pointer or non-positive size)";
+    case VAD_ERR_SHAPE: return "unsupported shape (H, W must be multiples of 16; channels multiples of 32)";
+    case VAD_ERR_UNSUPPORTED: return "no kernel instantiation for this layer configuration";
+    case VAD_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed (needs an sm_100 driver)";
+    case VAD_ERR_WORKSPACE: return "workspace too small";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+int vad_version(void) { return 100; }
+
+unsigned long long vad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles) {
+  if (B <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  return pick_tile_geometry(B, H, W, force_single_frame_tiles != 0).m_tiles();
+}
+
+int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || !d->src0 || !d->weight || !d->bias) return VAD_ERR_ARG;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->n_total <= 0) return VAD_ERR_ARG;
+  if (d->ntaps != 9 && d->ntaps != 1) return VAD_ERR_ARG;
+  if (d->c0 <= 0 || d->c0 % 32 != 0 || d->c1 < 0 || d->c1 % 32 != 0) return VAD_ERR_SHAPE;
+  if (d->c1 > 0 && !d->src1) return VAD_ERR_ARG;
+  const int epi = d->epilogue;
+  const bool is_score = (epi == VAD_EPI_TANH_SCORE || epi == VAD_EPI_CONVT_TANH_SCORE);
+  const int CK = (d->c0 % 64 == 0 && d->c1 % 64 == 0) ? 64 : 32;
+  int BN;
+  switch (epi) {
+    case VAD_EPI_STORE:
+    case VAD_EPI_POOL:
+      if (d->n_total % 32 != 0) return VAD_ERR_SHAPE;
+      BN = d->n_total >= 256 && d->n_total % 256 == 0 ? 256 : d->n_total % 128 == 0 ? 128 : d->n_total % 64 == 0 ? 64 : 32;
+      if (CK == 32 && BN > 64) BN = 64;
+      if (!d->out) return VAD_ERR_ARG;
+      if (epi == VAD_EPI_POOL && ((d->H | d->W) & 1)) return VAD_ERR_SHAPE;
+      break;
+    case VAD_EPI_CONVT:
+      if (d->n_total % 128 != 0 || d->cout * 4 != d->n_total || d->cout % 32 != 0) return VAD_ERR_SHAPE;
+      BN = 128;
+      if (!d->out) return VAD_ERR_ARG;
+      break;
+    case VAD_EPI_LSTM:
+      if (d->n_total % 128 != 0 || d->cout * 4 != d->n_total) return VAD_ERR_SHAPE;
+      BN = 128;
+      if (!d->out || !d->c_state) return VAD_ERR_ARG;
+      break;
+    case VAD_EPI_TANH_SCORE:
+    case VAD_EPI_CONVT_TANH_SCORE:
+      if (d->n_total != 16 || d->cout != 3) return VAD_ERR_SHAPE;
+      BN = 16;
+      if (!d->x || !d->partials) return VAD_ERR_ARG;
+      break;
+    default:
+      return VAD_ERR_ARG;
+  }
+
+  ConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  const TileGeom g = pick_tile_geometry(d->B, d->H, d->W, is_score);
+  int rc = encode_act_map(&a.mapA0, d->src0, d->c0, d->W, d->H, d->T0 > 0 ? d->T0 : 1, d->B, CK, g);
+  if (rc != VAD_OK) return rc;
+  if (d->c1 > 0) {
+    rc = encode_act_map(&a.mapA1, d->src1, d->c1, d->W, d->H, d->T1 > 0 ? d->T1 : 1, d->B, CK, g);
+    if (rc != VAD_OK) return rc;
+  }
+  const int w_ctap = d->w_ctap > 0 ? d->w_ctap : d->c0 + d->c1;
+  if (w_ctap < d->c0 + d->c1) return VAD_ERR_ARG;
+  const int K = d->ntaps * w_ctap;
+  rc = encode_weight_map(&a.mapB, d->weight, K, d->n_total, CK, BN);
+  if (rc != VAD_OK) return rc;
+  a.chunks0 = d->c0 / CK;
+  a.chunks1 = d->c1 / CK;
+  a.ntaps = d->ntaps;
+  a.w_ctap = w_ctap;
+  a.tA0 = d->t0;
+  a.tA1 = d->t1;
+  a.B = d->B; a.H = d->H; a.W = d->W;
+  a.lgTW = g.lgTW; a.lgTH = g.lgTH; a.lgTN = g.lgTN;
+  a.tiles_w = g.tiles_w; a.tiles_h = g.tiles_h; a.tiles_b = g.tiles_b;
+  a.n_tiles = d->n_total / BN;
+  a.total_tiles = g.m_tiles() * a.n_tiles;
+  a.bias = d->bias;
+  a.slope = d->slope;
+  a.out = d->out;
+  a.out_fs = d->out_frame_stride;
+  a.out_cp = d->out_cpitch;
+  a.cout = d->cout;
+  a.c_state = d->c_state;
+  a.lstm_first = d->lstm_first;
+  a.x = d->x; a.recon = d->recon; a.heat = d->heat; a.partials = d->partials;
+  const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return launch_conv_umma(CK, BN, epi, a, grid, stream);
+}
+
+int vad_first_conv(const float* x, const float* weight, const float* bias, int cout, float slope, int pool, int B,
+                   int H, int W, void* out, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !weight || !bias || !out || B <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  if (cout != 32) return VAD_ERR_UNSUPPORTED;
+  if (pool && ((H | W) & 1)) return VAD_ERR_SHAPE;
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  const long long blocks = static_cast<long long>(tiles_x) * tiles_y * B;
+  if (blocks > 0x7fffffffLL) return VAD_ERR_SHAPE;
+  if (pool)
+    first_conv_kernel<32, true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        x, weight, bias, slope, B, H, W, reinterpret_cast<__nv_bfloat16*>(out), tiles_x, tiles_y);
+  else
+    first_conv_kernel<32, false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        x, weight, bias, slope, B, H, W, reinterpret_cast<__nv_bfloat16*>(out), tiles_x, tiles_y);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vad_score_finalize(const float* partials, int frames, int tiles_per_frame, int H, int W, float* score,
+                       float* minmax, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!partials || !score || frames <= 0 || tiles_per_frame <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const float inv = 1.0f / (3.0f * static_cast<float>(H) * static_cast<float>(W));
+  score_finalize_kernel<<<(frames + 3) / 4, 128, 0, stream>>>(partials, frames, tiles_per_frame, inv, score, minmax);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int score_blocks_per_frame(int H, int W) {
+  const long long plane = static_cast<long long>(H) * W;
+  long long bpf = plane / 8192;
+  if (bpf < 1) bpf = 1;
+  if (bpf > 4096) bpf = 4096;
+  return static_cast<int>(bpf);
+}
+
+size_t vad_score_scratch_bytes(int frames, int H, int W) {
+  if (frames <= 0 || H <= 0 || W <= 0) return 0;
+  return static_cast<size_t>(frames) * score_blocks_per_frame(H, W) * 4 * sizeof(float);
+}
+
+int vad_score(const float* x, const float* recon, int frames, int H, int W, float* score, float* minmax, float* heat,
+              void* scratch, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !recon || !score || !scratch || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const long long plane = static_cast<long long>(H) * W;
+  if (plane % 4 != 0) return VAD_ERR_SHAPE;
+  const int bpf = score_blocks_per_frame(H, W);
+  long long chunk = (plane + bpf - 1) / bpf;
+  chunk = (chunk + 3) / 4 * 4;
+  const long long blocks = static_cast<long long>(frames) * bpf;
+  if (blocks > 0x7fffffffLL) return VAD_ERR_SHAPE;
+  score_partial_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, recon, plane, bpf, chunk, heat,
+                                                                         reinterpret_cast<float*>(scratch));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return vad_score_finalize(reinterpret_cast<const float*>(scratch), frames, bpf, H, W, score, minmax, stream_);
+}
+
+int vad_nhwc_bf16_to_nchw_f32(const void* src, int N, int H, int W, int C, float* dst, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || C <= 0) return VAD_ERR_ARG;
+  const long long total = static_cast<long long>(N) * C * H * W;
+  nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), total, H * W, C, dst);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vad_nchw_f32_to_nhwc_bf16(const float* src, int N, int C, int H, int W, void* dst, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || C <= 0) return VAD_ERR_ARG;
+  const long long total = static_cast<long long>(N) * C * H * W;
+  nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      src, total, H * W, C, reinterpret_cast<__nv_bfloat16*>(dst));
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vad_heatmap_u8(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
+                   vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!heat || !minmax || !out || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = plane * frames;
+  heatmap_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(heat, minmax, plane, total, out);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Layer schedules of the two autoencoders on top of libvad_b200 (one C-ABI call per fused layer).
+
+Activations are bf16 NHWC buffers cached per input shape; the model input `x` (fp32 NCHW) is read directly by the
+first conv kernel and again by the fused scoring epilogue of the last decoder layer, so the reconstruction itself
+only touches HBM when the caller asks for it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _native as nat
+from ._prepare import FirstConvWeights, GemmWeights
+
+LEAKY, RELU, IDENT = 0.2, 0.0, 1.0
+
+
+@dataclass
+class ScoreOutputs:
+    score: torch.Tensor                 # [frames] fp32: mean over (C,H,W) of (x - recon)^2
+    minmax: torch.Tensor                # [frames, 2] fp32: min / max of the per-pixel map (heat-map normalisation)
+    heat: Optional[torch.Tensor]        # [frames, H, W] fp32 per-pixel channel-mean squared error
+    recon: Optional[torch.Tensor]       # [frames, 3, H, W] fp32
+
+
+def _require_cuda_input(x: torch.Tensor, ndim: Tuple[int, ...]) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError("vad_b200 scoring path is CUDA-only (sm_100a kernels, no CPU fallback); "
+                           f"got a tensor on {x.device}")
+    if x.dim() not in ndim:
+        raise RuntimeError(f"expected a {ndim}-D input, got shape {tuple(x.shape)}")
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+class _Buffers:
+    """Shape-keyed cache of device buffers (the library itself never allocates)."""
+
+    def __init__(self) -> None:
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+
+    def get(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype, device) -> torch.Tensor:
+        key = (name, tuple(shape), dtype, str(device))
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._bufs[key] = t
+        return t
+
+
+def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: int, slope: float,
+                out: Optional[torch.Tensor], *, c0: int = 0, T0: int = 1, t0: int = 0, src1: Optional[torch.Tensor] = None,
+                c1: int = 0, T1: int = 1, t1: int = 0, out_frame_stride: int = 0, out_cpitch: int = 0,
+                out_offset_elems: int = 0, c_state: Optional[torch.Tensor] = None, lstm_first: bool = False,
+                x: Optional[torch.Tensor] = None, recon: Optional[torch.Tensor] = None,
+                heat: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None, what: str = "") -> None:
+    d = nat.ConvDesc()
+    d.src0 = src.data_ptr()
+    d.src1 = nat.ptr(src1)
+    d.c0 = c0 if c0 else w.ctap  # channels read from source 0 (ConvLSTM: the x half of cat[x, h])
+    d.c1 = c1 if src1 is not None else 0
+    d.T0, d.T1, d.t0, d.t1 = T0, T1, t0, t1
+    d.B, d.H, d.W = B, H, W
+    d.ntaps = w.ntaps
+    d.weight = w.w.data_ptr()
+    d.bias = w.bias.data_ptr()
+    d.w_ctap = w.ctap
+    d.n_total = w.n_total
+    d.cout = w.cout
+    d.epilogue = epi
+    d.slope = slope
+    if out is not None:
+        d.out = out.data_ptr() + out_offset_elems * out.element_size()
+    d.out_frame_stride = out_frame_stride
+    d.out_cpitch = out_cpitch
+    d.c_state = nat.ptr(c_state)
+    d.lstm_first = 1 if lstm_first else 0
+    d.x, d.recon, d.heat, d.partials = nat.ptr(x), nat.ptr(recon), nat.ptr(heat), nat.ptr(partials)
+    nat.conv_layer(d, what or "vad_conv_layer")
+
+
+def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
+    nat.check(nat.load().vad_first_conv(x.data_ptr(), w.w.data_ptr(), w.bias.data_ptr(), w.cout, LEAKY,
+                                        1 if pool else 0, B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv")
+
+
+def _conv(w: GemmWeights, src, B, H, W, out, slope, pool=False, what=""):
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    _gemm_layer(w, src, B, H, W, nat.EPI_POOL if pool else nat.EPI_STORE, slope, out,
+                out_frame_stride=Ho * Wo * w.n_total, out_cpitch=w.n_total, what=what)
+
+
+def _convt(w: GemmWeights, src, B, H, W, out, slope, what=""):
+    _gemm_layer(w, src, B, H, W, nat.EPI_CONVT, slope, out, out_frame_stride=4 * H * W * w.cout, out_cpitch=w.cout,
+                what=what)
+
+
+def _check_hw(H: int, W: int) -> None:
+    if H % 16 or W % 16 or H <= 0 or W <= 0:
+        # the reference fails here too (x - recon shape mismatch); fail before launching anything
+        raise RuntimeError(f"input height/width must be positive multiples of 16, got {H}x{W}")
+
+
+def _finalize(partials, frames, tiles_per_frame, H, W, bufs: _Buffers, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    score = torch.empty(frames, dtype=torch.float32, device=device)
+    minmax = torch.empty(frames, 2, dtype=torch.float32, device=device)
+    nat.check(nat.load().vad_score_finalize(partials.data_ptr(), frames, tiles_per_frame, H, W, score.data_ptr(),
+                                            minmax.data_ptr(), nat.stream_ptr()), "vad_score_finalize")
+    return score, minmax
+
+
+class ImageEngine:
+    """ConvAutoencoder forward + fused scoring (reference models/autoencoder.py:181-221)."""
+
+    def __init__(self, packed: Dict[str, object]) -> None:
+        self.p = packed
+        self.bufs = _Buffers()
+
+    def encode(self, x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+        """x fp32 [B,3,H,W] -> latent bf16 NHWC [B,H/16,W/16,latent]."""
+        p, dev = self.p, x.device
+        B, _, H, W = x.shape
+        _check_hw(H, W)
+        g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
+        a = g("e1a", (B, H, W, 32))
+        _first_conv(p["enc1.0"], x, B, H, W, False, a)
+        h, w, cur = H, W, a
+        for blk in ("enc1", "enc2", "enc3", "enc4"):
+            if blk != "enc1":
+                w0: GemmWeights = p[f"{blk}.0"]
+                nxt = g(f"{blk}a", (B, h, w, w0.n_total))
+                _conv(w0, cur, B, h, w, nxt, LEAKY, what=f"{blk}.0")
+                cur = nxt
+            w3: GemmWeights = p[f"{blk}.3"]
+            nxt = g(f"{blk}b", (B, h // 2, w // 2, w3.n_total))
+            _conv(w3, cur, B, h, w, nxt, LEAKY, pool=True, what=f"{blk}.3")
+            cur, h, w = nxt, h // 2, w // 2
+        return cur, h, w
+
+    def latent(self, x: torch.Tensor) -> torch.Tensor:
+        x = _require_cuda_input(x, (4,))
+        z, h, w = self.encode(x)
+        B, C = x.shape[0], z.shape[-1]
+        out = torch.empty(B, C, h, w, dtype=torch.float32, device=x.device)
+        nat.check(nat.load().vad_nhwc_bf16_to_nchw_f32(z.data_ptr(), B, h, w, C, out.data_ptr(), nat.stream_ptr()),
+                  "vad_nhwc_bf16_to_nchw_f32")
+        return out
+
+    def run(self, x: torch.Tensor, want_recon: bool, want_heat: bool) -> ScoreOutputs:
+        x = _require_cuda_input(x, (4,))
+        p, dev = self.p, x.device
+        B, _, H, W = x.shape
+        z, h, w = self.encode(x)
+        g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
+        cur = z
+        for blk in ("dec1", "dec2", "dec3", "dec4"):
+            wt: GemmWeights = p[f"{blk}.0"]
+            up = g(f"{blk}a", (B, 2 * h, 2 * w, wt.cout))
+            _convt(wt, cur, B, h, w, up, RELU, what=f"{blk}.0")
+            h, w, cur = 2 * h, 2 * w, up
+            if blk != "dec4":
+                wc: GemmWeights = p[f"{blk}.3"]
+                nxt = g(f"{blk}b", (B, h, w, wc.n_total))
+                _conv(wc, cur, B, h, w, nxt, RELU, what=f"{blk}.3")
+                cur = nxt
+        tiles = nat.m_tiles(B, H, W, True)
+        partials = self.bufs.get("partials", (tiles, 4), torch.float32, dev)
+        recon = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
+        heat = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_heat else None
+        _gemm_layer(p["dec4.3"], cur, B, H, W, nat.EPI_TANH_SCORE, IDENT, None, x=x, recon=recon, heat=heat,
+                    partials=partials, what="dec4.3+score")
+        score, minmax = _finalize(partials, B, tiles // B, H, W, self.bufs, dev)
+        return ScoreOutputs(score, minmax, heat, recon)
+
+
+class VideoEngine:
+    """VideoAutoencoder forward + fused scoring (reference models/video_autoencoder.py:329-384)."""
+
+    def __init__(self, packed: Dict[str, object]) -> None:
+        self.p = packed
+        self.bufs = _Buffers()
+
+    # ---- pieces (also used by the sub-module wrappers) ---------------------------------------------------------
+    def encode(self, x4: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+        """frames fp32 [F,3,H,W] -> bf16 NHWC [F,H/16,W/16,latent]."""
+        p, dev = self.p, x4.device
+        F, _, H, W = x4.shape
+        _check_hw(H, W)
+        g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
+        cur = g("e0", (F, H // 2, W // 2, 32))
+        _first_conv(p["enc.0"], x4, F, H, W, True, cur)
+        h, w = H // 2, W // 2
+        for i in (4, 8, 12):
+            wt: GemmWeights = p[f"enc.{i}"]
+            nxt = g(f"e{i}", (F, h // 2, w // 2, wt.n_total))
+            _conv(wt, cur, F, h, w, nxt, LEAKY, pool=True, what=f"encoder.{i}")
+            cur, h, w = nxt, h // 2, w // 2
+        return cur, h, w
+
+    def convlstm(self, seq: torch.Tensor, B: int, T: int, h: int, w: int) -> torch.Tensor:
+        """seq bf16 [B,T,h,w,C] -> last layer's hidden sequence bf16 [B,T,h,w,hid] (zero initial state)."""
+        p, dev = self.p, seq.device
+        cur = seq
+        for layer in range(p["lstm_layers"]):
+            wt: GemmWeights = p[f"lstm.{layer}"]
+            hid = wt.cout
+            cin = wt.ctap - hid
+            hseq = self.bufs.get(f"hseq{layer}", (B, T, h, w, hid), torch.bfloat16, dev)
+            cst = self.bufs.get(f"c{layer}", (B, h, w, hid), torch.float32, dev)
+            for t in range(T):
+                first = t == 0
+                _gemm_layer(wt, cur, B, h, w, nat.EPI_LSTM, IDENT, hseq, c0=cin, T0=T, t0=t,
+                            src1=None if first else hseq, c1=0 if first else hid, T1=T, t1=t - 1,
+                            out_frame_stride=T * h * w * hid, out_cpitch=hid, out_offset_elems=t * h * w * hid,
+                            c_state=cst, lstm_first=first, what=f"convlstm.{layer}.t{t}")
+            cur = hseq
+        return cur
+
+    def project(self, seq: torch.Tensor, F: int, h: int, w: int) -> torch.Tensor:
+        if "proj" not in self.p:
+            return seq
+        wt: GemmWeights = self.p["proj"]
+        out = self.bufs.get("proj", (F, h, w, wt.n_total), torch.bfloat16, seq.device)
+        _conv(wt, seq, F, h, w, out, IDENT, what="proj")
+        return out
+
+    def decode_to(self, z: torch.Tensor, F: int, h: int, w: int) -> Tuple[torch.Tensor, int, int]:
+        """bf16 NHWC [F,h,w,latent] -> input of the last ConvT, bf16 NHWC [F,8h,8w,32]."""
+        cur = z
+        for i in (0, 3, 6):
+            wt: GemmWeights = self.p[f"dec.{i}"]
+            up = self.bufs.get(f"d{i}", (F, 2 * h, 2 * w, wt.cout), torch.bfloat16, z.device)
+            _convt(wt, cur, F, h, w, up, RELU, what=f"decoder.{i}")
+            cur, h, w = up, 2 * h, 2 * w
+        return cur, h, w
+
+    def run(self, x: torch.Tensor, want_recon: bool, want_heat: bool) -> ScoreOutputs:
+        x = _require_cuda_input(x, (5,))
+        B, T, Cin, H, W = x.shape
+        F = B * T
+        dev = x.device
+        x4 = x.view(F, Cin, H, W)
+        z, h, w = self.encode(x4)
+        seq = self.convlstm(z.view(B, T, h, w, z.shape[-1]), B, T, h, w)
+        zp = self.project(seq.view(F, h, w, seq.shape[-1]), F, h, w)
+        d, hd, wd = self.decode_to(zp, F, h, w)
+        tiles = nat.m_tiles(F, hd, wd, True)
+        partials = self.bufs.get("partials", (tiles, 4), torch.float32, dev)
+        recon = torch.empty(F, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
+        heat = torch.empty(F, H, W, dtype=torch.float32, device=dev) if want_heat else None
+        _gemm_layer(self.p["dec.9"], d, F, hd, wd, nat.EPI_CONVT_TANH_SCORE, IDENT, None, x=x4, recon=recon,
+                    heat=heat, partials=partials, what="decoder.9+score")
+        score, minmax = _finalize(partials, F, tiles // F, H, W, self.bufs, dev)
+        return ScoreOutputs(score, minmax, heat, recon)

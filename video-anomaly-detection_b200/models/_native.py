@@ -1,0 +1,105 @@
+"""ctypes binding of libvad_b200.so (C ABI declared in include/vad_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_DIR, "libvad_b200.so")
+
+EPI_STORE, EPI_POOL, EPI_CONVT, EPI_LSTM, EPI_TANH_SCORE, EPI_CONVT_TANH_SCORE = range(6)
+
+# every symbol include/vad_b200.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "vad_error_string", "vad_version", "vad_launch_count", "vad_conv_layer", "vad_conv_m_tiles", "vad_first_conv",
+    "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
+    "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8",
+)
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `struct vad_conv_desc` (include/vad_b200.h)."""
+
+    _fields_ = [
+        ("src0", C.c_void_p), ("src1", C.c_void_p),
+        ("c0", C.c_int), ("c1", C.c_int),
+        ("T0", C.c_int), ("T1", C.c_int),
+        ("t0", C.c_int), ("t1", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("ntaps", C.c_int),
+        ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("w_ctap", C.c_int),
+        ("n_total", C.c_int), ("cout", C.c_int), ("epilogue", C.c_int),
+        ("slope", C.c_float),
+        ("out", C.c_void_p), ("out_frame_stride", C.c_longlong), ("out_cpitch", C.c_int),
+        ("c_state", C.c_void_p), ("lstm_first", C.c_int),
+        ("x", C.c_void_p), ("recon", C.c_void_p), ("heat", C.c_void_p), ("partials", C.c_void_p),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the scoring path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.vad_error_string.restype = C.c_char_p
+    lib.vad_error_string.argtypes = [C.c_int]
+    lib.vad_version.restype = C.c_int
+    lib.vad_launch_count.restype = C.c_ulonglong
+    lib.vad_conv_layer.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
+    lib.vad_conv_m_tiles.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.vad_first_conv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_void_p]
+    lib.vad_score_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    lib.vad_score_scratch_bytes.restype = C.c_size_t
+    lib.vad_score_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.vad_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p]
+    lib.vad_nhwc_bf16_to_nchw_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.vad_nchw_f32_to_nhwc_bf16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.vad_heatmap_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vad_error_string(rc).decode()
+        raise RuntimeError(f"libvad_b200: {what} failed with code {rc}: {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(load().vad_launch_count())
+
+
+def conv_layer(desc: ConvDesc, what: str = "vad_conv_layer") -> None:
+    check(load().vad_conv_layer(C.byref(desc), stream_ptr()), what)
+
+
+def m_tiles(B: int, H: int, W: int, single_frame: bool) -> int:
+    n = load().vad_conv_m_tiles(B, H, W, 1 if single_frame else 0)
+    if n <= 0:
+        check(n, "vad_conv_m_tiles")
+    return n

@@ -1,0 +1,168 @@
+"""Host-side weight preparation: fold eval-mode BatchNorm into the preceding conv and repack weights into the
+K-major bf16 GEMM operands libvad_b200 consumes.  Pure torch; runs on CPU or GPU tensors (tests exercise it on CPU).
+
+Arithmetic restated from the reference (Appendix B of SURVEY.md):
+  BatchNorm2d eval: y = (x - mean) / sqrt(var + 1e-5) * gamma + beta       (models/autoencoder.py:40 etc.)
+  Conv2d 3x3 weight [Cout, Cin, 3, 3]; ConvTranspose2d k2 s2 weight [Cin, Cout, 2, 2]
+  ConvLSTM gate conv over cat[x, h]; output chunks i, f, g, o                (models/video_autoencoder.py:64-75)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Mapping, Optional, Tuple
+
+import torch
+
+BN_EPS = 1e-5
+LSTM_CH_PER_TILE = 32  # one 128-column GEMM tile = 4 gates x 32 hidden channels
+
+
+@dataclass
+class GemmWeights:
+    """One layer's B operand: `w` bf16 [n_total, ntaps * ctap] (K-major), `bias` fp32 [n_total]."""
+    w: torch.Tensor
+    bias: torch.Tensor
+    ntaps: int
+    ctap: int      # input channels per tap (weight columns per tap)
+    n_total: int
+    cout: int      # real output channels
+
+
+@dataclass
+class FirstConvWeights:
+    """3-channel first conv: `w` fp32 [27, cout] with k = (ky*3+kx)*3+ci, `bias` fp32 [cout]."""
+    w: torch.Tensor
+    bias: torch.Tensor
+    cout: int
+
+
+def bn_scale_shift(sd: Mapping[str, torch.Tensor], bn: Optional[str], cout: int, ref: torch.Tensor
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-channel (scale, shift) of an eval-mode BatchNorm; identity when `bn` is None."""
+    if bn is None:
+        return torch.ones(cout, dtype=torch.float64, device=ref.device), torch.zeros(cout, dtype=torch.float64,
+                                                                                     device=ref.device)
+    g = sd[bn + ".weight"].double()
+    b = sd[bn + ".bias"].double()
+    m = sd[bn + ".running_mean"].double()
+    v = sd[bn + ".running_var"].double()
+    s = g / torch.sqrt(v + BN_EPS)
+    return s, b - m * s
+
+
+def fold_conv(sd: Mapping[str, torch.Tensor], conv: str, bn: Optional[str]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Conv2d [Cout,Cin,kh,kw] followed by eval BN -> (weight', bias') in fp64."""
+    w = sd[conv + ".weight"].double()
+    b = sd[conv + ".bias"].double()
+    s, t = bn_scale_shift(sd, bn, w.shape[0], w)
+    return w * s.view(-1, 1, 1, 1), b * s + t
+
+
+def fold_convt(sd: Mapping[str, torch.Tensor], conv: str, bn: Optional[str]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ConvTranspose2d [Cin,Cout,2,2] followed by eval BN -> (weight', bias') in fp64."""
+    w = sd[conv + ".weight"].double()
+    b = sd[conv + ".bias"].double()
+    s, t = bn_scale_shift(sd, bn, w.shape[1], w)
+    return w * s.view(1, -1, 1, 1), b * s + t
+
+
+def pack_conv3x3(w: torch.Tensor, b: torch.Tensor, pad_n_to: int = 0) -> GemmWeights:
+    """[Cout,Cin,3,3] -> [Cout, 9*Cin] with K = (ky*3+kx)*Cin + ci; optional zero rows up to `pad_n_to`."""
+    cout, cin = w.shape[0], w.shape[1]
+    wk = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    n_total = max(cout, pad_n_to)
+    if n_total > cout:
+        wk = torch.cat([wk, wk.new_zeros(n_total - cout, 9 * cin)], 0)
+        b = torch.cat([b, b.new_zeros(n_total - cout)], 0)
+    return GemmWeights(wk.to(torch.bfloat16).contiguous(), b.float().contiguous(), 9, cin, n_total, cout)
+
+
+def pack_conv1x1(w: torch.Tensor, b: torch.Tensor) -> GemmWeights:
+    cout, cin = w.shape[0], w.shape[1]
+    return GemmWeights(w.reshape(cout, cin).to(torch.bfloat16).contiguous(), b.float().contiguous(), 1, cin, cout, cout)
+
+
+def pack_convt2x2(w: torch.Tensor, b: torch.Tensor, pad_n_to: int = 0) -> GemmWeights:
+    """[Cin,Cout,2,2] -> [4*Cout, Cin], row n = (di*2+dj)*Cout + co; bias repeated per (di,dj)."""
+    cin, cout = w.shape[0], w.shape[1]
+    wk = w.permute(2, 3, 1, 0).reshape(4 * cout, cin)
+    bk = b.repeat(4)
+    n_total = max(4 * cout, pad_n_to)
+    if n_total > 4 * cout:
+        wk = torch.cat([wk, wk.new_zeros(n_total - 4 * cout, cin)], 0)
+        bk = torch.cat([bk, bk.new_zeros(n_total - 4 * cout)], 0)
+    return GemmWeights(wk.to(torch.bfloat16).contiguous(), bk.float().contiguous(), 1, cin, n_total, cout)
+
+
+def lstm_row_permutation(hid: int, device=None) -> torch.Tensor:
+    """new GEMM row -> original gate-conv output channel.
+
+    Original rows: gate*hid + j (gate order i,f,g,o — models/video_autoencoder.py:75).  New rows: tiles of 128 =
+    [gate][32 channels] so that one accumulator row holds all four gates of the same hidden channels."""
+    if hid % LSTM_CH_PER_TILE != 0:
+        raise ValueError(f"lstm hidden dim {hid} must be a multiple of {LSTM_CH_PER_TILE}")
+    n = torch.arange(4 * hid, device=device)
+    tile, within = n // 128, n % 128
+    gate, jj = within // LSTM_CH_PER_TILE, within % LSTM_CH_PER_TILE
+    return gate * hid + tile * LSTM_CH_PER_TILE + jj
+
+
+def pack_lstm(w: torch.Tensor, b: torch.Tensor, hid: int) -> GemmWeights:
+    """Gate conv [4*hid, in+hid, 3, 3] -> row-permuted [4*hid, 9*(in+hid)]."""
+    perm = lstm_row_permutation(hid, w.device)
+    g = pack_conv3x3(w[perm], b[perm])
+    g.cout = hid
+    return g
+
+
+def pack_first_conv(w: torch.Tensor, b: torch.Tensor) -> FirstConvWeights:
+    cout = w.shape[0]
+    wk = w.permute(2, 3, 1, 0).reshape(27, cout)  # [ky,kx,ci,co]
+    return FirstConvWeights(wk.float().contiguous(), b.float().contiguous(), cout)
+
+
+def prepare_image(sd: Mapping[str, torch.Tensor]) -> Dict[str, object]:
+    """ConvAutoencoder state_dict (SURVEY Appendix D keys) -> packed layers, in execution order."""
+    out: Dict[str, object] = {}
+    out["enc1.0"] = pack_first_conv(*fold_conv(sd, "encoder.enc1.0", "encoder.enc1.1"))
+    out["enc1.3"] = pack_conv3x3(*fold_conv(sd, "encoder.enc1.3", "encoder.enc1.4"))
+    for blk in ("enc2", "enc3", "enc4"):
+        out[f"{blk}.0"] = pack_conv3x3(*fold_conv(sd, f"encoder.{blk}.0", f"encoder.{blk}.1"))
+        out[f"{blk}.3"] = pack_conv3x3(*fold_conv(sd, f"encoder.{blk}.3", f"encoder.{blk}.4"))
+    for blk in ("dec1", "dec2", "dec3"):
+        out[f"{blk}.0"] = pack_convt2x2(*fold_convt(sd, f"decoder.{blk}.0", f"decoder.{blk}.1"))
+        out[f"{blk}.3"] = pack_conv3x3(*fold_conv(sd, f"decoder.{blk}.3", f"decoder.{blk}.4"))
+    out["dec4.0"] = pack_convt2x2(*fold_convt(sd, "decoder.dec4.0", "decoder.dec4.1"))
+    out["dec4.3"] = pack_conv3x3(*fold_conv(sd, "decoder.dec4.3", None), pad_n_to=16)
+    return out
+
+
+def prepare_video(sd: Mapping[str, torch.Tensor]) -> Dict[str, object]:
+    """VideoAutoencoder state_dict -> packed layers."""
+    out: Dict[str, object] = {}
+    out["enc.0"] = pack_first_conv(*fold_conv(sd, "encoder.encoder.0", "encoder.encoder.1"))
+    for i in (4, 8, 12):
+        out[f"enc.{i}"] = pack_conv3x3(*fold_conv(sd, f"encoder.encoder.{i}", f"encoder.encoder.{i + 1}"))
+    layer = 0
+    while f"convlstm.cells.{layer}.conv.weight" in sd:
+        w = sd[f"convlstm.cells.{layer}.conv.weight"].double()
+        b = sd[f"convlstm.cells.{layer}.conv.bias"].double()
+        out[f"lstm.{layer}"] = pack_lstm(w, b, w.shape[0] // 4)
+        layer += 1
+    out["lstm_layers"] = layer
+    if "proj.weight" in sd:
+        out["proj"] = pack_conv1x1(sd["proj.weight"].double(), sd["proj.bias"].double())
+    for i in (0, 3, 6):
+        out[f"dec.{i}"] = pack_convt2x2(*fold_convt(sd, f"decoder.decoder.{i}", f"decoder.decoder.{i + 1}"))
+    out["dec.9"] = pack_convt2x2(*fold_convt(sd, "decoder.decoder.9", None), pad_n_to=16)
+    return out
+
+
+def to_device(packed: Dict[str, object], device) -> Dict[str, object]:
+    res: Dict[str, object] = {}
+    for k, v in packed.items():
+        if isinstance(v, (GemmWeights, FirstConvWeights)):
+            v.w = v.w.to(device)
+            v.bias = v.bias.to(device)
+        res[k] = v
+    return res
