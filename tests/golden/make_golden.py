@@ -94,7 +94,7 @@ def main():
     loader = torch.utils.data.DataLoader(ds, batch_size=32, shuffle=False)
     torch.manual_seed(0)
     m = ConvAutoencoder().eval()
-    auroc, scores, labels, _types = evaluate.compute_auroc(m, loader, torch.device("cpu"))
+    auroc, labels, scores, _types = evaluate.compute_auroc(m, loader, torch.device("cpu"))  # evaluate.py:91
     imgs = torch.stack([ds[i]["image"] for i in range(len(ds))])
     # store the dataset as uint8 (it was decoded from 8-bit PNGs: x = (u8/255 - 0.5)/0.5 exactly)
     u8 = torch.round((imgs * 0.5 + 0.5) * 255).to(torch.uint8)

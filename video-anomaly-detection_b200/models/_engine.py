@@ -16,6 +16,20 @@ from ._prepare import FirstConvWeights, GemmWeights
 
 LEAKY, RELU, IDENT = 0.2, 0.0, 1.0
 
+# bench.py sets this to a list to get (layer name, start event, end event) for every kernel launch
+PROFILE: Optional[list] = None
+
+
+def _timed(what: str, fn) -> None:
+    if PROFILE is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((what, e0, e1))
+
 
 @dataclass
 class ScoreOutputs:
@@ -79,12 +93,13 @@ def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: 
     d.c_state = nat.ptr(c_state)
     d.lstm_first = 1 if lstm_first else 0
     d.x, d.recon, d.heat, d.partials = nat.ptr(x), nat.ptr(recon), nat.ptr(heat), nat.ptr(partials)
-    nat.conv_layer(d, what or "vad_conv_layer")
+    _timed(what or "vad_conv_layer", lambda: nat.conv_layer(d, what or "vad_conv_layer"))
 
 
 def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
-    nat.check(nat.load().vad_first_conv(x.data_ptr(), w.w.data_ptr(), w.bias.data_ptr(), w.cout, LEAKY,
-                                        1 if pool else 0, B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv")
+    _timed("first_conv", lambda: nat.check(
+        nat.load().vad_first_conv(x.data_ptr(), w.w.data_ptr(), w.bias.data_ptr(), w.cout, LEAKY, 1 if pool else 0,
+                                  B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv"))
 
 
 def _conv(w: GemmWeights, src, B, H, W, out, slope, pool=False, what=""):
