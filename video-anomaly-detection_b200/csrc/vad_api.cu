@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "vad_internal.h"
@@ -86,6 +87,45 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VAD_OK : VAD_ERR_DRIVER;
+}
+
+// generic bf16 5-D map whose innermost box extent is one swizzle span (64 ch -> 128B swizzle, 32 ch -> 64B)
+static int encode_map5(CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                       const cuuint32_t* box, int inner_channels) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return VAD_ERR_DRIVER;
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  inner_channels == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VAD_OK : VAD_ERR_DRIVER;
+}
+
+static int encode_act_map_box(CUtensorMap* m, const void* base, int C, int W, int H, int T, int B, int CK, int box_w,
+                              int box_h, int box_n) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)T * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)CK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u, (cuuint32_t)box_n};
+  return encode_map5(m, base, dims, strides, box, CK);
+}
+
+// Tuning / bring-up switches (environment, read once):
+//   VAD_HALO = 0 off | 1 one (TW+2)-wide patch, descriptor base offset 0 | 2 same, base offset (addr>>7)&7 |
+//              3 three TW-wide patches shifted by dx (only whole-row descriptor shifts)
+//   VAD_TMA_STORE = 0 direct epilogue stores | 1 staged TMA stores
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+static int halo_mode_setting() {
+  static int v = env_int("VAD_HALO", 1);
+  return v;
+}
+static int tma_store_setting() {
+  static int v = env_int("VAD_TMA_STORE", 1);
+  return v;
 }
 
 static int encode_weight_map(CUtensorMap* m, const void* base, int K, int N, int CK, int BN) {
@@ -381,10 +421,57 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
       return VAD_ERR_ARG;
   }
 
+  if (d->n_total > 512) return VAD_ERR_SHAPE;  // bias slab in shared memory
+
   ConvArgs a;
   std::memset(&a, 0, sizeof(a));
-  const TileGeom g = pick_tile_geometry(d->B, d->H, d->W, is_score);
-  int rc = encode_act_map(&a.mapA0, d->src0, d->c0, d->W, d->H, d->T0 > 0 ? d->T0 : 1, d->B, CK, g);
+  TileGeom g = pick_tile_geometry(d->B, d->H, d->W, is_score);
+
+  // ---- halo kernel: 3x3 conv, one source of 32/64 channels, all of N in one tile, frames of at least one tile
+  const int halo_mode = halo_mode_setting();
+  bool use_halo = halo_mode != 0 && d->ntaps == 9 && d->c1 == 0 && (d->c0 == 32 || d->c0 == 64) &&
+                  d->n_total == BN && (d->T0 <= 1) && d->H >= 16 && d->W >= 16 &&
+                  (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_TANH_SCORE);
+  int halo_box_w = 0, halo_box_h = 0;
+  if (use_halo) {
+    const bool three = (halo_mode == 3);
+    g.lgTW = three ? 4 : 3;
+    g.lgTH = three ? 3 : 4;
+    g.lgTN = 0;
+    g.tiles_w = (d->W + (1 << g.lgTW) - 1) >> g.lgTW;
+    g.tiles_h = (d->H + (1 << g.lgTH) - 1) >> g.lgTH;
+    g.tiles_b = d->B;
+    const int TW = 1 << g.lgTW, TH = 1 << g.lgTH;
+    a.halo_npatch = three ? 3 : 1;
+    a.halo_pw = halo_box_w = three ? TW : TW + 2;
+    a.halo_ph = halo_box_h = TH + 2;
+    a.halo_patch_bytes = (a.halo_pw * a.halo_ph * CK * 2 + 1023) / 1024 * 1024;
+    a.halo_sbo_rows = three ? 8 : a.halo_pw;
+    a.halo_base_mode = (halo_mode == 2) ? 1 : 0;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      a.tap_patch[tap] = three ? kx : 0;
+      a.tap_row[tap] = three ? ky * a.halo_pw : ky * a.halo_pw + kx;
+    }
+    const int per_stage = a.halo_patch_bytes * a.halo_npatch;
+    int stages = 8;
+    while (stages >= 2 && halo_smem_bytes(CK, BN, epi, per_stage, stages) > 227 * 1024 - 4096) --stages;
+    if (stages < 2 || halo_smem_bytes(CK, BN, epi, per_stage, stages) == 0) {
+      use_halo = false;
+      g = pick_tile_geometry(d->B, d->H, d->W, is_score);
+    } else {
+      a.halo_stages = stages;
+    }
+  }
+
+  int rc;
+  if (use_halo) {
+    TileGeom box = g;  // box {CK, PW, PH, 1, 1}: PW/PH need not be powers of two
+    rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, CK, halo_box_w, halo_box_h, 1);
+    (void)box;
+  } else {
+    rc = encode_act_map(&a.mapA0, d->src0, d->c0, d->W, d->H, d->T0 > 0 ? d->T0 : 1, d->B, CK, g);
+  }
   if (rc != VAD_OK) return rc;
   if (d->c1 > 0) {
     rc = encode_act_map(&a.mapA1, d->src1, d->c1, d->W, d->H, d->T1 > 0 ? d->T1 : 1, d->B, CK, g);
@@ -415,7 +502,52 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
   a.c_state = d->c_state;
   a.lstm_first = d->lstm_first;
   a.x = d->x; a.recon = d->recon; a.heat = d->heat; a.partials = d->partials;
+
+  // ---- output tensor map: the epilogue stages each bf16 chunk in swizzled smem and TMA-stores it
+  if (tma_store_setting() && (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_CONVT || epi == VAD_EPI_LSTM)) {
+    const int TW = 1 << g.lgTW, TH = 1 << g.lgTH, TN = 1 << g.lgTN;
+    const long long cp = d->out_cpitch;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d->out) % 16 == 0) && cp % 8 == 0 && d->out_frame_stride % 8 == 0;
+    if (aligned && epi == VAD_EPI_STORE) {
+      a.out_chunk = (BN % 64 == 0) ? 64 : 32;
+      cuuint64_t dims[5] = {(cuuint64_t)d->n_total, (cuuint64_t)d->W, (cuuint64_t)d->H, 1, (cuuint64_t)d->B};
+      cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)d->W * cp * 2, (cuuint64_t)d->H * d->W * cp * 2,
+                          (cuuint64_t)d->out_frame_stride * 2};
+      cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
+      a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK;
+    } else if (aligned && epi == VAD_EPI_LSTM) {
+      a.out_chunk = 32;
+      cuuint64_t dims[5] = {(cuuint64_t)d->cout, (cuuint64_t)d->W, (cuuint64_t)d->H, 1, (cuuint64_t)d->B};
+      cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)d->W * cp * 2, (cuuint64_t)d->H * d->W * cp * 2,
+                          (cuuint64_t)d->out_frame_stride * 2};
+      cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
+      a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, 32) == VAD_OK;
+    } else if (aligned && epi == VAD_EPI_POOL && TW >= 2 && TH >= 2) {
+      a.out_chunk = (BN % 64 == 0) ? 64 : 32;
+      const int Wo = d->W / 2, Ho = d->H / 2;
+      cuuint64_t dims[5] = {(cuuint64_t)d->n_total, (cuuint64_t)Wo, (cuuint64_t)Ho, 1, (cuuint64_t)d->B};
+      cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)Wo * cp * 2, (cuuint64_t)Ho * Wo * cp * 2,
+                          (cuuint64_t)d->out_frame_stride * 2};
+      cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, (cuuint32_t)(TW / 2), (cuuint32_t)(TH / 2), 1, (cuuint32_t)TN};
+      a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK;
+    } else if (aligned && epi == VAD_EPI_CONVT) {
+      // pixel shuffle as a 5-D map {co, dj, w, di, b*H + h}; needs dense frames and tiles whose rows are
+      // consecutive in the merged (b, h) dimension
+      const bool dense = d->out_frame_stride == 4LL * d->H * d->W * cp;
+      const bool rows_ok = (TN == 1 && d->H % TH == 0) || (TN > 1 && TH == d->H);
+      if (dense && rows_ok) {
+        a.out_chunk = (d->cout % 64 == 0) ? 64 : 32;
+        cuuint64_t dims[5] = {(cuuint64_t)d->cout, 2, (cuuint64_t)d->W, 2, (cuuint64_t)d->B * d->H};
+        cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)2 * cp * 2, (cuuint64_t)2 * d->W * cp * 2,
+                            (cuuint64_t)4 * d->W * cp * 2};
+        cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, 1, (cuuint32_t)TW, 1, (cuuint32_t)(TH * TN)};
+        a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK;
+      }
+    }
+  }
+
   const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  if (use_halo) return launch_conv_halo(CK, BN, epi, a, grid, stream);
   return launch_conv_umma(CK, BN, epi, a, grid, stream);
 }
 

@@ -1,12 +1,18 @@
-// Implicit-GEMM convolution / transposed convolution / ConvLSTM gate kernel for sm_100a.
+// Implicit-GEMM convolution / transposed convolution / ConvLSTM gate kernels for sm_100a.
 //
 //   D[128 pixels, BN] (fp32, TMEM)  +=  A[128 pixels, CK channels of one tap] (bf16, smem via TMA, 5-D tiled map
 //                                        over [B][T][H][W][C] with out-of-bounds zero fill = conv padding)
 //                                     x  B[BN, CK] (bf16, smem via TMA, weights K-major)
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM -> registers -> fused bias/activation/pool/pixel-shuffle/LSTM/score -> HBM).
-// Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+// Two kernels share one epilogue:
+//   conv_umma_kernel  — "streaming": one (A tile, B tile) pair per tap and channel chunk through an mbarrier ring.
+//                       Used for wide layers (tensor-bound), 1-tap GEMMs (ConvT / 1x1) and the ConvLSTM gates.
+//   conv_halo_kernel  — 3x3 conv with Cin in {32, 64} and small N: the nine weight slabs stay resident in smem for
+//                       the whole (persistent) CTA and each tile loads ONE input patch with a 1-pixel halo that all
+//                       nine taps read through shifted shared-memory descriptors — 1.4x instead of 9x operand traffic.
+// Both are persistent and warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/activation/pool/pixel-shuffle/LSTM/score -> swizzled smem
+// -> TMA store).  Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Replaces (reference file:line): nn.Conv2d 3x3 models/autoencoder.py:39-76,107-137; nn.ConvTranspose2d k2 s2
 // models/autoencoder.py:104-134 and models/video_autoencoder.py:244-259; ConvLSTMCell.forward
@@ -21,20 +27,33 @@ constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr int kTileM = 128;
 constexpr int kAccStages = 2;
+constexpr int kStagingBuf = 16384;  // one staged output chunk: 128 rows x 128 B
+constexpr int kMaxBias = 512;
+constexpr int kSmemBudget = 227 * 1024 - 4096;  // dynamic smem we allow ourselves (static smem + slack kept free)
 
-template <int CK, int BN>
+__host__ __device__ constexpr bool epi_uses_staging(int epi) {
+  return epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_CONVT || epi == VAD_EPI_LSTM;
+}
+__host__ __device__ constexpr int staging_bufs(int bn, int epi) {
+  return !epi_uses_staging(epi) ? 0 : (bn >= 256 ? 1 : 2);
+}
+__host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
+  return (2 * bn <= 32) ? 32u : (2 * bn <= 64) ? 64u : (2 * bn <= 128) ? 128u : (2 * bn <= 256) ? 256u : 512u;
+}
+
+template <int CK, int BN, int EPI>
 struct Cfg {
-  static constexpr int kRowBytes = CK * 2;               // one swizzle span per row: 128 B or 64 B
-  static constexpr int kABytes = kTileM * kRowBytes;     // 16 KB / 8 KB
-  static constexpr int kBBytes = BN * kRowBytes;         // multiple of 1024 for BN >= 16
+  static constexpr int kRowBytes = CK * 2;            // one swizzle span per row: 128 B or 64 B
+  static constexpr int kABytes = kTileM * kRowBytes;  // 16 KB / 8 KB
+  static constexpr int kBBytes = BN * kRowBytes;      // multiple of 1024 for BN >= 16
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
+  static constexpr int kStagingBytes = staging_bufs(BN, EPI) * kStagingBuf;
+  static constexpr int kStagesRaw = (kSmemBudget - 1024 - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // +1024 alignment slack
-  static constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;        // SWIZZLE_128B : SWIZZLE_64B
-  static constexpr uint32_t kSBO = 8 * kRowBytes;                  // bytes between 8-row groups
-  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                        : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024;  // +1024 alignment slack
+  static constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;                        // SWIZZLE_128B : SWIZZLE_64B
+  static constexpr uint32_t kSBO = 8 * kRowBytes;                                  // bytes between 8-row groups
+  static constexpr uint32_t kTmemCols = tmem_cols_for(BN);
   static_assert(CK == 64 || CK == 32, "K chunk must be one 128B or 64B swizzle span");
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
   static_assert(kStages >= 2, "pipeline too shallow");
@@ -64,9 +83,316 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile, in
 __device__ __forceinline__ float act_fn(float v, float slope) { return v > 0.f ? v : v * slope; }
 __device__ __forceinline__ float sigmoid_fn(float v) { return 1.f / (1.f + __expf(-v)); }
 
+// Byte offset of 16-byte chunk `c16` of row `row` in a staged tile whose rows are one swizzle span wide.
+__device__ __forceinline__ uint32_t staged_off(int row, int c16, int out_chunk) {
+  return out_chunk == 64 ? static_cast<uint32_t>(row * 128 + ((c16 ^ (row & 7)) << 4))
+                         : static_cast<uint32_t>(row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------------- epilogue
+// Runs on the four epilogue warps for one finished accumulator tile.  `stg_i` counts staged chunks (ring index).
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& t, uint32_t tacc, int q, int lane,
+                                              uint8_t* stg, const float* s_bias, float (*red_smem)[3], int& stg_i) {
+  const int r = q * 32 + lane;  // accumulator row = pixel slot in the tile
+  const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
+  const int ww = r & (TW - 1);
+  const int hh = (r >> a.lgTW) & (TH - 1);
+  const int bb = r >> (a.lgTW + a.lgTH);
+  const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);
+  const int fb = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
+  const bool valid = (r < rows_valid) && (fb < a.B) && (h < a.H) && (w < a.W);
+  const bool leader = (q == 0 && lane == 0);
+  constexpr int kBufs = staging_bufs(BN, EPI);
+
+  if constexpr (EPI == VAD_EPI_STORE || EPI == VAD_EPI_POOL || EPI == VAD_EPI_CONVT) {
+    if (a.tma_store) {
+      const int OC = a.out_chunk;
+      const int n_chunks = BN / OC;
+#pragma unroll 1
+      for (int oc = 0; oc < n_chunks; ++oc) {
+        uint8_t* buf = stg + (kBufs > 1 ? (stg_i & 1) : 0) * kStagingBuf;
+        if (leader) {  // the TMA store that last read this buffer must have finished reading it
+          if (kBufs > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+        }
+        named_bar_sync(1, 128);
+#pragma unroll 1
+        for (int sub = 0; sub < OC / 32; ++sub) {
+          const int lc = oc * OC + sub * 32;
+          uint32_t v[32];
+          tmem_ld_x32(tacc + lc, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if constexpr (EPI == VAD_EPI_POOL) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], TW));
+            }
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc);
+          uint32_t p[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = b4[j];
+            p[2 * j] = pack_bf16x2(act_fn(f[4 * j] + bv.x, a.slope), act_fn(f[4 * j + 1] + bv.y, a.slope));
+            p[2 * j + 1] = pack_bf16x2(act_fn(f[4 * j + 2] + bv.z, a.slope), act_fn(f[4 * j + 3] + bv.w, a.slope));
+          }
+          if constexpr (EPI == VAD_EPI_POOL) {
+            // the 4 lanes of a 2x2 window hold the same max; each writes one quarter (8 channels) of the pooled row
+            const int part = (ww & 1) | ((hh & 1) << 1);
+            const int prow = ((bb << (a.lgTH - 1)) + (hh >> 1)) * (TW >> 1) + (ww >> 1);
+            uint4 val;
+            if (part == 0) val = make_uint4(p[0], p[1], p[2], p[3]);
+            else if (part == 1) val = make_uint4(p[4], p[5], p[6], p[7]);
+            else if (part == 2) val = make_uint4(p[8], p[9], p[10], p[11]);
+            else val = make_uint4(p[12], p[13], p[14], p[15]);
+            *reinterpret_cast<uint4*>(buf + staged_off(prow, sub * 4 + part, OC)) = val;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(buf + staged_off(r, sub * 4 + j, OC)) =
+                  make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (leader) {
+          const int col = t.n0 + oc * OC;
+          if constexpr (EPI == VAD_EPI_STORE) {
+            tma_store_5d(&a.mapOut, buf, col, t.w0, t.h0, 0, t.b0);
+          } else if constexpr (EPI == VAD_EPI_POOL) {
+            tma_store_5d(&a.mapOut, buf, col, t.w0 >> 1, t.h0 >> 1, 0, t.b0);
+          } else {  // ConvT pixel shuffle: map dims {co, dj, w, di, b*H + h}
+            const int quad = col / a.cout;
+            tma_store_5d(&a.mapOut, buf, col - quad * a.cout, quad & 1, t.w0, quad >> 1, t.b0 * a.H + t.h0);
+          }
+          bulk_commit_group();
+        }
+        ++stg_i;
+      }
+    } else {
+      // direct stores (fallback for tile shapes the output tensor map cannot express)
+      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tacc + c * 32, v);
+        tmem_ld_wait();
+        const int col = t.n0 + c * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if constexpr (EPI == VAD_EPI_POOL) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], TW));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fn(f[j] + s_bias[col + j], a.slope);
+        uint32_t p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        if constexpr (EPI == VAD_EPI_STORE) {
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(outp + fb * a.out_fs +
+                                                  (static_cast<long long>(h) * a.W + w) * a.out_cp + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+          }
+        } else if constexpr (EPI == VAD_EPI_POOL) {
+          if (valid) {
+            const int part = (ww & 1) | ((hh & 1) << 1);
+            uint4* dst = reinterpret_cast<uint4*>(
+                outp + fb * a.out_fs + (static_cast<long long>(h >> 1) * (a.W >> 1) + (w >> 1)) * a.out_cp + col +
+                part * 8);
+            uint4 val;
+            if (part == 0) val = make_uint4(p[0], p[1], p[2], p[3]);
+            else if (part == 1) val = make_uint4(p[4], p[5], p[6], p[7]);
+            else if (part == 2) val = make_uint4(p[8], p[9], p[10], p[11]);
+            else val = make_uint4(p[12], p[13], p[14], p[15]);
+            *dst = val;
+          }
+        } else {  // VAD_EPI_CONVT: column = quad*cout + co, quad = di*2 + dj
+          if (valid) {
+            const int quad = col / a.cout;
+            const int co = col - quad * a.cout;
+            const int ho = 2 * h + (quad >> 1), wo = 2 * w + (quad & 1);
+            uint4* dst = reinterpret_cast<uint4*>(outp + fb * a.out_fs +
+                                                  (static_cast<long long>(ho) * (2 * a.W) + wo) * a.out_cp + co);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+          }
+        }
+      }
+    }
+  } else if constexpr (EPI == VAD_EPI_LSTM) {
+    // columns of this tile: [gate g in i,f,g,o][32 hidden channels j0..j0+31]; weights/bias pre-permuted on host
+    static_assert(EPI != VAD_EPI_LSTM || BN == 128, "LSTM tile is 4 gates x 32 channels");
+    const int hid = a.cout;
+    const int j0 = (t.n0 >> 7) * 32;
+    const long long pix = (static_cast<long long>(fb) * a.H + h) * a.W + w;
+    float* cptr = a.c_state + pix * hid + j0;
+    uint8_t* buf = stg + (stg_i & 1) * kStagingBuf;
+    if (a.tma_store) {
+      if (leader) bulk_wait_group_read<1>();
+      named_bar_sync(1, 128);
+    }
+    __nv_bfloat16* hptr = reinterpret_cast<__nv_bfloat16*>(a.out) + fb * a.out_fs +
+                          (static_cast<long long>(h) * a.W + w) * a.out_cp + j0;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      uint32_t gi[8], gf[8], gg[8], go[8];
+      tmem_ld_x8(tacc + 0 + s * 8, gi);
+      tmem_ld_x8(tacc + 32 + s * 8, gf);
+      tmem_ld_x8(tacc + 64 + s * 8, gg);
+      tmem_ld_x8(tacc + 96 + s * 8, go);
+      tmem_ld_wait();
+      float cprev[8];
+      if (valid && !a.lstm_first) {
+        const float4 c0 = *reinterpret_cast<const float4*>(cptr + s * 8);
+        const float4 c1 = *reinterpret_cast<const float4*>(cptr + s * 8 + 4);
+        cprev[0] = c0.x; cprev[1] = c0.y; cprev[2] = c0.z; cprev[3] = c0.w;
+        cprev[4] = c1.x; cprev[5] = c1.y; cprev[6] = c1.z; cprev[7] = c1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cprev[e] = 0.f;
+      }
+      float cn[8], hn[8];
+      const float* bp = s_bias + t.n0 + s * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xi = __uint_as_float(gi[e]) + bp[e];
+        const float xf = __uint_as_float(gf[e]) + bp[32 + e];
+        const float xg = __uint_as_float(gg[e]) + bp[64 + e];
+        const float xo = __uint_as_float(go[e]) + bp[96 + e];
+        cn[e] = sigmoid_fn(xf) * cprev[e] + sigmoid_fn(xi) * tanhf(xg);
+        hn[e] = sigmoid_fn(xo) * tanhf(cn[e]);
+      }
+      const uint4 hv = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
+                                  pack_bf16x2(hn[6], hn[7]));
+      if (valid) {
+        *reinterpret_cast<float4*>(cptr + s * 8) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(cptr + s * 8 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        if (!a.tma_store) *reinterpret_cast<uint4*>(hptr + s * 8) = hv;
+      }
+      if (a.tma_store) *reinterpret_cast<uint4*>(buf + staged_off(r, s, 32)) = hv;
+    }
+    if (a.tma_store) {
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (leader) {
+        tma_store_5d(&a.mapOut, buf, j0, t.w0, t.h0, 0, t.b0);
+        bulk_commit_group();
+      }
+      ++stg_i;
+    }
+  } else {
+    // ------------------------------------------------ fused tanh + reconstruction-error reduction (N tile = 16)
+    static_assert((EPI != VAD_EPI_TANH_SCORE && EPI != VAD_EPI_CONVT_TANH_SCORE) || BN == 16, "score tile is 16 wide");
+    uint32_t v[16];
+    tmem_ld_x16(tacc, v);
+    tmem_ld_wait();
+    float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
+    if constexpr (EPI == VAD_EPI_TANH_SCORE) {
+      if (valid) {
+        const long long plane = static_cast<long long>(a.H) * a.W;
+        const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(h) * a.W + w;
+        float sq = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float rec = tanhf(__uint_as_float(v[ch]) + s_bias[ch]);
+          const float d = __ldg(a.x + off + ch * plane) - rec;
+          sq += d * d;
+          if (a.recon) a.recon[off + ch * plane] = rec;
+        }
+        if (a.heat) a.heat[static_cast<long long>(fb) * plane + static_cast<long long>(h) * a.W + w] = sq * (1.f / 3.f);
+        ssum = sq; smin = sq; smax = sq;
+      }
+    } else {
+      if (valid) {
+        const int Ho = 2 * a.H, Wo = 2 * a.W;
+        const long long plane = static_cast<long long>(Ho) * Wo;
+#pragma unroll
+        for (int di = 0; di < 2; ++di) {
+          const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(2 * h + di) * Wo + 2 * w;
+          float sq0 = 0.f, sq1 = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const float r0 = tanhf(__uint_as_float(v[(di * 2 + 0) * 3 + ch]) + s_bias[(di * 2 + 0) * 3 + ch]);
+            const float r1 = tanhf(__uint_as_float(v[(di * 2 + 1) * 3 + ch]) + s_bias[(di * 2 + 1) * 3 + ch]);
+            const float2 xv = __ldg(reinterpret_cast<const float2*>(a.x + off + ch * plane));
+            const float d0 = xv.x - r0, d1 = xv.y - r1;
+            sq0 += d0 * d0;
+            sq1 += d1 * d1;
+            if (a.recon) *reinterpret_cast<float2*>(a.recon + off + ch * plane) = make_float2(r0, r1);
+          }
+          if (a.heat)
+            *reinterpret_cast<float2*>(a.heat + static_cast<long long>(fb) * plane +
+                                       static_cast<long long>(2 * h + di) * Wo + 2 * w) =
+                make_float2(sq0 * (1.f / 3.f), sq1 * (1.f / 3.f));
+          ssum += sq0 + sq1;
+          smin = fminf(smin, fminf(sq0, sq1));
+          smax = fmaxf(smax, fmaxf(sq0, sq1));
+        }
+      }
+    }
+    // tile reduction in a fixed order (deterministic): lanes -> warps -> one writer
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+      smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+      smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    }
+    if (lane == 0) { red_smem[q][0] = ssum; red_smem[q][1] = smin; red_smem[q][2] = smax; }
+    named_bar_sync(1, 128);
+    if (leader) {
+      const float s = (red_smem[0][0] + red_smem[1][0]) + (red_smem[2][0] + red_smem[3][0]);
+      const float mn = fminf(fminf(red_smem[0][1], red_smem[1][1]), fminf(red_smem[2][1], red_smem[3][1]));
+      const float mx = fmaxf(fmaxf(red_smem[0][2], red_smem[1][2]), fmaxf(red_smem[2][2], red_smem[3][2]));
+      *reinterpret_cast<float4*>(a.partials + static_cast<long long>(t.m_tile) * 4) =
+          make_float4(s, mn * (1.f / 3.f), mx * (1.f / 3.f), 0.f);
+    }
+    named_bar_sync(1, 128);  // red_smem is reused by the next tile
+  }
+}
+
+// Shared body of the epilogue warps: loop over this CTA's tiles.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_base, int warp, int lane, uint8_t* stg,
+                                              const float* s_bias, float (*red_smem)[3], uint64_t* acc_full_bar,
+                                              uint64_t* acc_empty_bar) {
+  const int q = warp - kEpiWarp0;  // TMEM lane quarter == warp_id % 4
+  int as = 0;
+  uint32_t aphase = 0;
+  int stg_i = 0;
+  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(a, tile, BN);
+    mbar_wait(&acc_full_bar[as], aphase);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, stg, s_bias, red_smem, stg_i);
+    // release this accumulator stage back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty_bar[as]);
+    if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+  }
+  if (q == 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this CTA have landed before it exits
+}
+
+__device__ __forceinline__ void load_bias_smem(const ConvArgs& a, float* s_bias, int n_total) {
+  for (int i = threadIdx.x; i < n_total && i < kMaxBias; i += kThreads) s_bias[i] = a.bias[i];
+}
+
+// ---------------------------------------------------------------------------------------------------- streaming
 template <int CK, int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
-  using C = Cfg<CK, BN>;
+  using C = Cfg<CK, BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[C::kStages];
   __shared__ uint64_t empty_bar[C::kStages];
@@ -74,10 +400,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   __shared__ uint64_t acc_empty_bar[kAccStages];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_smem[4][3];
+  __shared__ __align__(16) float s_bias[kMaxBias];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + C::kStages * C::kStageBytes;
 
   const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);  // <= 128
   const uint32_t tx_bytes = static_cast<uint32_t>(rows_valid * C::kRowBytes + C::kBBytes);
@@ -87,6 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     tma_prefetch_desc(&a.mapA0);
     if (a.chunks1 > 0) tma_prefetch_desc(&a.mapA1);
     tma_prefetch_desc(&a.mapB);
+    if (a.tma_store) tma_prefetch_desc(&a.mapOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -103,6 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     tmem_alloc<C::kTmemCols>(&tmem_base_slot);
     tmem_relinquish();
   }
+  load_bias_smem(a, s_bias, a.n_tiles * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,199 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================================================================== epilogue warps
-    const int q = warp - kEpiWarp0;  // TMEM lane quarter == warp_id % 4
-    const int r = q * 32 + lane;     // accumulator row = pixel slot in the tile
-    const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
-    const int ww = r & (TW - 1);
-    const int hh = (r >> a.lgTW) & (TH - 1);
-    const int bb = r >> (a.lgTW + a.lgTH);
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(a, tile, BN);
-      const int fb = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
-      const bool valid = (r < rows_valid) && (fb < a.B) && (h < a.H) && (w < a.W);
-      mbar_wait(&acc_full_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-
-      if constexpr (EPI == VAD_EPI_STORE || EPI == VAD_EPI_POOL || EPI == VAD_EPI_CONVT) {
-        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(tacc + c * 32, v);
-          tmem_ld_wait();
-          const int col = t.n0 + c * 32;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if constexpr (EPI == VAD_EPI_POOL) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], TW));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = act_fn(f[j] + __ldg(a.bias + col + j), a.slope);
-          uint32_t p[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-          if constexpr (EPI == VAD_EPI_STORE) {
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(outp + fb * a.out_fs +
-                                                    (static_cast<long long>(h) * a.W + w) * a.out_cp + col);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-            }
-          } else if constexpr (EPI == VAD_EPI_POOL) {
-            // the 4 lanes of a 2x2 window all hold the max; each stores one quarter (8 channels) of the chunk
-            if (valid) {
-              const int part = (ww & 1) | ((hh & 1) << 1);
-              uint4* dst = reinterpret_cast<uint4*>(
-                  outp + fb * a.out_fs + (static_cast<long long>(h >> 1) * (a.W >> 1) + (w >> 1)) * a.out_cp + col +
-                  part * 8);
-              uint4 val;
-              if (part == 0) val = make_uint4(p[0], p[1], p[2], p[3]);
-              else if (part == 1) val = make_uint4(p[4], p[5], p[6], p[7]);
-              else if (part == 2) val = make_uint4(p[8], p[9], p[10], p[11]);
-              else val = make_uint4(p[12], p[13], p[14], p[15]);
-              *dst = val;
-            }
-          } else {  // VAD_EPI_CONVT: column = quad*cout + co, quad = di*2 + dj
-            if (valid) {
-              const int quad = col / a.cout;
-              const int co = col - quad * a.cout;
-              const int ho = 2 * h + (quad >> 1), wo = 2 * w + (quad & 1);
-              uint4* dst = reinterpret_cast<uint4*>(outp + fb * a.out_fs +
-                                                    (static_cast<long long>(ho) * (2 * a.W) + wo) * a.out_cp + co);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-            }
-          }
-        }
-      } else if constexpr (EPI == VAD_EPI_LSTM) {
-        // columns of this tile: [gate g in i,f,g,o][32 hidden channels j0..j0+31]; weights/bias pre-permuted on host
-        static_assert(EPI != VAD_EPI_LSTM || BN == 128, "LSTM tile is 4 gates x 32 channels");
-        const int hid = a.cout;
-        const int j0 = (t.n0 >> 7) * 32;
-        const long long pix = (static_cast<long long>(fb) * a.H + h) * a.W + w;
-        float* cptr = a.c_state + pix * hid + j0;
-        __nv_bfloat16* hptr =
-            reinterpret_cast<__nv_bfloat16*>(a.out) + fb * a.out_fs + (static_cast<long long>(h) * a.W + w) * a.out_cp + j0;
-#pragma unroll 1
-        for (int s = 0; s < 4; ++s) {
-          uint32_t gi[8], gf[8], gg[8], go[8];
-          tmem_ld_x8(tacc + 0 + s * 8, gi);
-          tmem_ld_x8(tacc + 32 + s * 8, gf);
-          tmem_ld_x8(tacc + 64 + s * 8, gg);
-          tmem_ld_x8(tacc + 96 + s * 8, go);
-          tmem_ld_wait();
-          float cprev[8];
-          if (valid && !a.lstm_first) {
-            const float4 c0 = *reinterpret_cast<const float4*>(cptr + s * 8);
-            const float4 c1 = *reinterpret_cast<const float4*>(cptr + s * 8 + 4);
-            cprev[0] = c0.x; cprev[1] = c0.y; cprev[2] = c0.z; cprev[3] = c0.w;
-            cprev[4] = c1.x; cprev[5] = c1.y; cprev[6] = c1.z; cprev[7] = c1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cprev[e] = 0.f;
-          }
-          float cn[8], hn[8];
-          const float* bp = a.bias + t.n0 + s * 8;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float xi = __uint_as_float(gi[e]) + __ldg(bp + e);
-            const float xf = __uint_as_float(gf[e]) + __ldg(bp + 32 + e);
-            const float xg = __uint_as_float(gg[e]) + __ldg(bp + 64 + e);
-            const float xo = __uint_as_float(go[e]) + __ldg(bp + 96 + e);
-            cn[e] = sigmoid_fn(xf) * cprev[e] + sigmoid_fn(xi) * tanhf(xg);
-            hn[e] = sigmoid_fn(xo) * tanhf(cn[e]);
-          }
-          if (valid) {
-            *reinterpret_cast<float4*>(cptr + s * 8) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(cptr + s * 8 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-            *reinterpret_cast<uint4*>(hptr + s * 8) = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
-                                                                 pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7]));
-          }
-        }
-      } else {
-        // ------------------------------------------------ fused tanh + reconstruction-error reduction (N tile = 16)
-        static_assert((EPI != VAD_EPI_TANH_SCORE && EPI != VAD_EPI_CONVT_TANH_SCORE) || BN == 16, "score tile is 16 wide");
-        uint32_t v[16];
-        tmem_ld_x16(tacc, v);
-        tmem_ld_wait();
-        float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
-        if constexpr (EPI == VAD_EPI_TANH_SCORE) {
-          if (valid) {
-            const long long plane = static_cast<long long>(a.H) * a.W;
-            const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(h) * a.W + w;
-            float sq = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              const float rec = tanhf(__uint_as_float(v[ch]) + __ldg(a.bias + ch));
-              const float d = __ldg(a.x + off + ch * plane) - rec;
-              sq += d * d;
-              if (a.recon) a.recon[off + ch * plane] = rec;
-            }
-            if (a.heat) a.heat[static_cast<long long>(fb) * plane + static_cast<long long>(h) * a.W + w] = sq * (1.f / 3.f);
-            ssum = sq; smin = sq; smax = sq;
-          }
-        } else {
-          if (valid) {
-            const int Ho = 2 * a.H, Wo = 2 * a.W;
-            const long long plane = static_cast<long long>(Ho) * Wo;
-#pragma unroll
-            for (int di = 0; di < 2; ++di) {
-              const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(2 * h + di) * Wo + 2 * w;
-              float sq0 = 0.f, sq1 = 0.f;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                const float r0 = tanhf(__uint_as_float(v[(di * 2 + 0) * 3 + ch]) + __ldg(a.bias + (di * 2 + 0) * 3 + ch));
-                const float r1 = tanhf(__uint_as_float(v[(di * 2 + 1) * 3 + ch]) + __ldg(a.bias + (di * 2 + 1) * 3 + ch));
-                const float2 xv = __ldg(reinterpret_cast<const float2*>(a.x + off + ch * plane));
-                const float d0 = xv.x - r0, d1 = xv.y - r1;
-                sq0 += d0 * d0;
-                sq1 += d1 * d1;
-                if (a.recon) *reinterpret_cast<float2*>(a.recon + off + ch * plane) = make_float2(r0, r1);
-              }
-              if (a.heat)
-                *reinterpret_cast<float2*>(a.heat + static_cast<long long>(fb) * plane +
-                                           static_cast<long long>(2 * h + di) * Wo + 2 * w) =
-                    make_float2(sq0 * (1.f / 3.f), sq1 * (1.f / 3.f));
-              ssum += sq0 + sq1;
-              smin = fminf(smin, fminf(sq0, sq1));
-              smax = fmaxf(smax, fmaxf(sq0, sq1));
-            }
-          }
-        }
-        // tile reduction in a fixed order (deterministic): lanes -> warps -> one writer
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-          smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-          smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-        }
-        if (lane == 0) { red_smem[q][0] = ssum; red_smem[q][1] = smin; red_smem[q][2] = smax; }
-        named_bar_sync(1, 128);
-        if (q == 0 && lane == 0) {
-          const float s = (red_smem[0][0] + red_smem[1][0]) + (red_smem[2][0] + red_smem[3][0]);
-          const float mn = fminf(fminf(red_smem[0][1], red_smem[1][1]), fminf(red_smem[2][1], red_smem[3][1]));
-          const float mx = fmaxf(fmaxf(red_smem[0][2], red_smem[1][2]), fmaxf(red_smem[2][2], red_smem[3][2]));
-          *reinterpret_cast<float4*>(a.partials + static_cast<long long>(t.m_tile) * 4) =
-              make_float4(s, mn * (1.f / 3.f), mx * (1.f / 3.f), 0.f);
-        }
-        named_bar_sync(1, 128);  // red_smem is reused by the next tile
-      }
-
-      // release this accumulator stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty_bar[as]);
-      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
-    }
+    epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
   }
 
   tc_fence_before();
@@ -370,10 +508,129 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- halo
+constexpr int kHaloMaxStages = 8;
+
+template <int CK, int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int kRowBytes = CK * 2;
+  constexpr int kBBytes = BN * kRowBytes;  // one tap's weight slab
+  constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;
+  constexpr uint32_t kTmemCols = tmem_cols_for(BN);
+  static_assert(kBBytes % 1024 == 0, "weight slab must keep 1024B alignment");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_bar;
+  __shared__ uint64_t full_bar[kHaloMaxStages];
+  __shared__ uint64_t empty_bar[kHaloMaxStages];
+  __shared__ uint64_t acc_full_bar[kAccStages];
+  __shared__ uint64_t acc_empty_bar[kAccStages];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float red_smem[4][3];
+  __shared__ __align__(16) float s_bias[kMaxBias];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;                                   // 9 weight slabs, resident for the CTA's lifetime
+  uint8_t* s_a = smem + 9 * kBBytes;                     // ring of input patches
+  const int stage_bytes = a.halo_patch_bytes * a.halo_npatch;
+  uint8_t* stg = s_a + a.halo_stages * stage_bytes;      // epilogue staging
+  const uint32_t patch_tx = static_cast<uint32_t>(a.halo_npatch * a.halo_pw * a.halo_ph * kRowBytes);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapB);
+    if (a.tma_store) tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < a.halo_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kTmemCols>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  load_bias_smem(a, s_bias, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights: nine [BN x CK] slabs, once
+      mbar_arrive_expect_tx(&w_bar, 9u * kBBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_w + tap * kBBytes, &a.mapB, &w_bar, tap * a.w_ctap, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, BN);
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = s_a + stage * stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], patch_tx);
+        for (int p = 0; p < a.halo_npatch; ++p)
+          tma_load_5d(sa + p * a.halo_patch_bytes, &a.mapA0, &full_bar[stage], 0, t.w0 - 1 + p, t.h0 - 1, a.tA0, t.b0);
+        if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+      const uint32_t sbo = static_cast<uint32_t>(a.halo_sbo_rows * kRowBytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      mbar_wait(&w_bar, 0);
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty_bar[as], aphase ^ 1u);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t sa = smem_u32(s_a + stage * stage_bytes);
+        const uint32_t sw = smem_u32(s_w);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a_addr = sa + static_cast<uint32_t>(a.tap_patch[tap] * a.halo_patch_bytes +
+                                                             a.tap_row[tap] * kRowBytes);
+          const uint32_t bo = a.halo_base_mode ? ((a_addr >> 7) & 7u) : 0u;
+          const uint64_t da = umma_smem_desc(a_addr, sbo, kLayout, bo);
+          const uint64_t db = umma_smem_desc(sw + tap * kBBytes, 8 * kRowBytes, kLayout);
+#pragma unroll
+          for (int kk = 0; kk < CK / 16; ++kk)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                      (tap > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&acc_full_bar[as]);
+        if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
+        if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host dispatch
 template <int CK, int BN, int EPI>
 static int launch_one(const ConvArgs& a, int grid, cudaStream_t stream) {
-  using C = Cfg<CK, BN>;
+  using C = Cfg<CK, BN, EPI>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CK, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -393,19 +650,68 @@ int launch_conv_umma(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaS
   // (K chunk, N tile, epilogue) instantiations used by the two models; anything else is VAD_ERR_UNSUPPORTED.
   VAD_CASE(32, 32, VAD_EPI_STORE)
   VAD_CASE(32, 64, VAD_EPI_STORE)
+  VAD_CASE(64, 32, VAD_EPI_STORE)
   VAD_CASE(64, 64, VAD_EPI_STORE)
   VAD_CASE(64, 128, VAD_EPI_STORE)
   VAD_CASE(64, 256, VAD_EPI_STORE)
   VAD_CASE(32, 32, VAD_EPI_POOL)
   VAD_CASE(32, 64, VAD_EPI_POOL)
+  VAD_CASE(64, 32, VAD_EPI_POOL)
   VAD_CASE(64, 64, VAD_EPI_POOL)
   VAD_CASE(64, 128, VAD_EPI_POOL)
   VAD_CASE(64, 256, VAD_EPI_POOL)
   VAD_CASE(32, 128, VAD_EPI_CONVT)
   VAD_CASE(64, 128, VAD_EPI_CONVT)
+  VAD_CASE(32, 128, VAD_EPI_LSTM)
   VAD_CASE(64, 128, VAD_EPI_LSTM)
   VAD_CASE(32, 16, VAD_EPI_TANH_SCORE)
   VAD_CASE(32, 16, VAD_EPI_CONVT_TANH_SCORE)
+  return VAD_ERR_UNSUPPORTED;
+}
+#undef VAD_CASE
+
+template <int CK, int BN, int EPI>
+static constexpr int halo_fixed_bytes() {
+  return 1024 + 9 * BN * CK * 2 + staging_bufs(BN, EPI) * kStagingBuf;
+}
+
+template <int CK, int BN, int EPI>
+static int launch_halo_one(const ConvArgs& a, int grid, cudaStream_t stream) {
+  const int smem = halo_fixed_bytes<CK, BN, EPI>() + a.halo_stages * a.halo_patch_bytes * a.halo_npatch;
+  static int configured = 0;  // largest size configured so far, per instantiation
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CK, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = smem;
+  }
+  conv_halo_kernel<CK, BN, EPI><<<grid, kThreads, smem, stream>>>(a);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+#define VAD_HALO_CASES(X)              \
+  X(32, 32, VAD_EPI_STORE)             \
+  X(32, 64, VAD_EPI_STORE)             \
+  X(64, 64, VAD_EPI_STORE)             \
+  X(32, 32, VAD_EPI_POOL)              \
+  X(32, 64, VAD_EPI_POOL)              \
+  X(64, 64, VAD_EPI_POOL)              \
+  X(32, 16, VAD_EPI_TANH_SCORE)
+
+int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages) {
+#define X(ck, bn, epi) \
+  if (CK == ck && BN == bn && EPI == epi) return halo_fixed_bytes<ck, bn, epi>() + stages * patch_bytes_total;
+  VAD_HALO_CASES(X)
+#undef X
+  return 0;
+}
+
+int launch_conv_halo(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
+#define X(ck, bn, epi) \
+  if (CK == ck && BN == bn && EPI == epi) return launch_halo_one<ck, bn, epi>(a, grid, stream);
+  VAD_HALO_CASES(X)
+#undef X
   return VAD_ERR_UNSUPPORTED;
 }
 

@@ -8,12 +8,13 @@
 
 namespace vad {
 
-// Kernel argument block of conv_umma_kernel (passed as a __grid_constant__ parameter; the three tensor maps
-// must stay 64-byte aligned).
+// Kernel argument block of the conv kernels (passed as a __grid_constant__ parameter; the tensor maps must stay
+// 64-byte aligned).
 struct alignas(64) ConvArgs {
-  CUtensorMap mapA0;  // bf16 [B][T][H][W][C] source 0, box {CK, TW, TH, 1, TN}
-  CUtensorMap mapA1;  // optional source 1 (ConvLSTM hidden state)
-  CUtensorMap mapB;   // bf16 [n_total][K] weights, box {CK, BN}
+  CUtensorMap mapA0;   // bf16 [B][T][H][W][C] source 0; box {CK, TW, TH, 1, TN} (streaming) or {CK, PW, PH, 1, 1} (halo)
+  CUtensorMap mapA1;   // optional source 1 (ConvLSTM hidden state)
+  CUtensorMap mapB;    // bf16 [n_total][K] weights, box {CK, BN}
+  CUtensorMap mapOut;  // bf16 output, used when tma_store != 0 (box = one staged chunk of the output tile)
   int chunks0, chunks1;  // CK-wide channel chunks per source
   int ntaps;
   int w_ctap;  // weight columns per tap
@@ -35,6 +36,18 @@ struct alignas(64) ConvArgs {
   float* recon;
   float* heat;
   float* partials;
+  // epilogue staging / TMA store
+  int tma_store;  // 1: stage the bf16 tile in swizzled smem and store it with TMA (coalesced, clipped by hardware)
+  int out_chunk;  // channels per staged chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+  // halo kernel (3x3 conv, weights resident in smem, one input patch per tile reused by all 9 taps)
+  int halo_pw, halo_ph;       // patch width / height in pixels
+  int halo_npatch;            // 1: one (TW+2)-wide patch; 3: three TW-wide patches shifted by dx
+  int halo_patch_bytes;       // bytes of one patch in smem (multiple of 1024)
+  int halo_stages;            // ring depth
+  int halo_sbo_rows;          // patch rows between consecutive 8-row groups of the A operand
+  int halo_base_mode;         // smem descriptor base-offset field: 0 -> 0, 1 -> (addr >> 7) & 7
+  int tap_patch[9];           // which patch a tap reads
+  int tap_row[9];             // first patch row (pixel index) of the tap's A operand
 };
 
 struct TileGeom {
@@ -45,6 +58,9 @@ struct TileGeom {
 TileGeom pick_tile_geometry(int B, int H, int W, bool single_frame_tiles);
 
 int launch_conv_umma(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
+int launch_conv_halo(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
+// dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)
+int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);
 void count_launch();
 int sm_count();
 

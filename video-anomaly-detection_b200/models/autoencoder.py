@@ -45,6 +45,12 @@ def _refuse_training(module: nn.Module) -> None:
             "call model.eval() first — training stays with the reference implementation")
 
 
+def _refuse_cpu(device: torch.device) -> None:
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("vad_b200 scoring path is CUDA-only (sm_100a kernels, no CPU fallback); "
+                           f"got a tensor on {device}")
+
+
 class Encoder(nn.Module):
     """4 x [conv3x3-BN-LeakyReLU x2, maxpool2]: 3 -> 32 -> 64 -> 128 -> latent_dim, spatial / 16."""
 
@@ -109,6 +115,7 @@ class ConvAutoencoder(nn.Module):
     # ---- prepared-weight cache -----------------------------------------------------------------------------
     def _get_engine(self, device: torch.device) -> ImageEngine:
         _refuse_training(self)
+        _refuse_cpu(device)
         sig = _state_signature(self)
         if self._engine is None or sig != self._engine_sig:
             sd: Dict[str, torch.Tensor] = {k: v.detach() for k, v in self.state_dict().items()}

@@ -15,7 +15,7 @@ import torch.nn as nn
 from . import _native as nat
 from . import _prepare as prep
 from ._engine import ScoreOutputs, VideoEngine, _require_cuda_input
-from .autoencoder import _refuse_training, _state_signature, _xavier_like_reference
+from .autoencoder import _refuse_cpu, _refuse_training, _state_signature, _xavier_like_reference
 
 
 def _owner_required(owner, name: str):
@@ -166,6 +166,7 @@ class VideoAutoencoder(nn.Module):
 
     def _get_engine(self, device: torch.device) -> VideoEngine:
         _refuse_training(self)
+        _refuse_cpu(device)
         sig = _state_signature(self)
         if self._engine is None or sig != self._engine_sig:
             sd: Dict[str, torch.Tensor] = {k: v.detach() for k, v in self.state_dict().items()}
