@@ -23,8 +23,7 @@
 
 namespace vad {
 
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarp0 = 4;  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, spare
 constexpr int kTileM = 128;
 constexpr int kAccStages = 2;
 constexpr int kStagingBuf = 16384;  // one staged output chunk: 128 rows x 128 B
@@ -34,8 +33,24 @@ constexpr int kSmemBudget = 227 * 1024 - 4096;  // dynamic smem we allow ourselv
 __host__ __device__ constexpr bool epi_uses_staging(int epi) {
   return epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_CONVT || epi == VAD_EPI_LSTM;
 }
+// Epilogue warps come in groups of four (one warp per TMEM lane quarter).  Narrow tiles are epilogue-bound, so they
+// get two groups that take alternate tiles (group g owns accumulator stage g); 256-wide tiles are MMA-bound and
+// keep one group (and the smem for a deeper operand ring).
+__host__ __device__ constexpr int epi_groups(int bn) { return bn >= 256 ? 1 : 2; }
+__host__ __device__ constexpr int block_threads(int bn) { return 128 + 128 * epi_groups(bn); }
+// staged-output buffers per epilogue group
 __host__ __device__ constexpr int staging_bufs(int bn, int epi) {
   return !epi_uses_staging(epi) ? 0 : (bn >= 256 ? 1 : 2);
+}
+// one staged chunk: 128 rows x (64 ch = 128 B | 32 ch = 64 B)
+__host__ __device__ constexpr int staging_buf_bytes(int bn, int epi) {
+  return (bn == 32 || epi == VAD_EPI_LSTM) ? kStagingBuf / 2 : kStagingBuf;
+}
+__host__ __device__ constexpr int staging_group_bytes(int bn, int epi) {
+  return staging_bufs(bn, epi) * staging_buf_bytes(bn, epi);
+}
+__host__ __device__ constexpr int staging_bytes(int bn, int epi) {
+  return epi_groups(bn) * staging_group_bytes(bn, epi);
 }
 __host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
   return (2 * bn <= 32) ? 32u : (2 * bn <= 64) ? 64u : (2 * bn <= 128) ? 128u : (2 * bn <= 256) ? 256u : 512u;
@@ -47,7 +62,7 @@ struct Cfg {
   static constexpr int kABytes = kTileM * kRowBytes;  // 16 KB / 8 KB
   static constexpr int kBBytes = BN * kRowBytes;      // multiple of 1024 for BN >= 16
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = staging_bufs(BN, EPI) * kStagingBuf;
+  static constexpr int kStagingBytes = staging_bytes(BN, EPI);
   static constexpr int kStagesRaw = (kSmemBudget - 1024 - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024;  // +1024 alignment slack
@@ -93,7 +108,8 @@ __device__ __forceinline__ uint32_t staged_off(int row, int c16, int out_chunk) 
 // Runs on the four epilogue warps for one finished accumulator tile.  `stg_i` counts staged chunks (ring index).
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& t, uint32_t tacc, int q, int lane,
-                                              uint8_t* stg, const float* s_bias, float (*red_smem)[3], int& stg_i) {
+                                              uint8_t* stg, const float* s_bias, float (*red_smem)[3], int& stg_i,
+                                              uint32_t bar_id, const float* xpre) {
   const int r = q * 32 + lane;  // accumulator row = pixel slot in the tile
   const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
   const int ww = r & (TW - 1);
@@ -111,11 +127,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
       const int n_chunks = BN / OC;
 #pragma unroll 1
       for (int oc = 0; oc < n_chunks; ++oc) {
-        uint8_t* buf = stg + (kBufs > 1 ? (stg_i & 1) : 0) * kStagingBuf;
+        uint8_t* buf = stg + (kBufs > 1 ? (stg_i & 1) : 0) * staging_buf_bytes(BN, EPI);
         if (leader) {  // the TMA store that last read this buffer must have finished reading it
           if (kBufs > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
 #pragma unroll 1
         for (int sub = 0; sub < OC / 32; ++sub) {
           const int lc = oc * OC + sub * 32;
@@ -158,7 +174,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (leader) {
           const int col = t.n0 + oc * OC;
           if constexpr (EPI == VAD_EPI_STORE) {
@@ -237,10 +253,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
     const int j0 = (t.n0 >> 7) * 32;
     const long long pix = (static_cast<long long>(fb) * a.H + h) * a.W + w;
     float* cptr = a.c_state + pix * hid + j0;
-    uint8_t* buf = stg + (stg_i & 1) * kStagingBuf;
+    uint8_t* buf = stg + (stg_i & 1) * staging_buf_bytes(BN, EPI);
     if (a.tma_store) {
       if (leader) bulk_wait_group_read<1>();
-      named_bar_sync(1, 128);
+      named_bar_sync(bar_id, 128);
     }
     __nv_bfloat16* hptr = reinterpret_cast<__nv_bfloat16*>(a.out) + fb * a.out_fs +
                           (static_cast<long long>(h) * a.W + w) * a.out_cp + j0;
@@ -284,7 +300,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
     }
     if (a.tma_store) {
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(bar_id, 128);
       if (leader) {
         tma_store_5d(&a.mapOut, buf, j0, t.w0, t.h0, 0, t.b0);
         bulk_commit_group();
@@ -306,7 +322,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float rec = tanhf(__uint_as_float(v[ch]) + s_bias[ch]);
-          const float d = __ldg(a.x + off + ch * plane) - rec;
+          const float d = xpre[ch] - rec;
           sq += d * d;
           if (a.recon) a.recon[off + ch * plane] = rec;
         }
@@ -325,8 +341,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           for (int ch = 0; ch < 3; ++ch) {
             const float r0 = tanhf(__uint_as_float(v[(di * 2 + 0) * 3 + ch]) + s_bias[(di * 2 + 0) * 3 + ch]);
             const float r1 = tanhf(__uint_as_float(v[(di * 2 + 1) * 3 + ch]) + s_bias[(di * 2 + 1) * 3 + ch]);
-            const float2 xv = __ldg(reinterpret_cast<const float2*>(a.x + off + ch * plane));
-            const float d0 = xv.x - r0, d1 = xv.y - r1;
+            const float d0 = xpre[(di * 3 + ch) * 2] - r0, d1 = xpre[(di * 3 + ch) * 2 + 1] - r1;
             sq0 += d0 * d0;
             sq1 += d1 * d1;
             if (a.recon) *reinterpret_cast<float2*>(a.recon + off + ch * plane) = make_float2(r0, r1);
@@ -349,7 +364,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
       smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
     }
     if (lane == 0) { red_smem[q][0] = ssum; red_smem[q][1] = smin; red_smem[q][2] = smax; }
-    named_bar_sync(1, 128);
+    named_bar_sync(bar_id, 128);
     if (leader) {
       const float s = (red_smem[0][0] + red_smem[1][0]) + (red_smem[2][0] + red_smem[3][0]);
       const float mn = fminf(fminf(red_smem[0][1], red_smem[1][1]), fminf(red_smem[2][1], red_smem[3][1]));
@@ -357,41 +372,80 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
       *reinterpret_cast<float4*>(a.partials + static_cast<long long>(t.m_tile) * 4) =
           make_float4(s, mn * (1.f / 3.f), mx * (1.f / 3.f), 0.f);
     }
-    named_bar_sync(1, 128);  // red_smem is reused by the next tile
+    named_bar_sync(bar_id, 128);  // red_smem is reused by the next tile
   }
 }
 
-// Shared body of the epilogue warps: loop over this CTA's tiles.
+// Loads the model-input pixels a score epilogue will compare against (issued before the accumulator wait so the HBM
+// latency overlaps the MMAs of the tile).
+template <int EPI>
+__device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t, int q, int lane, float* xpre) {
+  if constexpr (EPI == VAD_EPI_TANH_SCORE || EPI == VAD_EPI_CONVT_TANH_SCORE) {
+    const int r = q * 32 + lane;
+    const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
+    const int fb = t.b0 + (r >> (a.lgTW + a.lgTH)), h = t.h0 + ((r >> a.lgTW) & (TH - 1)), w = t.w0 + (r & (TW - 1));
+    const bool valid = (r < (1 << (a.lgTW + a.lgTH + a.lgTN))) && (fb < a.B) && (h < a.H) && (w < a.W);
+    if constexpr (EPI == VAD_EPI_TANH_SCORE) {
+      const long long plane = static_cast<long long>(a.H) * a.W;
+      const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(h) * a.W + w;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) xpre[ch] = valid ? __ldg(a.x + off + ch * plane) : 0.f;
+    } else {
+      const int Wo = 2 * a.W;
+      const long long plane = 4LL * a.H * a.W;
+#pragma unroll
+      for (int di = 0; di < 2; ++di) {
+        const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(2 * h + di) * Wo + 2 * w;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float2 xv = valid ? __ldg(reinterpret_cast<const float2*>(a.x + off + ch * plane)) : make_float2(0.f, 0.f);
+          xpre[(di * 3 + ch) * 2] = xv.x;
+          xpre[(di * 3 + ch) * 2 + 1] = xv.y;
+        }
+      }
+    }
+  }
+}
+
+// Shared body of the epilogue warps.  Group g (warps 4+4g .. 7+4g) handles this CTA's tiles g, g+G, g+2G, ...;
+// with G = 2 each group owns one TMEM accumulator stage.
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_base, int warp, int lane, uint8_t* stg,
-                                              const float* s_bias, float (*red_smem)[3], uint64_t* acc_full_bar,
+                                              const float* s_bias, float (*red_smem)[4][3], uint64_t* acc_full_bar,
                                               uint64_t* acc_empty_bar) {
-  const int q = warp - kEpiWarp0;  // TMEM lane quarter == warp_id % 4
-  int as = 0;
-  uint32_t aphase = 0;
+  constexpr int G = epi_groups(BN);
+  const int g = (warp - kEpiWarp0) >> 2;
+  const int q = warp & 3;  // TMEM lane quarter == warp_id % 4
+  uint8_t* my_stg = stg + g * staging_group_bytes(BN, EPI);
   int stg_i = 0;
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+  int it = 0;  // CTA-local tile counter
+  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+    if (G == 2 && (it & 1) != g) continue;
+    const int as = (G == 2) ? g : (it & 1);
+    const uint32_t aphase = (G == 2) ? ((it >> 1) & 1) : ((it >> 1) & 1);
     const TileCoord t = decode_tile(a, tile, BN);
+    float xpre[12];
+    prefetch_x<EPI>(a, t, q, lane, xpre);
     mbar_wait(&acc_full_bar[as], aphase);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, stg, s_bias, red_smem, stg_i);
+    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xpre);
     // release this accumulator stage back to the MMA warp
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&acc_empty_bar[as]);
-    if (++as == kAccStages) { as = 0; aphase ^= 1u; }
   }
-  if (q == 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this CTA have landed before it exits
+  if (q == 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this group have landed before the CTA exits
 }
 
+template <int BN>
 __device__ __forceinline__ void load_bias_smem(const ConvArgs& a, float* s_bias, int n_total) {
-  for (int i = threadIdx.x; i < n_total && i < kMaxBias; i += kThreads) s_bias[i] = a.bias[i];
+  for (int i = threadIdx.x; i < n_total && i < kMaxBias; i += block_threads(BN)) s_bias[i] = a.bias[i];
 }
 
 // ---------------------------------------------------------------------------------------------------- streaming
 template <int CK, int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   using C = Cfg<CK, BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[C::kStages];
@@ -399,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   __shared__ uint64_t acc_full_bar[kAccStages];
   __shared__ uint64_t acc_empty_bar[kAccStages];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[4][3];
+  __shared__ float red_smem[2][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
   const int warp = threadIdx.x >> 5;
@@ -409,7 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
   const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);  // <= 128
   const uint32_t tx_bytes = static_cast<uint32_t>(rows_valid * C::kRowBytes + C::kBBytes);
-  const int k_iters = a.ntaps * (a.chunks0 + a.chunks1);
+  const int chunks = a.chunks0 + a.chunks1;
+  const int k_iters = a.ntaps * chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.mapA0);
@@ -424,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
-      mbar_init(&acc_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty_bar[i], 4);  // one arrive per warp of the owning epilogue group
     }
     fence_barrier_init();
   }
@@ -432,25 +487,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     tmem_alloc<C::kTmemCols>(&tmem_base_slot);
     tmem_relinquish();
   }
-  load_bias_smem(a, s_bias, a.n_tiles * BN);
+  load_bias_smem<BN>(a, s_bias, a.n_tiles * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Role loops are executed by the WHOLE warp (uniform control flow); one elected lane issues the TMA / MMA.
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile, BN);
-        for (int tap = 0; tap < a.ntaps; ++tap) {
-          int kcol = tap * a.w_ctap;
-          const int dy = (a.ntaps == 9) ? (tap / 3 - 1) : 0;
-          const int dx = (a.ntaps == 9) ? (tap % 3 - 1) : 0;
-          for (int c = 0; c < a.chunks0 + a.chunks1; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile, BN);
+      for (int tap = 0; tap < a.ntaps; ++tap) {
+        int kcol = tap * a.w_ctap;
+        const int dy = (a.ntaps == 9) ? (tap / 3 - 1) : 0;
+        const int dx = (a.ntaps == 9) ? (tap % 3 - 1) : 0;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (elect_one()) {
             uint8_t* sa = smem + stage * C::kStageBytes;
             uint8_t* sb = sa + C::kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -459,27 +515,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             else
               tma_load_5d(sa, &a.mapA1, &full_bar[stage], (c - a.chunks0) * CK, t.w0 + dx, t.h0 + dy, a.tA1, t.b0);
             tma_load_2d(sb, &a.mapB, &full_bar[stage], kcol, t.n0);
-            kcol += CK;
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          kcol += CK;
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty_bar[as], aphase ^ 1u);
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t da = umma_smem_desc(sa, C::kSBO, C::kLayout);
           const uint64_t db = umma_smem_desc(sa + C::kABytes, C::kSBO, C::kLayout);
@@ -489,11 +546,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
                       (k > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
+          if (k == k_iters - 1) umma_commit(&acc_full_bar[as]);  // accumulator ready for the epilogue
         }
-        umma_commit(&acc_full_bar[as]);  // accumulator ready for the epilogue
-        if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -512,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 constexpr int kHaloMaxStages = 8;
 
 template <int CK, int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int kRowBytes = CK * 2;
   constexpr int kBBytes = BN * kRowBytes;  // one tap's weight slab
   constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;
@@ -525,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   __shared__ uint64_t acc_full_bar[kAccStages];
   __shared__ uint64_t acc_empty_bar[kAccStages];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[4][3];
+  __shared__ float red_smem[2][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
   const int warp = threadIdx.x >> 5;
@@ -558,52 +615,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     tmem_alloc<kTmemCols>(&tmem_base_slot);
     tmem_relinquish();
   }
-  load_bias_smem(a, s_bias, BN);
+  load_bias_smem<BN>(a, s_bias, BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // weights: nine [BN x CK] slabs, once
+    // ===================================================================== TMA producer (whole warp, elected issue)
+    if (elect_one()) {  // weights: nine [BN x CK] slabs, once
       mbar_arrive_expect_tx(&w_bar, 9u * kBBytes);
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_w + tap * kBBytes, &a.mapB, &w_bar, tap * a.w_ctap, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile, BN);
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile, BN);
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (elect_one()) {
         uint8_t* sa = s_a + stage * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], patch_tx);
         for (int p = 0; p < a.halo_npatch; ++p)
           tma_load_5d(sa + p * a.halo_patch_bytes, &a.mapA0, &full_bar[stage], 0, t.w0 - 1 + p, t.h0 - 1, a.tA0, t.b0);
-        if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
-      const uint32_t sbo = static_cast<uint32_t>(a.halo_sbo_rows * kRowBytes);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      mbar_wait(&w_bar, 0);
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty_bar[as], aphase ^ 1u);
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint32_t sbo = static_cast<uint32_t>(a.halo_sbo_rows * kRowBytes);
+    // per-tap operand start offsets in 16-byte units (the descriptor's address field), fixed for the whole kernel
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+      tap_off[tap] = static_cast<uint32_t>(a.tap_patch[tap] * a.halo_patch_bytes + a.tap_row[tap] * kRowBytes) >> 4;
+    const uint64_t da_hi = umma_smem_desc(0, sbo, kLayout);             // everything but the start address
+    const uint64_t db0 = umma_smem_desc(smem_u32(s_w), 8 * kRowBytes, kLayout);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    mbar_wait(&w_bar, 0);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        const uint32_t sa = smem_u32(s_a + stage * stage_bytes);
-        const uint32_t sw = smem_u32(s_w);
-#pragma unroll 1
+        const uint32_t sa16 = (smem_u32(s_a + stage * stage_bytes) & 0x3FFFF) >> 4;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t a_addr = sa + static_cast<uint32_t>(a.tap_patch[tap] * a.halo_patch_bytes +
-                                                             a.tap_row[tap] * kRowBytes);
-          const uint32_t bo = a.halo_base_mode ? ((a_addr >> 7) & 7u) : 0u;
-          const uint64_t da = umma_smem_desc(a_addr, sbo, kLayout, bo);
-          const uint64_t db = umma_smem_desc(sw + tap * kBBytes, 8 * kRowBytes, kLayout);
+          uint32_t a16 = sa16 + tap_off[tap];
+          if (a.halo_base_mode) a16 |= 0;  // (base-offset experiments removed: hardware swizzles absolute addresses)
+          const uint64_t da = da_hi | static_cast<uint64_t>(a16);
+          const uint64_t db = db0 + static_cast<uint64_t>((tap * kBBytes) >> 4);
 #pragma unroll
           for (int kk = 0; kk < CK / 16; ++kk)
             umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
@@ -611,9 +678,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         umma_commit(&empty_bar[stage]);
         umma_commit(&acc_full_bar[as]);
-        if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
-        if (++as == kAccStages) { as = 0; aphase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= kEpiWarp0) {
     epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
@@ -638,7 +705,7 @@ static int launch_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_umma_kernel<CK, BN, EPI><<<grid, kThreads, C::kSmemBytes, stream>>>(a);
+  conv_umma_kernel<CK, BN, EPI><<<grid, block_threads(BN), C::kSmemBytes, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -672,7 +739,7 @@ int launch_conv_umma(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaS
 
 template <int CK, int BN, int EPI>
 static constexpr int halo_fixed_bytes() {
-  return 1024 + 9 * BN * CK * 2 + staging_bufs(BN, EPI) * kStagingBuf;
+  return 1024 + 9 * BN * CK * 2 + staging_bytes(BN, EPI);
 }
 
 template <int CK, int BN, int EPI>
@@ -685,7 +752,7 @@ static int launch_halo_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
-  conv_halo_kernel<CK, BN, EPI><<<grid, kThreads, smem, stream>>>(a);
+  conv_halo_kernel<CK, BN, EPI><<<grid, block_threads(BN), smem, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
