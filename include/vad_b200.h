@@ -34,6 +34,9 @@ const char* vad_error_string(int code);
 int vad_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 unsigned long long vad_launch_count(void);
+/* Bring-up aid: if a kernel's bounded mbarrier wait timed out (the kernel then traps), out = {wait-site tag,
+ * blockIdx.x, threadIdx.x, parity}; all zero otherwise.  Readable even after the CUDA context reports an error. */
+int vad_debug_last_trap(unsigned long long out[4]);
 
 /* ---- one convolution-as-GEMM layer ----------------------------------------------------------------------------
  * Implicit-GEMM on tcgen05/TMEM fed by TMA.  M = B*H*W input pixels (tiles of 128), N = n_total, K = ntaps*(c0+c1).
@@ -91,6 +94,11 @@ int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles);
 int vad_first_conv(const float* x, const float* weight /* fp32 [27][cout], k = (ky*3+kx)*3+ci */,
                    const float* bias, int cout, float slope, int pool, int B, int H, int W, void* out_bf16_nhwc,
                    vad_stream_t stream);
+
+/* Tensor-core variant of the same layer (default): weight is bf16 [32][32], row = output channel, column
+ * k = (ky*3+kx)*3+ci for k < 27 and zero for k >= 27; input pixels are rounded to bf16 by the im2col producer. */
+int vad_first_conv_tc(const float* x, const void* weight_bf16, const float* bias, float slope, int pool, int B, int H,
+                      int W, void* out_bf16_nhwc, vad_stream_t stream);
 
 /* ---- scoring reduction ----------------------------------------------------------------------------------------
  * reference models/autoencoder.py:214-221, models/video_autoencoder.py:371-384, evaluate_video.py:56 (min/max) */

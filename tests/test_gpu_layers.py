@@ -105,14 +105,17 @@ def test_first_conv(cuda_device, pool, B, H, W):
     g = torch.Generator().manual_seed(5)
     w = torch.randn(32, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
     b = torch.randn(32, generator=g) * 0.1
-    fw = prep.pack_first_conv(w.double(), b.double())
-    fw.w, fw.bias = fw.w.to(dev), fw.bias.to(dev)
+    fw = prep.to_device({"w": prep.pack_first_conv(w.double(), b.double())}, dev)["w"]
     x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     out = torch.full((B, Ho, Wo, 32), float("nan"), dtype=torch.bfloat16, device=dev)
     eng._first_conv(fw, x, B, H, W, pool, out)
     torch.cuda.synchronize()
-    ref = F.leaky_relu(F.conv2d(x, w.to(dev), b.to(dev), padding=1), 0.2)
+    if eng.FIRST_CONV_TC:  # tensor-core path rounds both operands to bf16
+        ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float().to(dev), b.to(dev), padding=1)
+    else:
+        ref = F.conv2d(x, w.to(dev), b.to(dev), padding=1)
+    ref = F.leaky_relu(ref, 0.2)
     if pool:
         ref = F.max_pool2d(ref, 2, 2)
     _assert_close(out, _nhwc(ref), f"first conv pool={pool}", atol=1e-3)

@@ -41,7 +41,7 @@ def run_stage(stage):
     if stage == "first":
         w = torch.randn(32, 3, 3, 3, generator=g) * 0.3
         b = torch.randn(32, generator=g) * 0.1
-        fw = prep.pack_first_conv(w.double(), b.double()); fw.w, fw.bias = fw.w.to(dev), fw.bias.to(dev)
+        fw = prep.to_device({'w': prep.pack_first_conv(w.double(), b.double())}, dev)['w']
         x = (torch.rand(2, 3, 32, 64, generator=g) * 2 - 1).to(dev)
         for pool in (False, True):
             out = torch.full((2, 16 if pool else 32, 32 if pool else 64, 32), float("nan"), dtype=torch.bfloat16, device=dev)
@@ -109,7 +109,18 @@ def run_stage(stage):
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--stage":
-        run_stage(sys.argv[2])
+        import time
+        t0 = time.time()
+        try:
+            run_stage(sys.argv[2])
+        except Exception as e:  # noqa: BLE001  (bring-up tool: report the trap slot, then re-raise)
+            import ctypes
+            from models import _native as nat
+            trap = (ctypes.c_ulonglong * 4)()
+            nat.load().vad_debug_last_trap(trap)
+            print(f"[{sys.argv[2]}] FAILED after {time.time() - t0:.1f}s: {str(e).splitlines()[0][:200]}")
+            print(f"[{sys.argv[2]}] trap slot: tag={trap[0]} block={trap[1]} thread={trap[2]} parity={trap[3]}", flush=True)
+            sys.exit(1)
         sys.exit(0)
     stages = sys.argv[1:] or STAGES
     for s in stages:

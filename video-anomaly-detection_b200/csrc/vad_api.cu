@@ -15,6 +15,20 @@ namespace vad {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Host-mapped slot a timed-out mbarrier wait writes before trapping (readable even after the context is poisoned).
+static unsigned long long* g_trap_host = nullptr;
+static void ensure_trap_slot() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  unsigned long long* h = nullptr;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&h), 4 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) return;
+  std::memset(h, 0, 4 * sizeof(unsigned long long));
+  unsigned long long* d = nullptr;
+  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) return;
+  if (set_trap_slot(d) == 0) g_trap_host = h;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -376,6 +390,12 @@ int vad_version(void) { return 100; }
 
 unsigned long long vad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int vad_debug_last_trap(unsigned long long out[4]) {
+  if (!g_trap_host || !out) return VAD_ERR_ARG;
+  for (int i = 0; i < 4; ++i) out[i] = g_trap_host[i];
+  return VAD_OK;
+}
+
 int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles) {
   if (B <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
   return pick_tile_geometry(B, H, W, force_single_frame_tiles != 0).m_tiles();
@@ -423,6 +443,7 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
 
   if (d->n_total > 512) return VAD_ERR_SHAPE;  // bias slab in shared memory
 
+  ensure_trap_slot();
   ConvArgs a;
   std::memset(&a, 0, sizeof(a));
   TileGeom g = pick_tile_geometry(d->B, d->H, d->W, is_score);
@@ -568,6 +589,62 @@ int vad_first_conv(const float* x, const float* weight, const float* bias, int c
         x, weight, bias, slope, B, H, W, reinterpret_cast<__nv_bfloat16*>(out), tiles_x, tiles_y);
   count_launch();
   return static_cast<int>(cudaGetLastError());
+}
+
+int vad_first_conv_tc(const float* x, const void* weight, const float* bias, float slope, int pool, int B, int H,
+                      int W, void* out, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !weight || !bias || !out || B <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  if (pool && ((H | W) & 1)) return VAD_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(weight) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0) return VAD_ERR_ARG;
+  ensure_trap_slot();
+  ConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.lgTW = 4; a.lgTH = 3; a.lgTN = 0;  // 8 x 16 pixel tiles inside one frame
+  a.tiles_w = (W + 15) / 16;
+  a.tiles_h = (H + 7) / 8;
+  a.tiles_b = B;
+  a.n_tiles = 1;
+  const long long tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * B;
+  if (tiles > 0x7fffffffLL) return VAD_ERR_SHAPE;
+  a.total_tiles = static_cast<int>(tiles);
+  a.B = B; a.H = H; a.W = W;
+  a.bias = bias;
+  a.slope = slope;
+  a.x = x;
+  a.w_first = weight;
+  a.dbg = env_int("VAD_DBG", 0);
+  a.out = out;
+  a.cout = 32;
+  a.out_cp = 32;
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  a.out_fs = static_cast<long long>(Ho) * Wo * 32;
+  a.out_chunk = 32;
+  {
+    // fp32 NCHW input as a 4-D map {W, H, 3, B}; box = 24 x 10 x 3 patch starting at column w0-4 (16-byte aligned
+    // start; columns 3..20 are used), zero fill outside the frame = conv padding
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return VAD_ERR_DRIVER;
+    if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || W % 4 != 0) return VAD_ERR_SHAPE;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+    cuuint64_t st[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+    cuuint32_t box[4] = {24, 10, 3, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (fn(&a.mapA0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, st, box, es,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return VAD_ERR_DRIVER;
+  }
+  {
+    cuuint64_t dims[5] = {32, (cuuint64_t)Wo, (cuuint64_t)Ho, 1, (cuuint64_t)B};
+    cuuint64_t st[4] = {64, (cuuint64_t)Wo * 64, (cuuint64_t)Ho * Wo * 64, (cuuint64_t)Ho * Wo * 64};
+    cuuint32_t box[5] = {32, pool ? 8u : 16u, pool ? 4u : 8u, 1, 1};
+    const int rc = encode_map5(&a.mapOut, out, dims, st, box, 32);
+    if (rc != VAD_OK) return rc;
+    a.tma_store = 1;
+  }
+  const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return launch_conv_first(pool ? VAD_EPI_POOL : VAD_EPI_STORE, a, grid, stream);
 }
 
 int vad_score_finalize(const float* partials, int frames, int tiles_per_frame, int H, int W, float* score,

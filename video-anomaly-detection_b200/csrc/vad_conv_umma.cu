@@ -426,7 +426,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
     const TileCoord t = decode_tile(a, tile, BN);
     float xpre[12];
     prefetch_x<EPI>(a, t, q, lane, xpre);
-    mbar_wait(&acc_full_bar[as], aphase);
+    mbar_wait(&acc_full_bar[as], aphase, 4);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
     epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xpre);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
         const int dy = (a.ntaps == 9) ? (tap / 3 - 1) : 0;
         const int dx = (a.ntaps == 9) ? (tap % 3 - 1) : 0;
         for (int c = 0; c < chunks; ++c) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
           if (elect_one()) {
             uint8_t* sa = smem + stage * C::kStageBytes;
             uint8_t* sb = sa + C::kABytes;
@@ -530,11 +530,11 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
-      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u);
+      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u, 3);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
       for (int k = 0; k < k_iters; ++k) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], phase, 2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile, BN);
-      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
       if (elect_one()) {
         uint8_t* sa = s_a + stage * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], patch_tx);
@@ -656,11 +656,11 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    mbar_wait(&w_bar, 0);
+    mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
-      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u);
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u, 3);
+      mbar_wait(&full_bar[stage], phase, 2);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -692,6 +692,188 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------- first conv
+// 3 -> 32 channel 3x3 conv straight from the fp32 NCHW model input.  K = 27 (padded to 32).  TMA brings the fp32
+// input patch of a tile (3 channels x 10 rows x 24 columns, zero-filled outside the frame = conv padding) into smem;
+// four converter warps turn it into the bf16 im2col A tile [128 pixels][32] in swizzled smem (27 shared loads with
+// immediate offsets per pixel); the MMA (two K=16 steps against the resident 32x32 weight tile) and the epilogue are
+// the same as everywhere else.  Replaces models/autoencoder.py:39-41 and models/video_autoencoder.py:193-196 (with
+// the 2x2 max-pool fused for the video encoder).
+constexpr int kFirstStages = 6;
+constexpr int kFirstThreads = 128 + 256 + 128;  // roles | two epilogue groups | four converter warps
+constexpr int kFirstConvWarp0 = 12;
+// fp32 patch: 24 columns x 10 rows x 3 channels starting at column w0-4: TMA needs the box's first byte 16-byte
+// aligned in the innermost dimension, so the 1-pixel left halo is fetched as part of an aligned group of four
+constexpr int kPatchW = 24, kPatchH = 10, kPatchX0 = 4;
+constexpr int kPatchBytes = 3 * kPatchH * kPatchW * 4;         // 2880
+constexpr int kPatchStride = 3072;                             // ring pitch
+
+template <int EPI>
+__global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int BN = 32;
+  constexpr int kABytes = kTileM * 64;  // 128 rows x 32 bf16
+  constexpr uint32_t kTmemCols = tmem_cols_for(BN);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t patch_full[kFirstStages];
+  __shared__ uint64_t patch_empty[kFirstStages];
+  __shared__ uint64_t full_bar[kFirstStages];
+  __shared__ uint64_t empty_bar[kFirstStages];
+  __shared__ uint64_t acc_full_bar[kAccStages];
+  __shared__ uint64_t acc_empty_bar[kAccStages];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float red_smem[2][4][3];
+  __shared__ __align__(16) float s_bias[kMaxBias];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;                                   // [32 n][32 k] bf16, 64B-swizzled (2 KB slot)
+  uint8_t* s_a = smem + 2048;                            // ring of A tiles
+  uint8_t* s_p = s_a + kFirstStages * kABytes;           // ring of fp32 input patches
+  uint8_t* stg = s_p + kFirstStages * kPatchStride;      // epilogue staging (1024-aligned: 6*3072 = 18 KB)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    if (a.tma_store) tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kFirstStages; ++i) {
+      mbar_init(&patch_full[i], 1);
+      mbar_init(&patch_empty[i], 4);  // one arrive per converter warp
+      mbar_init(&full_bar[i], 4);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kTmemCols>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  // weights: global bf16 [32][32] row-major -> swizzled smem (16-byte chunks)
+  if (threadIdx.x < 128) {
+    const int n = threadIdx.x >> 2, c16 = threadIdx.x & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(a.w_first)[threadIdx.x];
+    *reinterpret_cast<uint4*>(s_w + staged_off(n, c16, 32)) = v;
+  }
+  for (int i = threadIdx.x; i < BN; i += kFirstThreads) s_bias[i] = a.bias[i];
+  fence_proxy_async_smem();  // s_w is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA: fp32 input patches
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile, BN);
+      mbar_wait(&patch_empty[stage], phase ^ 1u, 7);
+      if (elect_one() && !(a.dbg & 1)) {
+        mbar_arrive_expect_tx(&patch_full[stage], kPatchBytes);
+        tma_load_4d(s_p + stage * kPatchStride, &a.mapA0, &patch_full[stage], t.w0 - kPatchX0, t.h0 - 1, 0, t.b0);
+      }
+      __syncwarp();
+      if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w), 512, 4u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u, 3);
+      mbar_wait(&full_bar[stage], phase, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint64_t da = umma_smem_desc(smem_u32(s_a + stage * kABytes), 512, 4u);
+        umma_bf16(d_tmem, da, db, idesc, 0u);
+        umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&acc_full_bar[as]);
+      }
+      __syncwarp();
+      if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= kFirstConvWarp0) {
+    // ===================================================================== converters: fp32 patch -> bf16 im2col rows
+    const int r = (warp - kFirstConvWarp0) * 32 + lane;  // pixel slot = A row
+    const int ww = r & 15, hh = r >> 4;                  // tile = 8 rows x 16 columns of one frame
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait(&patch_full[stage], phase, 6);
+      const float* pp = reinterpret_cast<const float*>(s_p + stage * kPatchStride) + hh * kPatchW + ww + (kPatchX0 - 1);
+      float v[27];  // k = (ky*3 + kx)*3 + ci
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+            v[(ky * 3 + kx) * 3 + ci] = (a.dbg & 2) ? 0.f : pp[ci * (kPatchH * kPatchW) + ky * kPatchW + kx];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&patch_empty[stage]);  // patch slot may be refilled
+      uint32_t p[16];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      p[13] = pack_bf16x2(v[26], 0.f);
+      p[14] = 0u;
+      p[15] = 0u;
+      mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+      uint8_t* sa = s_a + stage * kABytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(sa + staged_off(r, j, 32)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
+  constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_first_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  conv_first_kernel<EPI><<<grid, kFirstThreads, smem, stream>>>(a);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
+  if (EPI == VAD_EPI_STORE) return launch_first_one<VAD_EPI_STORE>(a, grid, stream);
+  if (EPI == VAD_EPI_POOL) return launch_first_one<VAD_EPI_POOL>(a, grid, stream);
+  return VAD_ERR_UNSUPPORTED;
+}
+
+int set_trap_slot(unsigned long long* device_ptr) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_vad_trap_slot, &device_ptr, sizeof(device_ptr)));
 }
 
 // ------------------------------------------------------------------------------------------------ host dispatch

@@ -36,6 +36,8 @@ struct alignas(64) ConvArgs {
   float* recon;
   float* heat;
   float* partials;
+  int dbg;              // bring-up switches (VAD_DBG environment variable)
+  const void* w_first;  // first conv: bf16 [32 n][32 k] weights, k = (ky*3+kx)*3+ci (27 real + 5 zero)
   // epilogue staging / TMA store
   int tma_store;  // 1: stage the bf16 tile in swizzled smem and store it with TMA (coalesced, clipped by hardware)
   int out_chunk;  // channels per staged chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
@@ -59,8 +61,10 @@ TileGeom pick_tile_geometry(int B, int H, int W, bool single_frame_tiles);
 
 int launch_conv_umma(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_conv_halo(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
+int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 // dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)
 int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);
+int set_trap_slot(unsigned long long* device_ptr);
 void count_launch();
 int sm_count();
 

@@ -50,12 +50,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (cudaErrorLaunchFailure) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Host-mapped debug slot (set by vad_api.cu): a wait that times out records {tag, block, thread, parity} there.
+// (one copy per translation unit; vad_conv_umma.cu, which holds every waiting kernel, sets its own)
+static __device__ unsigned long long* g_vad_trap_slot = nullptr;
+
+// Bounded wait: a protocol bug becomes a trap (sticky CUDA error) instead of a hung GPU.  `tag` names the wait site.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+    if (clock64() - t0 > 2000000000LL) {  // ~1 s at 2 GHz
+      if (g_vad_trap_slot) {
+        g_vad_trap_slot[0] = tag;
+        g_vad_trap_slot[1] = blockIdx.x;
+        g_vad_trap_slot[2] = threadIdx.x;
+        g_vad_trap_slot[3] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
 }
 
@@ -67,6 +80,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1,

@@ -6,6 +6,7 @@ only touches HBM when the caller asks for it.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -96,7 +97,15 @@ def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: 
     _timed(what or "vad_conv_layer", lambda: nat.conv_layer(d, what or "vad_conv_layer"))
 
 
+FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
+
+
 def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
+    if FIRST_CONV_TC and w.cout == 32 and w.w_tc is not None:
+        _timed("first_conv", lambda: nat.check(
+            nat.load().vad_first_conv_tc(x.data_ptr(), w.w_tc.data_ptr(), w.bias.data_ptr(), LEAKY, 1 if pool else 0,
+                                         B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv_tc"))
+        return
     _timed("first_conv", lambda: nat.check(
         nat.load().vad_first_conv(x.data_ptr(), w.w.data_ptr(), w.bias.data_ptr(), w.cout, LEAKY, 1 if pool else 0,
                                   B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv"))

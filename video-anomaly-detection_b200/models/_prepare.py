@@ -30,10 +30,12 @@ class GemmWeights:
 
 @dataclass
 class FirstConvWeights:
-    """3-channel first conv: `w` fp32 [27, cout] with k = (ky*3+kx)*3+ci, `bias` fp32 [cout]."""
+    """3-channel first conv: `w` fp32 [27, cout] with k = (ky*3+kx)*3+ci, `bias` fp32 [cout];
+    `w_tc` bf16 [cout, 32] (K padded 27 -> 32 with zeros) for the tensor-core kernel."""
     w: torch.Tensor
     bias: torch.Tensor
     cout: int
+    w_tc: Optional[torch.Tensor] = None
 
 
 def bn_scale_shift(sd: Mapping[str, torch.Tensor], bn: Optional[str], cout: int, ref: torch.Tensor
@@ -118,7 +120,10 @@ def pack_lstm(w: torch.Tensor, b: torch.Tensor, hid: int) -> GemmWeights:
 def pack_first_conv(w: torch.Tensor, b: torch.Tensor) -> FirstConvWeights:
     cout = w.shape[0]
     wk = w.permute(2, 3, 1, 0).reshape(27, cout)  # [ky,kx,ci,co]
-    return FirstConvWeights(wk.float().contiguous(), b.float().contiguous(), cout)
+    w_tc = torch.zeros(cout, 32, dtype=torch.float64, device=w.device)
+    w_tc[:, :27] = wk.t()
+    return FirstConvWeights(wk.float().contiguous(), b.float().contiguous(), cout,
+                            w_tc.to(torch.bfloat16).contiguous())
 
 
 def prepare_image(sd: Mapping[str, torch.Tensor]) -> Dict[str, object]:
@@ -164,5 +169,7 @@ def to_device(packed: Dict[str, object], device) -> Dict[str, object]:
         if isinstance(v, (GemmWeights, FirstConvWeights)):
             v.w = v.w.to(device)
             v.bias = v.bias.to(device)
+            if isinstance(v, FirstConvWeights) and v.w_tc is not None:
+                v.w_tc = v.w_tc.to(device)
         res[k] = v
     return res
