@@ -95,8 +95,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile, in
   return t;
 }
 
-__device__ __forceinline__ float act_fn(float v, float slope) { return v > 0.f ? v : v * slope; }
-__device__ __forceinline__ float sigmoid_fn(float v) { return 1.f / (1.f + __expf(-v)); }
+// LeakyReLU family with 0 <= slope <= 1 (0 = ReLU, 1 = identity): act(v) = max(v, slope*v)
+__device__ __forceinline__ float act_fn(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ float sigmoid_fn(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+// tanh(v) = 1 - 2 / (1 + e^{2v}) on the fast exp / reciprocal units: absolute error ~1e-7 (fp32 rounding of the
+// subtraction), saturates correctly to +-1 for large |v|
+__device__ __forceinline__ float tanh_fn(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
 
 // Byte offset of 16-byte chunk `c16` of row `row` in a staged tile whose rows are one swizzle span wide.
 __device__ __forceinline__ uint32_t staged_off(int row, int c16, int out_chunk) {
@@ -109,7 +113,14 @@ __device__ __forceinline__ uint32_t staged_off(int row, int c16, int out_chunk) 
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& t, uint32_t tacc, int q, int lane,
                                               uint8_t* stg, const float* s_bias, float (*red_smem)[3], int& stg_i,
-                                              uint32_t bar_id, const float* xpre) {
+                                              uint32_t bar_id, const float* xpre, uint64_t* acc_empty) {
+  // Hand the TMEM accumulator stage back to the MMA warp as soon as its last column is in registers: the rest of
+  // the epilogue (math, staging, stores) then overlaps the next tile's MMAs into the same stage.
+  auto release_acc = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty);
+  };
   const int r = q * 32 + lane;  // accumulator row = pixel slot in the tile
   const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
   const int ww = r & (TW - 1);
@@ -138,35 +149,46 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           uint32_t v[32];
           tmem_ld_x32(tacc + lc, v);
           tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (lc + 32 == BN) release_acc();
           if constexpr (EPI == VAD_EPI_POOL) {
+            // 2x2 max-pool as a reduce-scatter over the 4 lanes of a window: exchange halves with the horizontal
+            // neighbour (lane^1), then quarters with the vertical neighbour (lane^TW); each lane ends up owning the
+            // max of 8 channels and applies bias / activation / packing to those only.
+            const bool up1 = (ww & 1) != 0, up2 = (hh & 1) != 0;
+            float g[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-              f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], TW));
+            for (int j = 0; j < 16; ++j) {
+              const float lo = __uint_as_float(v[j]), hi = __uint_as_float(v[j + 16]);
+              const float recv = __shfl_xor_sync(0xffffffffu, up1 ? lo : hi, 1);
+              g[j] = fmaxf(up1 ? hi : lo, recv);
             }
-          }
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc);
-          uint32_t p[16];
+            float m[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = b4[j];
-            p[2 * j] = pack_bf16x2(act_fn(f[4 * j] + bv.x, a.slope), act_fn(f[4 * j + 1] + bv.y, a.slope));
-            p[2 * j + 1] = pack_bf16x2(act_fn(f[4 * j + 2] + bv.z, a.slope), act_fn(f[4 * j + 3] + bv.w, a.slope));
-          }
-          if constexpr (EPI == VAD_EPI_POOL) {
-            // the 4 lanes of a 2x2 window hold the same max; each writes one quarter (8 channels) of the pooled row
-            const int part = (ww & 1) | ((hh & 1) << 1);
+            for (int j = 0; j < 8; ++j) {
+              const float recv = __shfl_xor_sync(0xffffffffu, up2 ? g[j] : g[j + 8], TW);
+              m[j] = fmaxf(up2 ? g[j + 8] : g[j], recv);
+            }
+            const int part = (up1 ? 2 : 0) + (up2 ? 1 : 0);  // channels [8*part, 8*part+8) of this 32-column chunk
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc + part * 8);
+            const float4 b0 = b4[0], b1 = b4[1];
             const int prow = ((bb << (a.lgTH - 1)) + (hh >> 1)) * (TW >> 1) + (ww >> 1);
-            uint4 val;
-            if (part == 0) val = make_uint4(p[0], p[1], p[2], p[3]);
-            else if (part == 1) val = make_uint4(p[4], p[5], p[6], p[7]);
-            else if (part == 2) val = make_uint4(p[8], p[9], p[10], p[11]);
-            else val = make_uint4(p[12], p[13], p[14], p[15]);
+            const uint4 val = make_uint4(
+                pack_bf16x2(act_fn(m[0] + b0.x, a.slope), act_fn(m[1] + b0.y, a.slope)),
+                pack_bf16x2(act_fn(m[2] + b0.z, a.slope), act_fn(m[3] + b0.w, a.slope)),
+                pack_bf16x2(act_fn(m[4] + b1.x, a.slope), act_fn(m[5] + b1.y, a.slope)),
+                pack_bf16x2(act_fn(m[6] + b1.z, a.slope), act_fn(m[7] + b1.w, a.slope)));
             *reinterpret_cast<uint4*>(buf + staged_off(prow, sub * 4 + part, OC)) = val;
           } else {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc);
+            uint32_t p[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = b4[j];
+              p[2 * j] = pack_bf16x2(act_fn(__uint_as_float(v[4 * j]) + bv.x, a.slope),
+                                     act_fn(__uint_as_float(v[4 * j + 1]) + bv.y, a.slope));
+              p[2 * j + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * j + 2]) + bv.z, a.slope),
+                                         act_fn(__uint_as_float(v[4 * j + 3]) + bv.w, a.slope));
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(buf + staged_off(r, sub * 4 + j, OC)) =
@@ -197,6 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         uint32_t v[32];
         tmem_ld_x32(tacc + c * 32, v);
         tmem_ld_wait();
+        if (c * 32 + 32 == BN) release_acc();
         const int col = t.n0 + c * 32;
         float f[32];
 #pragma unroll
@@ -268,6 +291,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
       tmem_ld_x8(tacc + 64 + s * 8, gg);
       tmem_ld_x8(tacc + 96 + s * 8, go);
       tmem_ld_wait();
+      if (s == 3) release_acc();
       float cprev[8];
       if (valid && !a.lstm_first) {
         const float4 c0 = *reinterpret_cast<const float4*>(cptr + s * 8);
@@ -286,8 +310,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         const float xf = __uint_as_float(gf[e]) + bp[32 + e];
         const float xg = __uint_as_float(gg[e]) + bp[64 + e];
         const float xo = __uint_as_float(go[e]) + bp[96 + e];
-        cn[e] = sigmoid_fn(xf) * cprev[e] + sigmoid_fn(xi) * tanhf(xg);
-        hn[e] = sigmoid_fn(xo) * tanhf(cn[e]);
+        cn[e] = sigmoid_fn(xf) * cprev[e] + sigmoid_fn(xi) * tanh_fn(xg);
+        hn[e] = sigmoid_fn(xo) * tanh_fn(cn[e]);
       }
       const uint4 hv = make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
                                   pack_bf16x2(hn[6], hn[7]));
@@ -313,6 +337,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
     uint32_t v[16];
     tmem_ld_x16(tacc, v);
     tmem_ld_wait();
+    release_acc();
     float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
     if constexpr (EPI == VAD_EPI_TANH_SCORE) {
       if (valid) {
@@ -321,7 +346,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         float sq = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          const float rec = tanhf(__uint_as_float(v[ch]) + s_bias[ch]);
+          const float rec = tanh_fn(__uint_as_float(v[ch]) + s_bias[ch]);
           const float d = xpre[ch] - rec;
           sq += d * d;
           if (a.recon) a.recon[off + ch * plane] = rec;
@@ -339,8 +364,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           float sq0 = 0.f, sq1 = 0.f;
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            const float r0 = tanhf(__uint_as_float(v[(di * 2 + 0) * 3 + ch]) + s_bias[(di * 2 + 0) * 3 + ch]);
-            const float r1 = tanhf(__uint_as_float(v[(di * 2 + 1) * 3 + ch]) + s_bias[(di * 2 + 1) * 3 + ch]);
+            const float r0 = tanh_fn(__uint_as_float(v[(di * 2 + 0) * 3 + ch]) + s_bias[(di * 2 + 0) * 3 + ch]);
+            const float r1 = tanh_fn(__uint_as_float(v[(di * 2 + 1) * 3 + ch]) + s_bias[(di * 2 + 1) * 3 + ch]);
             const float d0 = xpre[(di * 3 + ch) * 2] - r0, d1 = xpre[(di * 3 + ch) * 2 + 1] - r1;
             sq0 += d0 * d0;
             sq1 += d1 * d1;
@@ -429,11 +454,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
     mbar_wait(&acc_full_bar[as], aphase, 4);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xpre);
-    // release this accumulator stage back to the MMA warp
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&acc_empty_bar[as]);
+    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xpre, &acc_empty_bar[as]);
   }
   if (q == 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this group have landed before the CTA exits
 }
