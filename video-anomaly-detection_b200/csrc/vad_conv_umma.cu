@@ -96,6 +96,47 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile, in
 }
 
 // LeakyReLU family with 0 <= slope <= 1 (0 = ReLU, 1 = identity): act(v) = max(v, slope*v)
+// Tile walker for the persistent loops: tile index = ((tb*tiles_h + th)*tiles_w + tw)*n_tiles + n_t advances by a
+// fixed step; the step is decomposed once (integer divisions) and then added component-wise with carries, so the
+// per-tile cost is a handful of adds instead of three division sequences per role.
+struct TileIter {
+  int tile, step;
+  int n_t, tw, th, tb;
+  int dn, dw, dh, db;
+  __device__ __forceinline__ TileIter(const ConvArgs& a, int first, int step_) : tile(first), step(step_) {
+    int v = first;
+    n_t = v % a.n_tiles; v /= a.n_tiles;
+    tw = v % a.tiles_w; v /= a.tiles_w;
+    th = v % a.tiles_h; tb = v / a.tiles_h;
+    v = step_;
+    dn = v % a.n_tiles; v /= a.n_tiles;
+    dw = v % a.tiles_w; v /= a.tiles_w;
+    dh = v % a.tiles_h; db = v / a.tiles_h;
+  }
+  __device__ __forceinline__ void next(const ConvArgs& a) {
+    tile += step;
+    n_t += dn;
+    int c = n_t >= a.n_tiles;
+    n_t -= c ? a.n_tiles : 0;
+    tw += dw + c;
+    c = tw >= a.tiles_w;
+    tw -= c ? a.tiles_w : 0;
+    th += dh + c;
+    c = th >= a.tiles_h;
+    th -= c ? a.tiles_h : 0;
+    tb += db + c;
+  }
+  __device__ __forceinline__ TileCoord coord(const ConvArgs& a, int bn) const {
+    TileCoord t;
+    t.n0 = n_t * bn;
+    t.w0 = tw << a.lgTW;
+    t.h0 = th << a.lgTH;
+    t.b0 = tb << a.lgTN;
+    t.m_tile = (tb * a.tiles_h + th) * a.tiles_w + tw;
+    return t;
+  }
+};
+
 __device__ __forceinline__ float act_fn(float v, float slope) { return fmaxf(v, v * slope); }
 __device__ __forceinline__ float sigmoid_fn(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 // tanh(v) = 1 - 2 / (1 + e^{2v}) on the fast exp / reciprocal units: absolute error ~1e-7 (fp32 rounding of the
@@ -204,7 +245,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           } else if constexpr (EPI == VAD_EPI_POOL) {
             tma_store_5d(&a.mapOut, buf, col, t.w0 >> 1, t.h0 >> 1, 0, t.b0);
           } else {  // ConvT pixel shuffle: map dims {co, dj, w, di, b*H + h}
-            const int quad = col / a.cout;
+            const int quad = (col >= a.cout) + (col >= 2 * a.cout) + (col >= 3 * a.cout);
             tma_store_5d(&a.mapOut, buf, col - quad * a.cout, quad & 1, t.w0, quad >> 1, t.b0 * a.H + t.h0);
           }
           bulk_commit_group();
@@ -258,7 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           }
         } else {  // VAD_EPI_CONVT: column = quad*cout + co, quad = di*2 + dj
           if (valid) {
-            const int quad = col / a.cout;
+            const int quad = (col >= a.cout) + (col >= 2 * a.cout) + (col >= 3 * a.cout);
             const int co = col - quad * a.cout;
             const int ho = 2 * h + (quad >> 1), wo = 2 * w + (quad & 1);
             uint4* dst = reinterpret_cast<uint4*>(outp + fb * a.out_fs +
@@ -443,18 +484,22 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
   const int q = warp & 3;  // TMEM lane quarter == warp_id % 4
   uint8_t* my_stg = stg + g * staging_group_bytes(BN, EPI);
   int stg_i = 0;
-  int it = 0;  // CTA-local tile counter
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-    if (G == 2 && (it & 1) != g) continue;
-    const int as = (G == 2) ? g : (it & 1);
-    const uint32_t aphase = (G == 2) ? ((it >> 1) & 1) : ((it >> 1) & 1);
-    const TileCoord t = decode_tile(a, tile, BN);
-    float xpre[12];
-    prefetch_x<EPI>(a, t, q, lane, xpre);
+  // group g walks tiles g, g+G, ... of this CTA; the x pixels a score epilogue needs are fetched one tile ahead
+  TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x);
+  float xcur[12], xnext[12];
+  if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xcur);
+  for (int n = 0; ti.tile < a.total_tiles; ++n) {
+    const int as = (G == 2) ? g : (n & 1);
+    const uint32_t aphase = (G == 2) ? (n & 1) : ((n >> 1) & 1);
+    const TileCoord t = ti.coord(a, BN);
+    ti.next(a);
+    if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xnext);
     mbar_wait(&acc_full_bar[as], aphase, 4);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xpre, &acc_empty_bar[as]);
+    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xcur, &acc_empty_bar[as]);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) xcur[j] = xnext[j];
   }
   if (q == 0 && lane == 0) bulk_wait_group<0>();  // all TMA stores of this group have landed before the CTA exits
 }
@@ -519,8 +564,8 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(a, tile, BN);
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      const TileCoord t = ti.coord(a, BN);
       for (int tap = 0; tap < a.ntaps; ++tap) {
         int kcol = tap * a.w_ctap;
         const int dy = (a.ntaps == 9) ? (tap / 3 - 1) : 0;
@@ -651,8 +696,8 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(a, tile, BN);
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      const TileCoord t = ti.coord(a, BN);
       mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
       if (elect_one()) {
         uint8_t* sa = s_a + stage * stage_bytes;
@@ -793,8 +838,8 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     // ===================================================================== TMA: fp32 input patches
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(a, tile, BN);
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      const TileCoord t = ti.coord(a, BN);
       mbar_wait(&patch_empty[stage], phase ^ 1u, 7);
       if (elect_one() && !(a.dbg & 1)) {
         mbar_arrive_expect_tx(&patch_full[stage], kPatchBytes);
