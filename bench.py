@@ -182,7 +182,7 @@ def cpu_baseline(kind, T, H, W, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -270,7 +270,6 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel timing for the roofline (CUDA events around every launch, same inputs)
     eng.PROFILE = []
@@ -339,6 +338,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None  # sampled across the device-resident and the end-to-end timed regions
 
     if rank != 0:
         if world > 1:

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds/loads here and exports exactly what include/vad_b200.h declares; argument errors are
+reported as codes (no compute calls — there is no GPU in this container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "vad_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vad_[a-z0-9_]+)\s*\(", src)) - {"vad_stream_t"})
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from models import _native as nat
+    if not os.path.exists(nat.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return nat.load()
+
+
+def test_header_and_binding_agree(lib):
+    from models import _native as nat
+    declared = _header_functions()
+    assert declared == sorted(nat.EXPORTS), (declared, sorted(nat.EXPORTS))
+    for name in declared:
+        assert hasattr(lib, name), f"libvad_b200.so does not export {name}"
+
+
+def test_struct_layout_matches_c(tmp_path, lib):
+    """sizeof/offsetof of vad_conv_desc as the C compiler sees it == the ctypes mirror."""
+    import subprocess
+    from models._native import ConvDesc
+    prog = tmp_path / "sz.c"
+    fields = [f[0] for f in ConvDesc._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(vad_conv_desc, {f}));' for f in fields)
+    prog.write_text('#include "vad_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                    f'int main(){{printf("%zu\\n", sizeof(vad_conv_desc));{body}return 0;}}')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert vals[0] == ctypes.sizeof(ConvDesc)
+    assert vals[1:] == [getattr(ConvDesc, f).offset for f in fields]
+
+
+def test_argument_errors_are_codes_not_crashes(lib):
+    assert lib.vad_version() >= 100
+    assert lib.vad_error_string(0) == b"ok"
+    assert b"unsupported" in lib.vad_error_string(-2).lower() or b"shape" in lib.vad_error_string(-2).lower()
+    assert lib.vad_conv_layer(None, None) == -1
+    assert lib.vad_conv_m_tiles(0, 16, 16, 0) == -1
+    assert lib.vad_conv_m_tiles(2, 256, 256, 1) == 2 * 512
+    assert lib.vad_score_scratch_bytes(0, 16, 16) == 0
+    assert lib.vad_score_scratch_bytes(4, 256, 256) == 4 * 8 * 16
+    assert lib.vad_first_conv(None, None, None, 32, 0.2, 0, 1, 16, 16, None, None) == -1
+    assert lib.vad_score(None, None, 1, 16, 16, None, None, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    from models import ConvAutoencoder
+    m = ConvAutoencoder().eval()
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        m.get_reconstruction_error(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        m(torch.zeros(1, 3, 32, 32))

@@ -180,6 +180,27 @@ def test_video_medium_vs_oracle(cuda_device, stress):
     assert bad == 0 and checked > 0
 
 
+def test_video_720p_window_vs_oracle(cuda_device):
+    """BASELINE cfg4 shape (1280x720 frames; latent 45x80 is not a multiple of the 8-row tile: partial tiles, the
+    direct-store ConvT fallback and the non-power-of-two ConvLSTM grid are all exercised).  4-frame window."""
+    m = make_video_model(cuda_device, stress=True)
+    x = video_input(777, 1, 4, 720, 1280)
+    sd = vad_oracle.cpu_sd(m.state_dict())
+    with torch.no_grad():
+        ref_map = vad_oracle.video_reconstruction_error(sd, x, per_pixel=True).numpy()
+    ref = ref_map.mean(axis=(2, 3, 4))
+    out = m.score_all(x.to(cuda_device))
+    frame = out.score.cpu().numpy().reshape(1, 4)
+    print(f"\nvideo 1x4x720x1280 stress: frame-score rel {rel_err(frame, ref):.3g}")
+    assert rel_err(frame, ref) <= SCORE_RTOL_STRESS
+    heat = out.heat.cpu().numpy()
+    nd = np.abs(norm_map(heat) - norm_map(ref_map[0, :, 0]))
+    assert nd.mean() <= 2e-2
+    mm = out.minmax.cpu().numpy()
+    np.testing.assert_array_equal(mm[:, 0], heat.min(axis=(1, 2)))
+    np.testing.assert_array_equal(mm[:, 1], heat.max(axis=(1, 2)))
+
+
 def test_full_size_properties_cfg2(cuda_device):
     """BASELINE cfg2 (batch 256 of 256x256): determinism, batch-partition invariance, map/score consistency."""
     m = make_image_model(cuda_device, stress=True)

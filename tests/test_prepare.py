@@ -1,0 +1,153 @@
+"""CPU: host-side weight preparation (BN folding + GEMM repacking) checked against the oracle.
+
+A tiny torch emulator below executes the EXACT GEMM formulation the kernels implement (same K ordering, pixel-shuffle
+column order, ConvLSTM gate-row permutation, zero-padded rows) on the packed operands; it must reproduce the oracle's
+reference arithmetic up to the bf16 rounding of the weights.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from models import _prepare as prep
+from oracle import vad_oracle
+from oracle.stress import stress_state_dict
+
+
+def _image_sd(stress=True):
+    from models import ConvAutoencoder
+    torch.manual_seed(0)
+    sd = ConvAutoencoder().state_dict()
+    return stress_state_dict(sd, seed=1) if stress else sd
+
+
+def _video_sd(stress=True, **kw):
+    from models.video_autoencoder import VideoAutoencoder
+    torch.manual_seed(0)
+    sd = VideoAutoencoder(**kw).state_dict()
+    return stress_state_dict(sd, seed=1) if stress else sd
+
+
+def im2col3x3(x):  # x NHWC fp32 -> [N,H,W,9*C] with K = (ky*3+kx)*C + c, zero padding
+    n, h, w, c = x.shape
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+    return torch.cat([xp[:, ky:ky + h, kx:kx + w, :] for ky in range(3) for kx in range(3)], dim=-1)
+
+
+def emu_conv(g, x, slope, pool=False):
+    y = im2col3x3(x) @ g.w.float().t() + g.bias
+    if pool:
+        n, h, w, c = y.shape
+        y = y.view(n, h // 2, 2, w // 2, 2, c).amax(dim=(2, 4))
+    y = torch.maximum(y, y * slope)
+    return y[..., :g.n_total]
+
+
+def emu_convt(g, x, slope):
+    n, h, w, c = x.shape
+    y = x @ g.w.float().t() + g.bias                       # [n,h,w,4*cout(+pad)]
+    y = torch.maximum(y, y * slope)[..., :4 * g.cout]
+    y = y.view(n, h, w, 2, 2, g.cout).permute(0, 1, 3, 2, 4, 5)   # n, h, di, w, dj, co
+    return y.reshape(n, 2 * h, 2 * w, g.cout)
+
+
+def emu_first(fw, x_nchw, pool):
+    x = x_nchw.permute(0, 2, 3, 1)
+    y = im2col3x3(x) @ fw.w + fw.bias                       # fw.w is [27, cout]
+    y_tc = im2col3x3(x) @ fw.w_tc.float()[:, :27].t() + fw.bias
+    assert torch.allclose(y, y_tc, rtol=2e-2, atol=2e-2)    # the two packings describe the same layer
+    assert float(fw.w_tc.float()[:, 27:].abs().max()) == 0.0
+    if pool:
+        n, h, w, c = y.shape
+        y = y.view(n, h // 2, 2, w // 2, 2, c).amax(dim=(2, 4))
+    return torch.maximum(y, y * 0.2)
+
+
+def test_image_packing_reproduces_oracle():
+    sd = _image_sd()
+    p = prep.prepare_image(sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    a = emu_first(p["enc1.0"], x, pool=False)
+    a = emu_conv(p["enc1.3"], a, 0.2, pool=True)
+    for blk in ("enc2", "enc3", "enc4"):
+        a = emu_conv(p[f"{blk}.0"], a, 0.2)
+        a = emu_conv(p[f"{blk}.3"], a, 0.2, pool=True)
+    with torch.no_grad():
+        ref_lat = vad_oracle.image_encoder(sd, x)
+    assert (a.permute(0, 3, 1, 2) - ref_lat).abs().max() <= 0.03 * ref_lat.abs().max()
+    for blk in ("dec1", "dec2", "dec3"):
+        a = emu_convt(p[f"{blk}.0"], a, 0.0)
+        a = emu_conv(p[f"{blk}.3"], a, 0.0)
+    a = emu_convt(p["dec4.0"], a, 0.0)
+    last = p["dec4.3"]
+    assert last.n_total == 16 and last.cout == 3 and float(last.w[3:].float().abs().max()) == 0.0
+    rec = torch.tanh(im2col3x3(a) @ last.w.float().t() + last.bias)[..., :3].permute(0, 3, 1, 2)
+    with torch.no_grad():
+        ref = vad_oracle.image_forward(sd, x)
+    assert (rec - ref).abs().mean() < 5e-3 and (rec - ref).abs().max() < 0.1
+
+
+@pytest.mark.parametrize("kw", [{}, dict(latent_dim=128, lstm_hidden_dim=64, lstm_num_layers=1)])
+def test_video_packing_reproduces_oracle(kw):
+    sd = _video_sd(**kw)
+    p = prep.prepare_video(sd)
+    g = torch.Generator().manual_seed(5)
+    b, t = 2, 3
+    x = torch.rand(b, t, 3, 32, 32, generator=g) * 2 - 1
+    a = emu_first(p["enc.0"], x.view(b * t, 3, 32, 32), pool=True)
+    for i in (4, 8, 12):
+        a = emu_conv(p[f"enc.{i}"], a, 0.2, pool=True)
+    seq = a.view(b, t, *a.shape[1:])
+    for layer in range(p["lstm_layers"]):
+        gw = p[f"lstm.{layer}"]
+        hid = gw.cout
+        h = torch.zeros(b, *seq.shape[2:4], hid)
+        c = torch.zeros_like(h)
+        outs = []
+        for ti in range(t):
+            gates = im2col3x3(torch.cat([seq[:, ti], h], dim=-1)) @ gw.w.float().t() + gw.bias
+            # kernel column layout: tiles of 128 = [gate][32 channels]
+            gt = gates.view(*gates.shape[:-1], hid // 32, 4, 32)
+            gi, gf, gg, go = (gt[..., k, :].reshape(*gates.shape[:-1], hid) for k in range(4))
+            c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+            h = torch.sigmoid(go) * torch.tanh(c)
+            outs.append(h)
+        seq = torch.stack(outs, dim=1)
+    a = seq.reshape(b * t, *seq.shape[2:])
+    if "proj" in p:
+        a = a @ p["proj"].w.float().t() + p["proj"].bias
+    for i in (0, 3, 6):
+        a = emu_convt(p[f"dec.{i}"], a, 0.0)
+    last = p["dec.9"]
+    assert last.n_total == 16 and last.cout == 3
+    y = torch.tanh(a @ last.w.float().t() + last.bias)[..., :12]
+    n, h, w, _ = y.shape
+    rec = y.view(n, h, w, 2, 2, 3).permute(0, 5, 1, 3, 2, 4).reshape(n, 3, 2 * h, 2 * w).view(b, t, 3, 32, 32)
+    with torch.no_grad():
+        ref = vad_oracle.video_forward(sd, x)
+    assert (rec - ref).abs().mean() < 5e-3 and (rec - ref).abs().max() < 0.1
+
+
+def test_bn_fold_is_exact_in_fp64():
+    sd = _image_sd()
+    w, b = prep.fold_conv(sd, "encoder.enc2.0", "encoder.enc2.1")
+    x = torch.randn(1, 32, 8, 8, dtype=torch.float64)
+    sd64 = vad_oracle.to_dtype(sd, torch.float64)
+    ref = vad_oracle._bn_eval(sd64, "encoder.enc2.1", vad_oracle._conv3x3(sd64, "encoder.enc2.0", x))
+    got = F.conv2d(x, w, b, padding=1)
+    assert torch.allclose(got, ref, rtol=1e-10, atol=1e-10)
+    wt, bt = prep.fold_convt(sd, "decoder.dec2.0", "decoder.dec2.1")
+    z = torch.randn(1, 128, 4, 4, dtype=torch.float64)
+    ref = vad_oracle._bn_eval(sd64, "decoder.dec2.1", vad_oracle._convt2x2(sd64, "decoder.dec2.0", z))
+    assert torch.allclose(F.conv_transpose2d(z, wt, bt, stride=2), ref, rtol=1e-10, atol=1e-10)
+
+
+def test_lstm_row_permutation_is_a_permutation():
+    for hid in (32, 64, 128):
+        perm = prep.lstm_row_permutation(hid)
+        assert sorted(perm.tolist()) == list(range(4 * hid))
+        # first tile: gate-major, 32 channels each
+        assert perm[:32].tolist() == list(range(0, 32)) and perm[32:64].tolist() == list(range(hid, hid + 32))
+    with pytest.raises(ValueError):
+        prep.lstm_row_permutation(48)

@@ -1,0 +1,62 @@
+"""CPU: the N>1 host logic — block partition and the score gather — on world_size-2/3 gloo process groups."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from runtime.sharding import ShardPlan, gather_scores, shard_range
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 7, 8, 10000, 10001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_range(10000, 3, 8) == (3750, 5000)  # BASELINE cfg5: 1250 clips per GPU
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _fake_frame_scores(lo, hi, t):
+    """Deterministic stand-in for model.get_reconstruction_error(clips[lo:hi], per_frame=True)."""
+    idx = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1)
+    return (idx * 0.001 + torch.arange(t, dtype=torch.float32).view(1, -1) * 1e-5 + 0.25).contiguous()
+
+
+def _worker(rank, world, n_items, t, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = ShardPlan(n_items, world)
+        lo, hi = plan.range(rank)
+        local = _fake_frame_scores(lo, hi, t)
+        full = gather_scores(local, plan, rank, dst=0)
+        if rank == 0:
+            torch.save(full, out_path)
+        else:
+            assert full is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_items", [(2, 10), (2, 7), (3, 8)])
+def test_gather_scores_matches_single_process(tmp_path, world, n_items):
+    t = 4
+    out = str(tmp_path / "gathered.pt")
+    port = 29500 + (os.getpid() + world * 7 + n_items) % 2000
+    mp.spawn(_worker, args=(world, n_items, t, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    assert torch.equal(got, _fake_frame_scores(0, n_items, t)), "sharded + gathered must equal the 1-process result"
+
+
+def test_single_rank_is_identity():
+    x = torch.arange(6.0).view(3, 2)
+    assert gather_scores(x, ShardPlan(3, 1), 0) is x

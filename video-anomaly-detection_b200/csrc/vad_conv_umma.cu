@@ -25,7 +25,7 @@ namespace vad {
 
 constexpr int kEpiWarp0 = 4;  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, spare
 constexpr int kTileM = 128;
-constexpr int kAccStages = 2;
+constexpr int kMaxAccStages = 4;
 constexpr int kStagingBuf = 16384;  // one staged output chunk: 128 rows x 128 B
 constexpr int kMaxBias = 512;
 constexpr int kSmemBudget = 227 * 1024 - 4096;  // dynamic smem we allow ourselves (static smem + slack kept free)
@@ -33,10 +33,12 @@ constexpr int kSmemBudget = 227 * 1024 - 4096;  // dynamic smem we allow ourselv
 __host__ __device__ constexpr bool epi_uses_staging(int epi) {
   return epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_CONVT || epi == VAD_EPI_LSTM;
 }
-// Epilogue warps come in groups of four (one warp per TMEM lane quarter).  Narrow tiles are epilogue-bound, so they
-// get two groups that take alternate tiles (group g owns accumulator stage g); 256-wide tiles are MMA-bound and
-// keep one group (and the smem for a deeper operand ring).
-__host__ __device__ constexpr int epi_groups(int bn) { return bn >= 256 ? 1 : 2; }
+// Epilogue warps come in groups of four (one warp per TMEM lane quarter); group g takes this CTA's tiles g, g+G, ...
+// and owns TMEM accumulator stage g.  The narrowest tiles (N <= 32: full-resolution layers, thousands of tiny tiles
+// per SM) are bound by epilogue latency and get four groups, mid-size tiles two, and 256-wide tiles (MMA-bound) one
+// group plus the smem for a deeper operand ring.
+__host__ __device__ constexpr int epi_groups(int bn) { return bn >= 256 ? 1 : (bn <= 32 ? 4 : 2); }
+__host__ __device__ constexpr int acc_stages_for(int groups) { return groups < 2 ? 2 : groups; }
 __host__ __device__ constexpr int block_threads(int bn) { return 128 + 128 * epi_groups(bn); }
 // staged-output buffers per epilogue group
 __host__ __device__ constexpr int staging_bufs(int bn, int epi) {
@@ -49,11 +51,12 @@ __host__ __device__ constexpr int staging_buf_bytes(int bn, int epi) {
 __host__ __device__ constexpr int staging_group_bytes(int bn, int epi) {
   return staging_bufs(bn, epi) * staging_buf_bytes(bn, epi);
 }
-__host__ __device__ constexpr int staging_bytes(int bn, int epi) {
-  return epi_groups(bn) * staging_group_bytes(bn, epi);
+__host__ __device__ constexpr int staging_bytes(int bn, int epi, int groups = 0) {
+  return (groups ? groups : epi_groups(bn)) * staging_group_bytes(bn, epi);
 }
-__host__ __device__ constexpr uint32_t tmem_cols_for(int bn) {
-  return (2 * bn <= 32) ? 32u : (2 * bn <= 64) ? 64u : (2 * bn <= 128) ? 128u : (2 * bn <= 256) ? 256u : 512u;
+__host__ __device__ constexpr uint32_t tmem_cols_for(int bn, int groups = 0) {
+  const int c = acc_stages_for(groups ? groups : epi_groups(bn)) * bn;
+  return (c <= 32) ? 32u : (c <= 64) ? 64u : (c <= 128) ? 128u : (c <= 256) ? 256u : 512u;
 }
 
 template <int CK, int BN, int EPI>
@@ -475,11 +478,10 @@ __device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t
 
 // Shared body of the epilogue warps.  Group g (warps 4+4g .. 7+4g) handles this CTA's tiles g, g+G, g+2G, ...;
 // with G = 2 each group owns one TMEM accumulator stage.
-template <int BN, int EPI>
+template <int BN, int EPI, int G = epi_groups(BN)>
 __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_base, int warp, int lane, uint8_t* stg,
                                               const float* s_bias, float (*red_smem)[4][3], uint64_t* acc_full_bar,
                                               uint64_t* acc_empty_bar) {
-  constexpr int G = epi_groups(BN);
   const int g = (warp - kEpiWarp0) >> 2;
   const int q = warp & 3;  // TMEM lane quarter == warp_id % 4
   uint8_t* my_stg = stg + g * staging_group_bytes(BN, EPI);
@@ -489,8 +491,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
   float xcur[12], xnext[12];
   if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xcur);
   for (int n = 0; ti.tile < a.total_tiles; ++n) {
-    const int as = (G == 2) ? g : (n & 1);
-    const uint32_t aphase = (G == 2) ? (n & 1) : ((n >> 1) & 1);
+    const int as = (G >= 2) ? g : (n & 1);
+    const uint32_t aphase = (G >= 2) ? (n & 1) : ((n >> 1) & 1);
     const TileCoord t = ti.coord(a, BN);
     ti.next(a);
     if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xnext);
@@ -513,13 +515,14 @@ __device__ __forceinline__ void load_bias_smem(const ConvArgs& a, float* s_bias,
 template <int CK, int BN, int EPI>
 __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   using C = Cfg<CK, BN, EPI>;
+  constexpr int kAS = acc_stages_for(epi_groups(BN));
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[C::kStages];
   __shared__ uint64_t empty_bar[C::kStages];
-  __shared__ uint64_t acc_full_bar[kAccStages];
-  __shared__ uint64_t acc_empty_bar[kAccStages];
+  __shared__ uint64_t acc_full_bar[kMaxAccStages];
+  __shared__ uint64_t acc_empty_bar[kMaxAccStages];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[2][4][3];
+  __shared__ float red_smem[4][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
   const int warp = threadIdx.x >> 5;
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);  // one arrive per warp of the owning epilogue group
     }
@@ -595,8 +598,8 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u, 3);
+      const int as = it % kAS;
+      mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
       for (int k = 0; k < k_iters; ++k) {
@@ -640,15 +643,16 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
   constexpr int kBBytes = BN * kRowBytes;  // one tap's weight slab
   constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;
   constexpr uint32_t kTmemCols = tmem_cols_for(BN);
+  constexpr int kAS = acc_stages_for(epi_groups(BN));
   static_assert(kBBytes % 1024 == 0, "weight slab must keep 1024B alignment");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_bar;
   __shared__ uint64_t full_bar[kHaloMaxStages];
   __shared__ uint64_t empty_bar[kHaloMaxStages];
-  __shared__ uint64_t acc_full_bar[kAccStages];
-  __shared__ uint64_t acc_empty_bar[kAccStages];
+  __shared__ uint64_t acc_full_bar[kMaxAccStages];
+  __shared__ uint64_t acc_empty_bar[kMaxAccStages];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[2][4][3];
+  __shared__ float red_smem[4][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
   const int warp = threadIdx.x >> 5;
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);
     }
@@ -724,8 +728,8 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     int it = 0;
     mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u, 3);
+      const int as = it % kAS;
+      mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
       mbar_wait(&full_bar[stage], phase, 2);
       tc_fence_after();
       if (elect_one()) {
@@ -779,17 +783,19 @@ constexpr int kPatchStride = 3072;                             // ring pitch
 template <int EPI>
 __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int BN = 32;
+  constexpr int kFirstGroups = 2;       // 16 warps are already spoken for (roles, converters): two epilogue groups
+  constexpr int kAS = acc_stages_for(kFirstGroups);
   constexpr int kABytes = kTileM * 64;  // 128 rows x 32 bf16
-  constexpr uint32_t kTmemCols = tmem_cols_for(BN);
+  constexpr uint32_t kTmemCols = tmem_cols_for(BN, kFirstGroups);
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t patch_full[kFirstStages];
   __shared__ uint64_t patch_empty[kFirstStages];
   __shared__ uint64_t full_bar[kFirstStages];
   __shared__ uint64_t empty_bar[kFirstStages];
-  __shared__ uint64_t acc_full_bar[kAccStages];
-  __shared__ uint64_t acc_empty_bar[kAccStages];
+  __shared__ uint64_t acc_full_bar[kMaxAccStages];
+  __shared__ uint64_t acc_empty_bar[kMaxAccStages];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[2][4][3];
+  __shared__ float red_smem[4][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
   const int warp = threadIdx.x >> 5;
@@ -811,7 +817,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       mbar_init(&full_bar[i], 4);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);
     }
@@ -856,8 +862,8 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      mbar_wait(&acc_empty_bar[as], ((it >> 1) & 1) ^ 1u, 3);
+      const int as = it % kAS;
+      mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
       mbar_wait(&full_bar[stage], phase, 2);
       tc_fence_after();
       if (elect_one()) {
@@ -907,7 +913,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
+    epilogue_loop<BN, EPI, kFirstGroups>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
   }
 
   tc_fence_before();
@@ -920,7 +926,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
 
 template <int EPI>
 static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
-  constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI);
+  constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI, 2);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_first_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
