@@ -300,7 +300,11 @@ def main():
                 "unit": "TFLOP/s"}
     else:
         roof = {"bound": "hbm", "achieved": round(byts / (avg_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s"}
-    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": None, "kernel": top_name,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(tpath):  # measured once with ncu --set full at this exact shape (see profiles/)
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(top["rep"])
+    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": traffic, "kernel": top_name,
                  "launch_ms": round(avg_ms, 4), "share_of_step": round(top["ms"] / total_kernel_ms, 3),
                  "peak_src": pk["src"], "alg_flops_per_launch": flops, "alg_bytes_per_launch": byts,
                  "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}})
