@@ -132,12 +132,10 @@ def layer_cost(kind, name, B, T, H, W):
         "decoder.3": (128, 64, 8, 1, "convt", False), "decoder.6": (64, 32, 4, 1, "convt", False),
         "decoder.9+score": (32, 3, 2, 1, "scoret", False),
     }
-    if name.startswith("convlstm."):
+    if name.startswith("convlstm."):  # one launch group = the T steps of one layer (step 0 skips the h half of K)
         h, w = H // 16, W // 16
-        first = name.endswith(".t0")
-        k = 9 * (128 if first else 256)
-        flops = 2.0 * B * h * w * 512 * k
-        byts = B * h * w * (128 * 2 * (1 if first else 2) + 128 * 2 + 128 * 4 * (1 if first else 2))
+        flops = 2.0 * B * h * w * 512 * 9 * (128 + 256 * (T - 1))
+        byts = B * h * w * ((128 * 2 * 2 + 128 * 2 + 128 * 4 * 2) * T - 128 * 2 - 128 * 4)
         return flops, byts
     cin, cout, div, taps, typ, pooled = img[name]
     h, w = H // div, W // div
@@ -284,8 +282,6 @@ def main():
     kern = {}
     for name, ts in per.items():
         key = name
-        if name.startswith("convlstm."):
-            key = name.rsplit(".t", 1)[0] + (".t0" if name.endswith(".t0") else ".t1+")
         d = kern.setdefault(key, {"ms": 0.0, "launches": 0, "rep": name})
         d["ms"] += statistics.median(ts)
         d["launches"] += 1

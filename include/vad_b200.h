@@ -37,6 +37,9 @@ unsigned long long vad_launch_count(void);
 /* Bring-up aid: if a kernel's bounded mbarrier wait timed out (the kernel then traps), out = {wait-site tag,
  * blockIdx.x, threadIdx.x, parity}; all zero otherwise.  Readable even after the CUDA context reports an error. */
 int vad_debug_last_trap(unsigned long long out[4]);
+/* Bring-up aid: when set, CTA 0 of every vad_conv_layer kernel stamps clock64 at role events of its first 64 tiles
+ * into device_buf[4 roles][64][8] (role 0 TMA producer, 1 MMA issuer, 2/3 epilogue group 0/1).  NULL disables. */
+int vad_debug_set_timeline(long long* device_buf);
 
 /* ---- one convolution-as-GEMM layer ----------------------------------------------------------------------------
  * Implicit-GEMM on tcgen05/TMEM fed by TMA.  M = B*H*W input pixels (tiles of 128), N = n_total, K = ntaps*(c0+c1).
@@ -86,6 +89,11 @@ typedef struct vad_conv_desc {
 } vad_conv_desc;
 
 int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
+/* One ConvLSTM layer over a whole sequence (reference ConvLSTM.forward time loop, models/video_autoencoder.py:153-167):
+ * T launches of the VAD_EPI_LSTM layer with the tensor maps encoded once.  `d` describes a step t >= 1: src0 = input
+ * sequence bf16 [B][T][h][w][c0] (T0 = T), src1 = out = hidden sequence bf16 [B][T][h][w][hid] (T1 = T, c1 = hid,
+ * out_frame_stride = T*h*w*hid), c_state fp32 [B][h][w][hid]; zero initial state. */
+int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream);
 /* number of 128-pixel tiles (rows of `partials`) a *_SCORE layer produces for (B,H,W) input */
 int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles);
 

@@ -137,6 +137,11 @@ static int halo_mode_setting() {
   static int v = env_int("VAD_HALO", 1);
   return v;
 }
+// VAD_DUAL_MMA bit mask: 1 halo kernel, 2 first conv, 4 streaming kernel (short k-loops only)
+static int dual_mma_setting() {
+  static int v = env_int("VAD_DUAL_MMA", 1);
+  return v;
+}
 static int tma_store_setting() {
   static int v = env_int("VAD_TMA_STORE", 1);
   return v;
@@ -390,6 +395,12 @@ int vad_version(void) { return 100; }
 
 unsigned long long vad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+static long long* g_timeline = nullptr;
+int vad_debug_set_timeline(long long* device_buf) {  // 4 roles x 64 tiles x 8 events; NULL disables
+  g_timeline = device_buf;
+  return VAD_OK;
+}
+
 int vad_debug_last_trap(unsigned long long out[4]) {
   if (!g_trap_host || !out) return VAD_ERR_ARG;
   for (int i = 0; i < 4; ++i) out[i] = g_trap_host[i];
@@ -401,8 +412,22 @@ int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles) {
   return pick_tile_geometry(B, H, W, force_single_frame_tiles != 0).m_tiles();
 }
 
-int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+}  // extern "C"
+
+namespace {
+struct ConvLaunch {
+  ConvArgs a;
+  int CK, BN, epi, grid;
+  bool use_halo;
+};
+
+int launch_built(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.use_halo) return launch_conv_halo(L.CK, L.BN, L.epi, L.a, L.grid, stream);
+  return launch_conv_umma(L.CK, L.BN, L.epi, L.a, L.grid, stream);
+}
+
+// Validates a layer description and fills the kernel argument block (tensor maps, tile geometry, kernel choice).
+int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   if (!d || !d->src0 || !d->weight || !d->bias) return VAD_ERR_ARG;
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->n_total <= 0) return VAD_ERR_ARG;
   if (d->ntaps != 9 && d->ntaps != 1) return VAD_ERR_ARG;
@@ -444,7 +469,7 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
   if (d->n_total > 512) return VAD_ERR_SHAPE;  // bias slab in shared memory
 
   ensure_trap_slot();
-  ConvArgs a;
+  ConvArgs& a = L.a;
   std::memset(&a, 0, sizeof(a));
   TileGeom g = pick_tile_geometry(d->B, d->H, d->W, is_score);
 
@@ -567,9 +592,59 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
     }
   }
 
-  const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
-  if (use_halo) return launch_conv_halo(CK, BN, epi, a, grid, stream);
-  return launch_conv_umma(CK, BN, epi, a, grid, stream);
+  a.timeline = g_timeline;
+  a.dual_mma = (dual_mma_setting() & (use_halo ? 1 : 4)) != 0;
+  L.CK = CK;
+  L.BN = BN;
+  L.epi = epi;
+  L.use_halo = use_halo;
+  L.grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return VAD_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
+  ConvLaunch L;
+  const int rc = build_conv(d, L);
+  if (rc != VAD_OK) return rc;
+  return launch_built(L, static_cast<cudaStream_t>(stream_));
+}
+
+int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
+  // d describes a generic step t >= 1: src0 = layer input sequence [B][T][h][w][c0], src1 = out = hidden sequence
+  // [B][T][h][w][hid] (step t reads h_{t-1} from it and writes h_t into it), c_state fp32 [B][h][w][hid].
+  if (!d || T <= 0 || d->epilogue != VAD_EPI_LSTM || !d->src1 || d->src1 != d->out || d->c1 != d->cout) return VAD_ERR_ARG;
+  if (d->T0 != T || d->T1 != T) return VAD_ERR_ARG;
+  ConvLaunch L;
+  int rc = build_conv(d, L);
+  if (rc != VAD_OK) return rc;
+  ConvArgs& a = L.a;
+  const long long step_elems = static_cast<long long>(d->H) * d->W * d->out_cpitch;
+  if (d->out_frame_stride != step_elems * T) return VAD_ERR_ARG;
+  if (a.tma_store) {  // output map over the whole sequence; the step index becomes the T coordinate of the store
+    const int TW = 1 << a.lgTW, TH = 1 << a.lgTH, TN = 1 << a.lgTN;
+    const long long cp = d->out_cpitch;
+    cuuint64_t dims[5] = {(cuuint64_t)d->cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)T, (cuuint64_t)d->B};
+    cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)d->W * cp * 2, (cuuint64_t)step_elems * 2,
+                        (cuuint64_t)d->out_frame_stride * 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
+    if (encode_map5(&a.mapOut, d->out, dims, st, box, 32) != VAD_OK) a.tma_store = 0;
+  }
+  const int chunks1 = a.chunks1;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  for (int t = 0; t < T; ++t) {
+    a.tA0 = t;
+    a.tA1 = t > 0 ? t - 1 : 0;
+    a.chunks1 = t > 0 ? chunks1 : 0;  // step 0: h_{-1} = 0, skip the h half of K
+    a.lstm_first = t == 0;
+    a.out_t = t;
+    a.out = reinterpret_cast<__nv_bfloat16*>(d->out) + t * step_elems;  // direct-store fallback path
+    rc = launch_built(L, stream);
+    if (rc != VAD_OK) return rc;
+  }
+  return VAD_OK;
 }
 
 int vad_first_conv(const float* x, const float* weight, const float* bias, int cout, float slope, int pool, int B,
@@ -614,6 +689,8 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   a.x = x;
   a.w_first = weight;
   a.dbg = env_int("VAD_DBG", 0);
+  a.dual_mma = (dual_mma_setting() & 2) != 0;
+  a.timeline = g_timeline;
   a.out = out;
   a.cout = 32;
   a.out_cp = 32;

@@ -99,6 +99,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile, in
 }
 
 // LeakyReLU family with 0 <= slope <= 1 (0 = ReLU, 1 = identity): act(v) = max(v, slope*v)
+// Bring-up timeline: CTA 0 stamps clock64 at role events of its first 64 tiles (role 0 producer, 1 MMA, 2/3 epilogue
+// group 0/1 leader).  Compiled in always; one predictable branch per event when disabled.
+__device__ __forceinline__ void tl_stamp(const ConvArgs& a, int role, int n, int ev) {
+  if (a.timeline != nullptr && blockIdx.x == 0 && n < 64) a.timeline[(role * 64 + n) * 8 + ev] = clock64();
+}
+
 // Tile walker for the persistent loops: tile index = ((tb*tiles_h + th)*tiles_w + tw)*n_tiles + n_t advances by a
 // fixed step; the step is decomposed once (integer divisions) and then added component-wise with carries, so the
 // per-tile cost is a handful of adds instead of three division sequences per role.
@@ -244,7 +250,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         if (leader) {
           const int col = t.n0 + oc * OC;
           if constexpr (EPI == VAD_EPI_STORE) {
-            tma_store_5d(&a.mapOut, buf, col, t.w0, t.h0, 0, t.b0);
+            tma_store_5d(&a.mapOut, buf, col, t.w0, t.h0, a.out_t, t.b0);
           } else if constexpr (EPI == VAD_EPI_POOL) {
             tma_store_5d(&a.mapOut, buf, col, t.w0 >> 1, t.h0 >> 1, 0, t.b0);
           } else {  // ConvT pixel shuffle: map dims {co, dj, w, di, b*H + h}
@@ -370,7 +376,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
       fence_proxy_async_smem();
       named_bar_sync(bar_id, 128);
       if (leader) {
-        tma_store_5d(&a.mapOut, buf, j0, t.w0, t.h0, 0, t.b0);
+        tma_store_5d(&a.mapOut, buf, j0, t.w0, t.h0, a.out_t, t.b0);
         bulk_commit_group();
       }
       ++stg_i;
@@ -496,10 +502,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
     const TileCoord t = ti.coord(a, BN);
     ti.next(a);
     if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xnext);
+    const bool tl = (g < 2 && q == 0 && lane == 0);
+    if (tl) tl_stamp(a, 2 + g, n, 0);
     mbar_wait(&acc_full_bar[as], aphase, 4);
+    if (tl) tl_stamp(a, 2 + g, n, 1);
     tc_fence_after();
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
     epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xcur, &acc_empty_bar[as]);
+    if (tl) tl_stamp(a, 2 + g, n, 2);
 #pragma unroll
     for (int j = 0; j < 12; ++j) xcur[j] = xnext[j];
   }
@@ -591,13 +601,25 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ===================================================================== MMA issuers (two warps, alternate tiles)
+    // Two issuers are only safe while a tile's k-loop is SHORTER than the operand ring: the issuer that runs ahead
+    // then never waits on a slot a full ring revolution early (mbarrier phase parity would alias and let it through
+    // on stale data).  Long k-loops use warp 1 alone.
+    const bool dual = a.dual_mma && k_iters < C::kStages;
+    const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      if (!dual && mi == 1) break;
+      if (dual && (it & 1) != mi) {  // the other issuer's tile: only keep the ring position in step
+        stage += k_iters % C::kStages;
+        phase ^= static_cast<uint32_t>((k_iters / C::kStages) & 1);
+        if (stage >= C::kStages) { stage -= C::kStages; phase ^= 1u; }
+        continue;
+      }
       const int as = it % kAS;
       mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
       tc_fence_after();
@@ -700,9 +722,12 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+    int pn = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a), ++pn) {
       const TileCoord t = ti.coord(a, BN);
+      if (lane == 0) tl_stamp(a, 0, pn, 0);
       mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+      if (lane == 0) tl_stamp(a, 0, pn, 1);
       if (elect_one()) {
         uint8_t* sa = s_a + stage * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], patch_tx);
@@ -712,8 +737,11 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
       __syncwarp();
       if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ===================================================================== MMA issuers (two warps, alternate tiles)
+    // One issuer alone leaves the tensor pipe idle while it sits in the two mbarrier waits of the next tile
+    // (~350 cycles even when they are already satisfied); with two, one waits while the other's MMAs are in flight.
+    const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
     const uint32_t sbo = static_cast<uint32_t>(a.halo_sbo_rows * kRowBytes);
     // per-tap operand start offsets in 16-byte units (the descriptor's address field), fixed for the whole kernel
@@ -728,28 +756,33 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     int it = 0;
     mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it % kAS;
-      mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
-      mbar_wait(&full_bar[stage], phase, 2);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        const uint32_t sa16 = (smem_u32(s_a + stage * stage_bytes) & 0x3FFFF) >> 4;
+      if (!a.dual_mma && mi == 1) break;
+      if (!a.dual_mma || (it & 1) == mi) {
+        const int as = it % kAS;
+        if (lane == 0) tl_stamp(a, 1, it, 0);
+        mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
+        if (lane == 0) tl_stamp(a, 1, it, 1);
+        mbar_wait(&full_bar[stage], phase, 2);
+        if (lane == 0) tl_stamp(a, 1, it, 2);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+          const uint32_t sa16 = (smem_u32(s_a + stage * stage_bytes) & 0x3FFFF) >> 4;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t a16 = sa16 + tap_off[tap];
-          if (a.halo_base_mode) a16 |= 0;  // (base-offset experiments removed: hardware swizzles absolute addresses)
-          const uint64_t da = da_hi | static_cast<uint64_t>(a16);
-          const uint64_t db = db0 + static_cast<uint64_t>((tap * kBBytes) >> 4);
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t da = da_hi | static_cast<uint64_t>(sa16 + tap_off[tap]);
+            const uint64_t db = db0 + static_cast<uint64_t>((tap * kBBytes) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < CK / 16; ++kk)
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                      (tap > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < CK / 16; ++kk)
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (tap > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&acc_full_bar[as]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&acc_full_bar[as]);
+        __syncwarp();
+        if (lane == 0) tl_stamp(a, 1, it, 3);
       }
-      __syncwarp();
       if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= kEpiWarp0) {
@@ -772,7 +805,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
 // the same as everywhere else.  Replaces models/autoencoder.py:39-41 and models/video_autoencoder.py:193-196 (with
 // the 2x2 max-pool fused for the video encoder).
 constexpr int kFirstStages = 6;
-constexpr int kFirstThreads = 128 + 256 + 128;  // roles | two epilogue groups | four converter warps
+constexpr int kFirstThreads = 128 + 256 + 256;  // roles | two epilogue groups | two groups of four converter warps
 constexpr int kFirstConvWarp0 = 12;
 // fp32 patch: 24 columns x 10 rows x 3 channels starting at column w0-4: TMA needs the box's first byte 16-byte
 // aligned in the innermost dimension, so the 1-pixel left halo is fetched as part of an aligned group of four
@@ -854,37 +887,52 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       __syncwarp();
       if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ===================================================================== MMA issuers (two warps, alternate tiles)
+    const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
     const uint64_t db = umma_smem_desc(smem_u32(s_w), 512, 4u);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it % kAS;
-      mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
-      mbar_wait(&full_bar[stage], phase, 2);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        const uint64_t da = umma_smem_desc(smem_u32(s_a + stage * kABytes), 512, 4u);
-        umma_bf16(d_tmem, da, db, idesc, 0u);
-        umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&acc_full_bar[as]);
+      if (!a.dual_mma && mi == 1) break;
+      if (!a.dual_mma || (it & 1) == mi) {
+        const int as = it % kAS;
+        if (lane == 0) tl_stamp(a, 1, it, 0);
+        mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
+        if (lane == 0) tl_stamp(a, 1, it, 1);
+        mbar_wait(&full_bar[stage], phase, 2);
+        if (lane == 0) tl_stamp(a, 1, it, 2);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+          const uint64_t da = umma_smem_desc(smem_u32(s_a + stage * kABytes), 512, 4u);
+          umma_bf16(d_tmem, da, db, idesc, 0u);
+          umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&acc_full_bar[as]);
+        }
+        __syncwarp();
+        if (lane == 0) tl_stamp(a, 1, it, 3);
       }
-      __syncwarp();
       if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp >= kFirstConvWarp0) {
     // ===================================================================== converters: fp32 patch -> bf16 im2col rows
-    const int r = (warp - kFirstConvWarp0) * 32 + lane;  // pixel slot = A row
-    const int ww = r & 15, hh = r >> 4;                  // tile = 8 rows x 16 columns of one frame
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    // two groups of four warps take alternate tiles (the conversion is latency-bound: LDS -> pack -> STS -> fence)
+    const int cg = (warp - kFirstConvWarp0) >> 2;
+    const int r = ((warp - kFirstConvWarp0) & 3) * 32 + lane;  // pixel slot = A row
+    const int ww = r & 15, hh = r >> 4;                        // tile = 8 rows x 16 columns of one frame
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != cg) continue;
+      const int stage = it % kFirstStages;
+      const uint32_t phase = (it / kFirstStages) & 1;
+      const bool tl = (warp == kFirstConvWarp0 + 4 * cg && lane == 0);
+      if (tl) tl_stamp(a, 0, it, 0);
       mbar_wait(&patch_full[stage], phase, 6);
+      if (tl) tl_stamp(a, 0, it, 1);
       const float* pp = reinterpret_cast<const float*>(s_p + stage * kPatchStride) + hh * kPatchW + ww + (kPatchX0 - 1);
       float v[27];  // k = (ky*3 + kx)*3 + ci
 #pragma unroll
@@ -902,7 +950,9 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       p[13] = pack_bf16x2(v[26], 0.f);
       p[14] = 0u;
       p[15] = 0u;
+      if (tl) tl_stamp(a, 0, it, 2);
       mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+      if (tl) tl_stamp(a, 0, it, 3);
       uint8_t* sa = s_a + stage * kABytes;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -910,7 +960,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
-      if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
+      if (tl) tl_stamp(a, 0, it, 4);
     }
   } else if (warp >= kEpiWarp0) {
     epilogue_loop<BN, EPI, kFirstGroups>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);

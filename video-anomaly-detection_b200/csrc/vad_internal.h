@@ -37,10 +37,13 @@ struct alignas(64) ConvArgs {
   float* heat;
   float* partials;
   int dbg;              // bring-up switches (VAD_DBG environment variable)
+  int dual_mma;         // 1: two MMA-issuer warps take alternate tiles
+  long long* timeline;  // optional [role 0..3][64 tiles][8 events] clock64 stamps of CTA 0 (vad_debug_set_timeline)
   const void* w_first;  // first conv: bf16 [32 n][32 k] weights, k = (ky*3+kx)*3+ci (27 real + 5 zero)
   // epilogue staging / TMA store
   int tma_store;  // 1: stage the bf16 tile in swizzled smem and store it with TMA (coalesced, clipped by hardware)
   int out_chunk;  // channels per staged chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+  int out_t;      // T coordinate of the TMA store (ConvLSTM sequence: the step index)
   // halo kernel (3x3 conv, weights resident in smem, one input patch per tile reused by all 9 taps)
   int halo_pw, halo_ph;       // patch width / height in pixels
   int halo_npatch;            // 1: one (TW+2)-wide patch; 3: three TW-wide patches shifted by dx

@@ -72,6 +72,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// (Measured: letting one lane poll and parking the other 31 at __syncwarp is SLOWER than all 32 lanes polling —
+// 1307 vs 1033 cycles per tile on the halo kernel — so every role warp waits with all its lanes.)
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");

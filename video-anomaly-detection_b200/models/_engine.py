@@ -6,6 +6,7 @@ only touches HBM when the caller asks for it.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
@@ -234,12 +235,16 @@ class VideoEngine:
             cin = wt.ctap - hid
             hseq = self.bufs.get(f"hseq{layer}", (B, T, h, w, hid), torch.bfloat16, dev)
             cst = self.bufs.get(f"c{layer}", (B, h, w, hid), torch.float32, dev)
-            for t in range(T):
-                first = t == 0
-                _gemm_layer(wt, cur, B, h, w, nat.EPI_LSTM, IDENT, hseq, c0=cin, T0=T, t0=t,
-                            src1=None if first else hseq, c1=0 if first else hid, T1=T, t1=t - 1,
-                            out_frame_stride=T * h * w * hid, out_cpitch=hid, out_offset_elems=t * h * w * hid,
-                            c_state=cst, lstm_first=first, what=f"convlstm.{layer}.t{t}")
+            d = nat.ConvDesc()
+            d.src0, d.src1, d.out = cur.data_ptr(), hseq.data_ptr(), hseq.data_ptr()
+            d.c0, d.c1, d.T0, d.T1 = cin, hid, T, T
+            d.B, d.H, d.W, d.ntaps = B, h, w, 9
+            d.weight, d.bias, d.w_ctap = wt.w.data_ptr(), wt.bias.data_ptr(), wt.ctap
+            d.n_total, d.cout, d.epilogue, d.slope = wt.n_total, hid, nat.EPI_LSTM, IDENT
+            d.out_frame_stride, d.out_cpitch = T * h * w * hid, hid
+            d.c_state = cst.data_ptr()
+            _timed(f"convlstm.{layer}", lambda: nat.check(
+                nat.load().vad_convlstm_sequence(C.byref(d), T, nat.stream_ptr()), f"convlstm.{layer}"))
             cur = hseq
         return cur
 

@@ -17,7 +17,7 @@ EPI_STORE, EPI_POOL, EPI_CONVT, EPI_LSTM, EPI_TANH_SCORE, EPI_CONVT_TANH_SCORE =
 
 # every symbol include/vad_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_conv_layer", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
+    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_conv_layer", "vad_convlstm_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8",
 )
@@ -59,7 +59,9 @@ def load() -> C.CDLL:
     lib.vad_error_string.argtypes = [C.c_int]
     lib.vad_version.restype = C.c_int
     lib.vad_launch_count.restype = C.c_ulonglong
+    lib.vad_debug_set_timeline.argtypes = [C.c_void_p]
     lib.vad_conv_layer.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
+    lib.vad_convlstm_sequence.argtypes = [C.POINTER(ConvDesc), C.c_int, C.c_void_p]
     lib.vad_conv_m_tiles.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.vad_first_conv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]
@@ -82,7 +84,7 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().vad_error_string(rc).decode()
         trap = (C.c_ulonglong * 4)()
-        if rc > 0 and load().vad_debug_last_trap(trap) == 0 and any(trap):
+        if rc > 0 and load().vad_debug_last_trap(trap) == 0:
             msg += f" [mbarrier wait timed out: tag={trap[0]} block={trap[1]} thread={trap[2]} parity={trap[3]}]"
         raise RuntimeError(f"libvad_b200: {what} failed with code {rc}: {msg}")
 
