@@ -35,14 +35,14 @@ __host__ __device__ constexpr bool epi_uses_staging(int epi) {
 }
 // Epilogue warps come in groups of four (one warp per TMEM lane quarter); group g takes this CTA's tiles g, g+G, ...
 // and owns TMEM accumulator stage g.  The narrowest tiles (N <= 32: full-resolution layers, thousands of tiny tiles
-// per SM) are bound by epilogue latency and get four groups, mid-size tiles two, and 256-wide tiles (MMA-bound) one
+// per SM; N <= 64) are bound by epilogue latency and get four groups, 128-wide tiles two, and 256-wide tiles (MMA-bound) one
 // group plus the smem for a deeper operand ring.
-__host__ __device__ constexpr int epi_groups(int bn) { return bn >= 256 ? 1 : (bn <= 32 ? 4 : 2); }
+__host__ __device__ constexpr int epi_groups(int bn) { return bn >= 256 ? 1 : (bn <= 64 ? 4 : 2); }
 __host__ __device__ constexpr int acc_stages_for(int groups) { return groups < 2 ? 2 : groups; }
 __host__ __device__ constexpr int block_threads(int bn) { return 128 + 128 * epi_groups(bn); }
 // staged-output buffers per epilogue group
 __host__ __device__ constexpr int staging_bufs(int bn, int epi) {
-  return !epi_uses_staging(epi) ? 0 : (bn >= 256 ? 1 : 2);
+  return !epi_uses_staging(epi) ? 0 : ((bn >= 256 || bn == 64) ? 1 : 2);  // N=64 runs 4 groups: one 16 KB buffer each
 }
 // one staged chunk: 128 rows x (64 ch = 128 B | 32 ch = 64 B)
 __host__ __device__ constexpr int staging_buf_bytes(int bn, int epi) {
