@@ -37,8 +37,12 @@ unsigned long long vad_launch_count(void);
 /* Bring-up aid: if a kernel's bounded mbarrier wait timed out (the kernel then traps), out = {wait-site tag,
  * blockIdx.x, threadIdx.x, parity}; all zero otherwise.  Readable even after the CUDA context reports an error. */
 int vad_debug_last_trap(unsigned long long out[4]);
+/* Tuning aid: which narrow 3x3 layers may use the kernel that folds the horizontal taps into N when `weight_kx` is
+ * given: 0 none, 1 the 3-channel score layer (default), 2 also Cout = 32, 3 also Cout = 64; -1 restores the VAD_KX
+ * environment setting.  Returns the previous mode. */
+int vad_debug_set_kx(int mode);
 /* Bring-up aid: when set, CTA 0 of every vad_conv_layer kernel stamps clock64 at role events of its first 64 tiles
- * into device_buf[4 roles][64][8] (role 0 TMA producer, 1 MMA issuer, 2/3 epilogue group 0/1).  NULL disables. */
+ * into device_buf[4 roles][64][16] (role 0 TMA producer, 1 MMA issuer, 2/3 epilogue group 0/1).  NULL disables. */
 int vad_debug_set_timeline(long long* device_buf);
 
 /* ---- one convolution-as-GEMM layer ----------------------------------------------------------------------------
@@ -86,6 +90,11 @@ typedef struct vad_conv_desc {
   float* recon;               /* *_SCORE: optional fp32 [B,3,Ho,Wo] */
   float* heat;                /* *_SCORE: optional fp32 [B,Ho,Wo] per-pixel channel-mean squared error */
   float* partials;            /* *_SCORE: fp32 [m_tiles][4] per-tile (sum of squares, min, max, -) */
+  /* optional second layout of the same 3x3 weights for narrow layers (Cout <= 64, one source of 32/64 channels):
+   * bf16 [3*Cout rows, zero-padded to a multiple of 16][3*Cin], row = kx*Cout + co, column = ky*Cin + ci
+   * (*_SCORE: Cout = 3 -> 9 rows padded to 16).  When present the library may fold the horizontal taps into the
+   * GEMM N extent (3 instead of 9 shifted MMAs per K step); NULL keeps the tap-per-MMA kernels. */
+  const void* weight_kx;
 } vad_conv_desc;
 
 int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
@@ -94,7 +103,10 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
  * sequence bf16 [B][T][h][w][c0] (T0 = T), src1 = out = hidden sequence bf16 [B][T][h][w][hid] (T1 = T, c1 = hid,
  * out_frame_stride = T*h*w*hid), c_state fp32 [B][h][w][hid]; zero initial state. */
 int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream);
-/* number of 128-pixel tiles (rows of `partials`) a *_SCORE layer produces for (B,H,W) input */
+/* number of M tiles (= rows of `partials` for a *_SCORE layer) vad_conv_layer will use for this description;
+ * negative = the error vad_conv_layer would return.  Launches nothing. */
+int vad_conv_layer_tiles(const vad_conv_desc* d);
+/* number of 128-pixel tiles of the default tiling for a (B,H,W) input (upper bound helpers / tests) */
 int vad_conv_m_tiles(int B, int H, int W, int force_single_frame_tiles);
 
 /* ---- first layer: fp32 NCHW (3 ch) -> bf16 NHWC, conv3x3 + folded BN + LeakyReLU (+ 2x2 max-pool) --------------

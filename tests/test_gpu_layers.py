@@ -44,6 +44,14 @@ def _assert_close(got, ref, what, rtol=OUT_RTOL, atol=OUT_ATOL):
                            f"at ref {float(ref.flatten()[err.argmax()]):.4g}; ref rms {float(ref.pow(2).mean().sqrt()):.4g}")
 
 
+def _dev(packed, dev):
+    """Move one packed layer to the device (weights, bias and the optional kx-merged weight layout)."""
+    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    if getattr(packed, "w_kx", None) is not None:
+        packed.w_kx = packed.w_kx.to(dev)
+    return packed
+
+
 CONV_CASES = [
     # (cin, cout, B, H, W)
     (32, 32, 2, 32, 32),
@@ -54,23 +62,31 @@ CONV_CASES = [
     (128, 256, 2, 16, 16),
     (256, 256, 2, 32, 32),
     (128, 128, 1, 6, 10),     # H, W not powers of two, smaller than a tile
+    (32, 32, 2, 48, 80),      # kx-merged tiles: 80 = 13 x 6 + 2 (partial last tile), three tile rows
+    (32, 32, 1, 16, 256),     # full-width rows: 43 tiles of 6 columns, the last one clipped to 4
 ]
 
 
 @pytest.mark.parametrize("cin,cout,B,H,W", CONV_CASES)
 @pytest.mark.parametrize("pool", [False, True])
-def test_conv3x3(cuda_device, cin, cout, B, H, W, pool):
+@pytest.mark.parametrize("kx", [True, False])
+def test_conv3x3(cuda_device, cin, cout, B, H, W, pool, kx):
     eng, nat, prep = _mods()
     dev = cuda_device
     g = torch.Generator().manual_seed(cin * 1000 + cout + H)
     w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
-    packed = prep.pack_conv3x3(w.double(), b.double())
-    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    packed = _dev(prep.pack_conv3x3(w.double(), b.double()), dev)
+    if kx and packed.w_kx is None:
+        pytest.skip("layer has no kx-merged variant")
     x = _rand_nhwc(B, H, W, cin, dev, seed=H * W)
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     out = torch.full((B, Ho, Wo, cout), float("nan"), dtype=torch.bfloat16, device=dev)
-    eng._conv(packed, x, B, H, W, out, 0.2, pool=pool, what="test conv")
+    prev = nat.load().vad_debug_set_kx(3 if kx else 0)  # 3: every eligible layer takes the kx-merged kernel
+    try:
+        eng._conv(packed, x, B, H, W, out, 0.2, pool=pool, what="test conv")
+    finally:
+        nat.load().vad_debug_set_kx(-1)
     torch.cuda.synchronize()
     ref = F.conv2d(_nchw(x), w.to(torch.bfloat16).float().to(dev), b.to(dev), padding=1)
     ref = F.leaky_relu(ref, 0.2)
@@ -87,8 +103,7 @@ def test_convt2x2(cuda_device, cin, cout, B, H, W):
     g = torch.Generator().manual_seed(cin + cout)
     w = torch.randn(cin, cout, 2, 2, generator=g) * (2.0 / cin) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
-    packed = prep.pack_convt2x2(w.double(), b.double())
-    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    packed = _dev(prep.pack_convt2x2(w.double(), b.double()), dev)
     x = _rand_nhwc(B, H, W, cin, dev, seed=7)
     out = torch.full((B, 2 * H, 2 * W, cout), float("nan"), dtype=torch.bfloat16, device=dev)
     eng._convt(packed, x, B, H, W, out, 0.0, what="test convT")
@@ -151,23 +166,25 @@ def test_convlstm_sequence(cuda_device, B, T, H, W):
     _assert_close(cst, _nhwc(c), "convlstm final c", rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 48)])
-def test_last_conv_tanh_score(cuda_device, B, H, W):
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 48), (1, 48, 256)])
+@pytest.mark.parametrize("kx", [True, False])
+def test_last_conv_tanh_score(cuda_device, B, H, W, kx):
     eng, nat, prep = _mods()
     dev = cuda_device
     g = torch.Generator().manual_seed(13)
     w = torch.randn(3, 32, 3, 3, generator=g) * (1.0 / 288) ** 0.5
     b = torch.randn(3, generator=g) * 0.1
-    packed = prep.pack_conv3x3(w.double(), b.double(), pad_n_to=16)
-    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    packed = _dev(prep.pack_conv3x3(w.double(), b.double(), pad_n_to=16), dev)
+    assert packed.w_kx is not None and tuple(packed.w_kx.shape) == (16, 96)
     a = _rand_nhwc(B, H, W, 32, dev, seed=17)
     x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
-    tiles = nat.m_tiles(B, H, W, True)
-    partials = torch.zeros(tiles, 4, device=dev)
-    recon = torch.full((B, 3, H, W), float("nan"), device=dev)
-    heat = torch.full((B, H, W), float("nan"), device=dev)
-    eng._gemm_layer(packed, a, B, H, W, nat.EPI_TANH_SCORE, 1.0, None, x=x, recon=recon, heat=heat, partials=partials)
-    score, minmax = eng._finalize(partials, B, tiles // B, H, W, None, dev)
+    nat.load().vad_debug_set_kx(1 if kx else 0)
+    try:
+        res = eng._score_layer(packed, a, B, H, W, nat.EPI_TANH_SCORE, x, True, True, H, W, eng._Buffers(),
+                               "test score")
+    finally:
+        nat.load().vad_debug_set_kx(-1)
+    score, minmax, recon, heat = res.score, res.minmax, res.recon, res.heat
     torch.cuda.synchronize()
     ref = torch.tanh(F.conv2d(_nchw(a), w.to(torch.bfloat16).float().to(dev), b.to(dev), padding=1))
     err = ((x - ref) ** 2).mean(1)
@@ -185,18 +202,13 @@ def test_last_convt_tanh_score(cuda_device, B, H, W):
     g = torch.Generator().manual_seed(19)
     w = torch.randn(32, 3, 2, 2, generator=g) * (1.0 / 32) ** 0.5
     b = torch.randn(3, generator=g) * 0.1
-    packed = prep.pack_convt2x2(w.double(), b.double(), pad_n_to=16)
-    packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
+    packed = _dev(prep.pack_convt2x2(w.double(), b.double(), pad_n_to=16), dev)
     a = _rand_nhwc(B, H, W, 32, dev, seed=23)
     Ho, Wo = 2 * H, 2 * W
     x = (torch.rand(B, 3, Ho, Wo, generator=g) * 2 - 1).to(dev)
-    tiles = nat.m_tiles(B, H, W, True)
-    partials = torch.zeros(tiles, 4, device=dev)
-    recon = torch.full((B, 3, Ho, Wo), float("nan"), device=dev)
-    heat = torch.full((B, Ho, Wo), float("nan"), device=dev)
-    eng._gemm_layer(packed, a, B, H, W, nat.EPI_CONVT_TANH_SCORE, 1.0, None, x=x, recon=recon, heat=heat,
-                    partials=partials)
-    score, minmax = eng._finalize(partials, B, tiles // B, Ho, Wo, None, dev)
+    res = eng._score_layer(packed, a, B, H, W, nat.EPI_CONVT_TANH_SCORE, x, True, True, Ho, Wo, eng._Buffers(),
+                           "test score")
+    score, minmax, recon, heat = res.score, res.minmax, res.recon, res.heat
     torch.cuda.synchronize()
     ref = torch.tanh(F.conv_transpose2d(_nchw(a), w.to(torch.bfloat16).float().to(dev), b.to(dev), stride=2))
     err = ((x - ref) ** 2).mean(1)

@@ -14,7 +14,7 @@ w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
 fw = prep.to_device({"w": prep.pack_first_conv(w.double(), torch.zeros(32).double())}, dev)["w"]
 x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
 out = torch.empty(B, H // 2 if pool else H, W // 2 if pool else W, 32, dtype=torch.bfloat16, device=dev)
-buf = torch.zeros(4, 64, 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(4, 64, 16, dtype=torch.int64, device=dev)
 for _ in range(2):
     eng._first_conv(fw, x, B, H, W, bool(pool), out)
 torch.cuda.synchronize()

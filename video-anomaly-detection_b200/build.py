@@ -23,14 +23,17 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
+    """timeline=True compiles the per-tile clock stamps in (tools/timeline*.py need them; they slow the kernels)."""
     if not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DVAD_TIMELINE"] if timeline else []) + \
+          ["-o", OUT] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.run(cmd, check=True)
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--timeline" in sys.argv, verbose="-v" in sys.argv,
+                timeline="--timeline" in sys.argv))

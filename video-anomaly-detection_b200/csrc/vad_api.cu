@@ -142,6 +142,14 @@ static int dual_mma_setting() {
   static int v = env_int("VAD_DUAL_MMA", 1);
   return v;
 }
+// VAD_KX: 0 = never use the kx-merged kernel | 1 (default) = the 3-channel score layer only (for wider outputs the
+// 3x TMEM read of the merged accumulator costs more than the saved MMAs: TMEM -> registers runs at 64 B/clk/SM) |
+// 2 = also Cout = 32 | 3 = also Cout = 64
+static int g_kx_override = -1;  // vad_debug_set_kx
+static int kx_setting() {
+  static int v = env_int("VAD_KX", 1);
+  return g_kx_override >= 0 ? g_kx_override : v;
+}
 static int tma_store_setting() {
   static int v = env_int("VAD_TMA_STORE", 1);
   return v;
@@ -401,6 +409,12 @@ int vad_debug_set_timeline(long long* device_buf) {  // 4 roles x 64 tiles x 8 e
   return VAD_OK;
 }
 
+int vad_debug_set_kx(int mode) {  // -1 = back to the VAD_KX environment setting; returns the previous effective mode
+  const int prev = kx_setting();
+  g_kx_override = mode;
+  return prev;
+}
+
 int vad_debug_last_trap(unsigned long long out[4]) {
   if (!g_trap_host || !out) return VAD_ERR_ARG;
   for (int i = 0; i < 4; ++i) out[i] = g_trap_host[i];
@@ -419,9 +433,11 @@ struct ConvLaunch {
   ConvArgs a;
   int CK, BN, epi, grid;
   bool use_halo;
+  bool use_kx;
 };
 
 int launch_built(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.use_kx) return launch_conv_kx(L.CK, L.BN, L.epi, L.a, L.grid, stream);
   if (L.use_halo) return launch_conv_halo(L.CK, L.BN, L.epi, L.a, L.grid, stream);
   return launch_conv_umma(L.CK, L.BN, L.epi, L.a, L.grid, stream);
 }
@@ -473,9 +489,31 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   std::memset(&a, 0, sizeof(a));
   TileGeom g = pick_tile_geometry(d->B, d->H, d->W, is_score);
 
+  // ---- kx-merged halo kernel: narrow 3x3 layers whose caller supplied the [kx*Cout + co][ky*Cin + ci] weight matrix
+  const bool halo_shape = d->ntaps == 9 && d->c1 == 0 && (d->c0 == 32 || d->c0 == 64) && d->n_total == BN &&
+                          (d->T0 <= 1) && d->H >= 16 && d->W >= 16 &&
+                          (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_TANH_SCORE);
+  bool use_kx = kx_setting() != 0 && d->weight_kx != nullptr && halo_shape && BN <= (kx_setting() >= 3 ? 64 : kx_setting() == 2 ? 32 : 16) &&
+                kx_fixed_smem_bytes(CK, BN, epi) > 0;
+  if (use_kx) {
+    g.lgTW = 3; g.lgTH = 4; g.lgTN = 0;
+    g.tiles_w = (d->W + 5) / 6;
+    g.tiles_h = (d->H + 15) >> 4;
+    g.tiles_b = d->B;
+    const int patch = 8 * 18 * CK * 2;
+    int stages = 8;
+    while (stages >= 2 && kx_fixed_smem_bytes(CK, BN, epi) + stages * patch > 227 * 1024 - 4096) --stages;
+    if (stages < 2) {
+      use_kx = false;
+      g = pick_tile_geometry(d->B, d->H, d->W, is_score);
+    } else {
+      a.halo_stages = stages;
+    }
+  }
+
   // ---- halo kernel: 3x3 conv, one source of 32/64 channels, all of N in one tile, frames of at least one tile
   const int halo_mode = halo_mode_setting();
-  bool use_halo = halo_mode != 0 && d->ntaps == 9 && d->c1 == 0 && (d->c0 == 32 || d->c0 == 64) &&
+  bool use_halo = !use_kx && halo_mode != 0 && d->ntaps == 9 && d->c1 == 0 && (d->c0 == 32 || d->c0 == 64) &&
                   d->n_total == BN && (d->T0 <= 1) && d->H >= 16 && d->W >= 16 &&
                   (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_TANH_SCORE);
   int halo_box_w = 0, halo_box_h = 0;
@@ -511,7 +549,9 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   }
 
   int rc;
-  if (use_halo) {
+  if (use_kx) {
+    rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, CK, 8, 18, 1);
+  } else if (use_halo) {
     TileGeom box = g;  // box {CK, PW, PH, 1, 1}: PW/PH need not be powers of two
     rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, CK, halo_box_w, halo_box_h, 1);
     (void)box;
@@ -526,12 +566,19 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   const int w_ctap = d->w_ctap > 0 ? d->w_ctap : d->c0 + d->c1;
   if (w_ctap < d->c0 + d->c1) return VAD_ERR_ARG;
   const int K = d->ntaps * w_ctap;
-  rc = encode_weight_map(&a.mapB, d->weight, K, d->n_total, CK, BN);
+  if (use_kx) {  // [kx*Cout + co (zero rows up to the MMA N)][ky*Cin + ci]
+    const int nm = kx_mma_columns(BN, epi);
+    rc = encode_weight_map(&a.mapB, d->weight_kx, 3 * d->c0, nm, CK, nm);
+  } else {
+    rc = encode_weight_map(&a.mapB, d->weight, K, d->n_total, CK, BN);
+  }
   if (rc != VAD_OK) return rc;
   a.chunks0 = d->c0 / CK;
   a.chunks1 = d->c1 / CK;
   a.ntaps = d->ntaps;
-  a.w_ctap = w_ctap;
+  a.w_ctap = use_kx ? d->c0 : w_ctap;
+  a.w_step = use_kx ? 6 : (1 << g.lgTW);
+  a.tw_valid = use_kx ? 6 : (1 << g.lgTW);
   a.tA0 = d->t0;
   a.tA1 = d->t1;
   a.B = d->B; a.H = d->H; a.W = d->W;
@@ -559,7 +606,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
       cuuint64_t dims[5] = {(cuuint64_t)d->n_total, (cuuint64_t)d->W, (cuuint64_t)d->H, 1, (cuuint64_t)d->B};
       cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)d->W * cp * 2, (cuuint64_t)d->H * d->W * cp * 2,
                           (cuuint64_t)d->out_frame_stride * 2};
-      cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
+      cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, (cuuint32_t)(use_kx ? 6 : TW), (cuuint32_t)TH, 1, (cuuint32_t)TN};
       a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK;
     } else if (aligned && epi == VAD_EPI_LSTM) {
       a.out_chunk = 32;
@@ -574,7 +621,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
       cuuint64_t dims[5] = {(cuuint64_t)d->n_total, (cuuint64_t)Wo, (cuuint64_t)Ho, 1, (cuuint64_t)d->B};
       cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)Wo * cp * 2, (cuuint64_t)Ho * Wo * cp * 2,
                           (cuuint64_t)d->out_frame_stride * 2};
-      cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, (cuuint32_t)(TW / 2), (cuuint32_t)(TH / 2), 1, (cuuint32_t)TN};
+      cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, (cuuint32_t)(use_kx ? 3 : TW / 2), (cuuint32_t)(TH / 2), 1, (cuuint32_t)TN};
       a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK;
     } else if (aligned && epi == VAD_EPI_CONVT) {
       // pixel shuffle as a 5-D map {co, dj, w, di, b*H + h}; needs dense frames and tiles whose rows are
@@ -593,7 +640,9 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   }
 
   a.timeline = g_timeline;
-  a.dual_mma = (dual_mma_setting() & (use_halo ? 1 : 4)) != 0;
+  a.dbg = env_int("VAD_DBG", 0);
+  a.dual_mma = (dual_mma_setting() & ((use_halo || use_kx) ? 1 : 4)) != 0;
+  L.use_kx = use_kx;
   L.CK = CK;
   L.BN = BN;
   L.epi = epi;
@@ -610,6 +659,13 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream_) {
   const int rc = build_conv(d, L);
   if (rc != VAD_OK) return rc;
   return launch_built(L, static_cast<cudaStream_t>(stream_));
+}
+
+int vad_conv_layer_tiles(const vad_conv_desc* d) {
+  ConvLaunch L;
+  const int rc = build_conv(d, L);
+  if (rc != VAD_OK) return rc;
+  return L.a.total_tiles / L.a.n_tiles;
 }
 
 int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
@@ -676,6 +732,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   ConvArgs a;
   std::memset(&a, 0, sizeof(a));
   a.lgTW = 4; a.lgTH = 3; a.lgTN = 0;  // 8 x 16 pixel tiles inside one frame
+  a.w_step = 16; a.tw_valid = 16;
   a.tiles_w = (W + 15) / 16;
   a.tiles_h = (H + 7) / 8;
   a.tiles_b = B;

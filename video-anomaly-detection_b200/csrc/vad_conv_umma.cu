@@ -25,7 +25,7 @@ namespace vad {
 
 constexpr int kEpiWarp0 = 4;  // warps 0..3: TMA producer, MMA issuer, TMEM allocator, spare
 constexpr int kTileM = 128;
-constexpr int kMaxAccStages = 4;
+constexpr int kMaxAccStages = 8;
 constexpr int kStagingBuf = 16384;  // one staged output chunk: 128 rows x 128 B
 constexpr int kMaxBias = 512;
 constexpr int kSmemBudget = 227 * 1024 - 4096;  // dynamic smem we allow ourselves (static smem + slack kept free)
@@ -59,6 +59,30 @@ __host__ __device__ constexpr uint32_t tmem_cols_for(int bn, int groups = 0) {
   return (c <= 32) ? 32u : (c <= 64) ? 64u : (c <= 128) ? 128u : (c <= 256) ? 256u : 512u;
 }
 
+// ---- kx-merged halo mode ("kx kernel") ---------------------------------------------------------------------------
+// A tcgen05.mma with M=128, K=16 costs max(N/2, 32 + N/4) cycles (tools/umma_bench.cu): below N=128 it is bound by
+// streaming the 4 KB A slab from shared memory, not by math.  For the narrow 3x3 layers (Cout = 32, and the 3-channel
+// last conv) the three horizontal taps are therefore folded into the N extent: D[pixel q][kx][co] = sum over (ky, ci)
+// of in[q + ky row shift][ci] * w[co][ky][kx][ci] — three row-shifted MMAs per K step instead of nine — and the
+// epilogue forms out[x] = D[x-1][0] + D[x][1] + D[x+1][2] with two lane shuffles.  One tile = 16 rows x 8 patch
+// columns (x0-1 .. x0+6) -> 6 valid output columns.
+constexpr int kKxValid = 6;  // valid output columns of a kx tile (8 accumulator columns minus the two halo columns)
+__host__ __device__ constexpr bool is_score_epi(int epi) {
+  return epi == VAD_EPI_TANH_SCORE || epi == VAD_EPI_CONVT_TANH_SCORE;
+}
+__host__ __device__ constexpr int kx_mma_n(int bn, int epi) { return is_score_epi(epi) ? 16 : 3 * bn; }
+__host__ __device__ constexpr int kx_acc_stride(int bn, int epi) {
+  return kx_mma_n(bn, epi) <= 16 ? 16 : (kx_mma_n(bn, epi) <= 128 ? 128 : 256);
+}
+// epilogue groups: the score epilogue is light on registers and bound by latency -> six groups (896 threads)
+__host__ __device__ constexpr int kx_groups(int bn, int epi) {
+  return is_score_epi(epi) ? 6 : (kx_acc_stride(bn, epi) * 4 <= 512 ? 4 : 2);
+}
+__host__ __device__ constexpr uint32_t kx_tmem_cols(int bn, int epi) {
+  const int c = kx_groups(bn, epi) * kx_acc_stride(bn, epi);
+  return (c <= 32) ? 32u : (c <= 64) ? 64u : (c <= 128) ? 128u : (c <= 256) ? 256u : 512u;
+}
+
 template <int CK, int BN, int EPI>
 struct Cfg {
   static constexpr int kRowBytes = CK * 2;            // one swizzle span per row: 128 B or 64 B
@@ -83,26 +107,15 @@ struct TileCoord {
   int m_tile;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile, int bn) {
-  TileCoord t;
-  const int n_t = tile % a.n_tiles;
-  const int m_t = tile / a.n_tiles;
-  const int tw = m_t % a.tiles_w;
-  const int th = (m_t / a.tiles_w) % a.tiles_h;
-  const int tb = m_t / (a.tiles_w * a.tiles_h);
-  t.n0 = n_t * bn;
-  t.w0 = tw << a.lgTW;
-  t.h0 = th << a.lgTH;
-  t.b0 = tb << a.lgTN;
-  t.m_tile = m_t;
-  return t;
-}
-
 // LeakyReLU family with 0 <= slope <= 1 (0 = ReLU, 1 = identity): act(v) = max(v, slope*v)
 // Bring-up timeline: CTA 0 stamps clock64 at role events of its first 64 tiles (role 0 producer, 1 MMA, 2/3 epilogue
 // group 0/1 leader).  Compiled in always; one predictable branch per event when disabled.
+// The stamps cost real time in the single-warp role loops (a constant load, a predicate chain and a clock read per
+// event even when disabled), so they only exist in -DVAD_TIMELINE builds (`python build.py --timeline`).
 __device__ __forceinline__ void tl_stamp(const ConvArgs& a, int role, int n, int ev) {
-  if (a.timeline != nullptr && blockIdx.x == 0 && n < 64) a.timeline[(role * 64 + n) * 8 + ev] = clock64();
+#ifdef VAD_TIMELINE
+  if (a.timeline != nullptr && blockIdx.x == 0 && n < 64) a.timeline[(role * 64 + n) * 16 + ev] = clock64();
+#endif
 }
 
 // Tile walker for the persistent loops: tile index = ((tb*tiles_h + th)*tiles_w + tw)*n_tiles + n_t advances by a
@@ -138,7 +151,7 @@ struct TileIter {
   __device__ __forceinline__ TileCoord coord(const ConvArgs& a, int bn) const {
     TileCoord t;
     t.n0 = n_t * bn;
-    t.w0 = tw << a.lgTW;
+    t.w0 = tw * a.w_step;
     t.h0 = th << a.lgTH;
     t.b0 = tb << a.lgTN;
     t.m_tile = (tb * a.tiles_h + th) * a.tiles_w + tw;
@@ -160,16 +173,47 @@ __device__ __forceinline__ uint32_t staged_off(int row, int c16, int out_chunk) 
 
 // ---------------------------------------------------------------------------------------------------- epilogue
 // Runs on the four epilogue warps for one finished accumulator tile.  `stg_i` counts staged chunks (ring index).
-template <int BN, int EPI>
+// 32 accumulator columns [lc, lc+32) of this thread's row.  KX == 3: the three kx column groups (BN columns apart) are
+// combined across neighbouring rows: out[ww] = D[ww][kx=0] + D[ww+1][kx=1] + D[ww+2][kx=2] (rows = lanes).
+template <int BN, int KX>
+__device__ __forceinline__ void load_acc32(uint32_t tacc, int lc, uint32_t (&v)[32]) {
+  if constexpr (KX == 1) {
+    tmem_ld_x32(tacc + lc, v);
+    tmem_ld_wait();
+  } else {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t c0[16], c1[16], c2[16];
+      tmem_ld_x16(tacc + lc + half * 16, c0);
+      tmem_ld_x16(tacc + BN + lc + half * 16, c1);
+      tmem_ld_x16(tacc + 2 * BN + lc + half * 16, c2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(c1[j]), 1);
+        const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(c2[j]), 2);
+        v[half * 16 + j] = __float_as_uint((__uint_as_float(c0[j]) + s1) + s2);
+      }
+    }
+  }
+}
+
+template <int BN, int EPI, int KX = 1>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& t, uint32_t tacc, int q, int lane,
                                               uint8_t* stg, const float* s_bias, float (*red_smem)[3], int& stg_i,
-                                              uint32_t bar_id, const float* xpre, uint64_t* acc_empty) {
+                                              uint32_t bar_id, const float* xpre, uint32_t acc_empty, int tl_role = -1,
+                                              int tl_n = 0) {
+  auto stamp = [&](int ev) {
+#ifdef VAD_TIMELINE
+    if (tl_role >= 0) tl_stamp(a, tl_role, tl_n, ev);
+#endif
+  };
   // Hand the TMEM accumulator stage back to the MMA warp as soon as its last column is in registers: the rest of
   // the epilogue (math, staging, stores) then overlaps the next tile's MMAs into the same stage.
   auto release_acc = [&]() {
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty);
+    if (lane == 0) mbar_arrive_a(acc_empty);
   };
   const int r = q * 32 + lane;  // accumulator row = pixel slot in the tile
   const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
@@ -178,28 +222,32 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
   const int bb = r >> (a.lgTW + a.lgTH);
   const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);
   const int fb = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
-  const bool valid = (r < rows_valid) && (fb < a.B) && (h < a.H) && (w < a.W);
+  const bool valid = (r < rows_valid) && (fb < a.B) && (h < a.H) && (w < a.W) && (ww < a.tw_valid);
   const bool leader = (q == 0 && lane == 0);
   constexpr int kBufs = staging_bufs(BN, EPI);
 
   if constexpr (EPI == VAD_EPI_STORE || EPI == VAD_EPI_POOL || EPI == VAD_EPI_CONVT) {
     if (a.tma_store) {
-      const int OC = a.out_chunk;
-      const int n_chunks = BN / OC;
+      const int OC = a.out_chunk;                             // 64 or 32
+      const int n_chunks = (OC == 64) ? BN / 64 : BN / 32;    // (compile-time divisions)
+      stamp(9);
 #pragma unroll 1
       for (int oc = 0; oc < n_chunks; ++oc) {
         uint8_t* buf = stg + (kBufs > 1 ? (stg_i & 1) : 0) * staging_buf_bytes(BN, EPI);
         if (leader) {  // the TMA store that last read this buffer must have finished reading it
           if (kBufs > 1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
         }
+        stamp(10);
         named_bar_sync(bar_id, 128);
+        stamp(3);
 #pragma unroll 1
         for (int sub = 0; sub < OC / 32; ++sub) {
           const int lc = oc * OC + sub * 32;
           uint32_t v[32];
-          tmem_ld_x32(tacc + lc, v);
-          tmem_ld_wait();
+          load_acc32<BN, KX>(tacc, lc, v);
+          stamp(4);
           if (lc + 32 == BN) release_acc();
+          if (a.dbg & 32) continue;  // ablation: no epilogue math / staging
           if constexpr (EPI == VAD_EPI_POOL) {
             // 2x2 max-pool as a reduce-scatter over the 4 lanes of a window: exchange halves with the horizontal
             // neighbour (lane^1), then quarters with the vertical neighbour (lane^TW); each lane ends up owning the
@@ -221,13 +269,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
             const int part = (up1 ? 2 : 0) + (up2 ? 1 : 0);  // channels [8*part, 8*part+8) of this 32-column chunk
             const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc + part * 8);
             const float4 b0 = b4[0], b1 = b4[1];
-            const int prow = ((bb << (a.lgTH - 1)) + (hh >> 1)) * (TW >> 1) + (ww >> 1);
+            const int prow = (KX == 3) ? (hh >> 1) * (kKxValid / 2) + (ww >> 1)
+                                       : ((bb << (a.lgTH - 1)) + (hh >> 1)) * (TW >> 1) + (ww >> 1);
             const uint4 val = make_uint4(
                 pack_bf16x2(act_fn(m[0] + b0.x, a.slope), act_fn(m[1] + b0.y, a.slope)),
                 pack_bf16x2(act_fn(m[2] + b0.z, a.slope), act_fn(m[3] + b0.w, a.slope)),
                 pack_bf16x2(act_fn(m[4] + b1.x, a.slope), act_fn(m[5] + b1.y, a.slope)),
                 pack_bf16x2(act_fn(m[6] + b1.z, a.slope), act_fn(m[7] + b1.w, a.slope)));
-            *reinterpret_cast<uint4*>(buf + staged_off(prow, sub * 4 + part, OC)) = val;
+            if (KX == 1 || ww < kKxValid) *reinterpret_cast<uint4*>(buf + staged_off(prow, sub * 4 + part, OC)) = val;
           } else {
             const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc);
             uint32_t p[16];
@@ -239,15 +288,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
               p[2 * j + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * j + 2]) + bv.z, a.slope),
                                          act_fn(__uint_as_float(v[4 * j + 3]) + bv.w, a.slope));
             }
+            const int srow = (KX == 3) ? hh * kKxValid + ww : r;
+            if (KX == 1 || ww < kKxValid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(buf + staged_off(r, sub * 4 + j, OC)) =
-                  make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(buf + staged_off(srow, sub * 4 + j, OC)) =
+                    make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+            }
           }
         }
+        stamp(5);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        stamp(6);
         named_bar_sync(bar_id, 128);
-        if (leader) {
+        stamp(7);
+        if (leader && !(a.dbg & 64)) {  // (ablation bit 64: no TMA store)
           const int col = t.n0 + oc * OC;
           if constexpr (EPI == VAD_EPI_STORE) {
             tma_store_5d(&a.mapOut, buf, col, t.w0, t.h0, a.out_t, t.b0);
@@ -267,8 +322,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_x32(tacc + c * 32, v);
-        tmem_ld_wait();
+        load_acc32<BN, KX>(tacc, c * 32, v);
         if (c * 32 + 32 == BN) release_acc();
         const int col = t.n0 + c * 32;
         float f[32];
@@ -388,6 +442,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
     tmem_ld_x16(tacc, v);
     tmem_ld_wait();
     release_acc();
+    if constexpr (KX == 3) {  // columns [kx][co]: fold the three horizontal taps from the neighbouring rows
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[3 + ch]), 1);
+        const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[6 + ch]), 2);
+        v[ch] = __float_as_uint((__uint_as_float(v[ch]) + s1) + s2);
+      }
+    }
     float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
     if constexpr (EPI == VAD_EPI_TANH_SCORE) {
       if (valid) {
@@ -459,7 +521,8 @@ __device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t
     const int r = q * 32 + lane;
     const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
     const int fb = t.b0 + (r >> (a.lgTW + a.lgTH)), h = t.h0 + ((r >> a.lgTW) & (TH - 1)), w = t.w0 + (r & (TW - 1));
-    const bool valid = (r < (1 << (a.lgTW + a.lgTH + a.lgTN))) && (fb < a.B) && (h < a.H) && (w < a.W);
+    const bool valid = (r < (1 << (a.lgTW + a.lgTH + a.lgTN))) && (fb < a.B) && (h < a.H) && (w < a.W) &&
+                       ((r & (TW - 1)) < a.tw_valid);
     if constexpr (EPI == VAD_EPI_TANH_SCORE) {
       const long long plane = static_cast<long long>(a.H) * a.W;
       const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(h) * a.W + w;
@@ -484,7 +547,7 @@ __device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t
 
 // Shared body of the epilogue warps.  Group g (warps 4+4g .. 7+4g) handles this CTA's tiles g, g+G, g+2G, ...;
 // with G = 2 each group owns one TMEM accumulator stage.
-template <int BN, int EPI, int G = epi_groups(BN)>
+template <int BN, int EPI, int G = epi_groups(BN), int KX = 1, int STRIDE = BN>
 __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_base, int warp, int lane, uint8_t* stg,
                                               const float* s_bias, float (*red_smem)[4][3], uint64_t* acc_full_bar,
                                               uint64_t* acc_empty_bar) {
@@ -494,6 +557,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
   int stg_i = 0;
   // group g walks tiles g, g+G, ... of this CTA; the x pixels a score epilogue needs are fetched one tile ahead
   TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x);
+  const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
   float xcur[12], xnext[12];
   if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xcur);
   for (int n = 0; ti.tile < a.total_tiles; ++n) {
@@ -502,14 +566,18 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
     const TileCoord t = ti.coord(a, BN);
     ti.next(a);
     if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xnext);
-    const bool tl = (g < 2 && q == 0 && lane == 0);
-    if (tl) tl_stamp(a, 2 + g, n, 0);
-    mbar_wait(&acc_full_bar[as], aphase, 4);
-    if (tl) tl_stamp(a, 2 + g, n, 1);
+    // timeline rows 2/3: leaders of groups 0/1, or (VAD_DBG & 4) warps 0 and 3 of group 0
+    const bool tl = lane == 0 && ((a.dbg & 4) ? (g == 0 && (q == 0 || q == 3)) : (g < 2 && q == 0));
+    const int tl_row = (a.dbg & 4) ? (q == 0 ? 2 : 3) : 2 + g;
+    if (tl) tl_stamp(a, tl_row, n, 0);
+    mbar_wait_a(accf0 + as * 8, aphase, 4);
+    if (tl) tl_stamp(a, tl_row, n, 1);
     tc_fence_after();
-    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-    epilogue_tile<BN, EPI>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xcur, &acc_empty_bar[as]);
-    if (tl) tl_stamp(a, 2 + g, n, 2);
+    if (tl) tl_stamp(a, tl_row, n, 8);
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * STRIDE);
+    epilogue_tile<BN, EPI, KX>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xcur, acce0 + as * 8,
+                               tl ? tl_row : -1, n);
+    if (tl) tl_stamp(a, tl_row, n, 2);
 #pragma unroll
     for (int j = 0; j < 12; ++j) xcur[j] = xnext[j];
   }
@@ -531,11 +599,12 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
   __shared__ uint64_t empty_bar[C::kStages];
   __shared__ uint64_t acc_full_bar[kMaxAccStages];
   __shared__ uint64_t acc_empty_bar[kMaxAccStages];
+  __shared__ uint64_t turn_bar[2];  // MMA issuer ping-pong token
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[4][4][3];
+  __shared__ float red_smem[kMaxAccStages][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + C::kStages * C::kStageBytes;
@@ -556,6 +625,8 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
+    mbar_init(&turn_bar[0], 1);
+    mbar_init(&turn_bar[1], 1);
     for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);  // one arrive per warp of the owning epilogue group
@@ -673,11 +744,12 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
   __shared__ uint64_t empty_bar[kHaloMaxStages];
   __shared__ uint64_t acc_full_bar[kMaxAccStages];
   __shared__ uint64_t acc_empty_bar[kMaxAccStages];
+  __shared__ uint64_t turn_bar[2];  // MMA issuer ping-pong token
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[4][4][3];
+  __shared__ float red_smem[kMaxAccStages][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;                                   // 9 weight slabs, resident for the CTA's lifetime
@@ -697,6 +769,8 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
+    mbar_init(&turn_bar[0], 1);
+    mbar_init(&turn_bar[1], 1);
     for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);
@@ -720,27 +794,36 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
       for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_w + tap * kBBytes, &a.mapB, &w_bar, tap * a.w_ctap, 0);
     }
     __syncwarp();
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t sa0 = smem_addr_once(s_a);
     int stage = 0;
     uint32_t phase = 0;
     int pn = 0;
     for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a), ++pn) {
       const TileCoord t = ti.coord(a, BN);
       if (lane == 0) tl_stamp(a, 0, pn, 0);
-      mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
       if (lane == 0) tl_stamp(a, 0, pn, 1);
       if (elect_one()) {
-        uint8_t* sa = s_a + stage * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], patch_tx);
-        for (int p = 0; p < a.halo_npatch; ++p)
-          tma_load_5d(sa + p * a.halo_patch_bytes, &a.mapA0, &full_bar[stage], 0, t.w0 - 1 + p, t.h0 - 1, a.tA0, t.b0);
+        const uint32_t sa = sa0 + stage * stage_bytes;
+        if ((a.dbg & 128) && pn >= a.halo_stages) {  // ablation: no input traffic after the ring's first fill
+          mbar_arrive_a(full0 + stage * 8);
+        } else {
+          mbar_arrive_expect_tx_a(full0 + stage * 8, patch_tx);
+          for (int p = 0; p < a.halo_npatch; ++p)
+            tma_load_5d_a(sa + p * a.halo_patch_bytes, &a.mapA0, full0 + stage * 8, 0, t.w0 - 1 + p, t.h0 - 1, a.tA0,
+                          t.b0);
+        }
       }
       __syncwarp();
       if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1 || warp == 3) {
     // ===================================================================== MMA issuers (two warps, alternate tiles)
-    // One issuer alone leaves the tensor pipe idle while it sits in the two mbarrier waits of the next tile
-    // (~350 cycles even when they are already satisfied); with two, one waits while the other's MMAs are in flight.
+    // The issuer is a single warp running scalar code whose per-tile latency (two barrier waits, 18 descriptor
+    // updates, 18 issues, two commits) exceeds the tensor pipe's time for the tile; with two warps taking alternate
+    // tiles one waits / prepares while the other's MMAs are in flight.  A token (turn_bar) makes them issue strictly
+    // in tile order.
     const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
     const uint32_t sbo = static_cast<uint32_t>(a.halo_sbo_rows * kRowBytes);
@@ -751,34 +834,42 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
       tap_off[tap] = static_cast<uint32_t>(a.tap_patch[tap] * a.halo_patch_bytes + a.tap_row[tap] * kRowBytes) >> 4;
     const uint64_t da_hi = umma_smem_desc(0, sbo, kLayout);             // everything but the start address
     const uint64_t db0 = umma_smem_desc(smem_u32(s_w), 8 * kRowBytes, kLayout);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint32_t turn0 = smem_addr_once(&turn_bar[0]);
+    const uint32_t sa16_0 = (smem_u32(s_a) & 0x3FFFF) >> 4, stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+    const bool dual = a.dual_mma != 0;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      if (!a.dual_mma && mi == 1) break;
-      if (!a.dual_mma || (it & 1) == mi) {
+      if (!dual && mi == 1) break;
+      if (!dual || (it & 1) == mi) {
         const int as = it % kAS;
         if (lane == 0) tl_stamp(a, 1, it, 0);
-        mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
+        mbar_wait_a(acce0 + as * 8, ((it / kAS) & 1) ^ 1u, 3);
         if (lane == 0) tl_stamp(a, 1, it, 1);
-        mbar_wait(&full_bar[stage], phase, 2);
+        mbar_wait_a(full0 + stage * 8, phase, 2);
+        if (dual && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-          const uint32_t sa16 = (smem_u32(s_a + stage * stage_bytes) & 0x3FFFF) >> 4;
+          const uint64_t da0 = da_hi + static_cast<uint64_t>(sa16_0 + stage * stage16);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t da = da_hi | static_cast<uint64_t>(sa16 + tap_off[tap]);
+            if ((a.dbg & 16) && tap > 0) break;  // ablation: one tap only
+            const uint64_t da = da0 + static_cast<uint64_t>(tap_off[tap]);
             const uint64_t db = db0 + static_cast<uint64_t>((tap * kBBytes) >> 4);
 #pragma unroll
             for (int kk = 0; kk < CK / 16; ++kk)
               umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
                         (tap > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&acc_full_bar[as]);
+          umma_commit_a(empty0 + stage * 8);
+          umma_commit_a(accf0 + as * 8);
+          if (dual) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);
@@ -787,6 +878,148 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     }
   } else if (warp >= kEpiWarp0) {
     epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- kx-merged halo
+// 3x3 conv with the horizontal taps folded into N (see kx_mma_n above).  Per tile: ONE TMA patch of 18 rows x 8
+// columns x CK channels (rows h0-1 .. h0+16, columns w0-1 .. w0+6); A operand of vertical tap ky = the patch shifted
+// down by ky rows (start address + ky*8 pixel rows, standard 8-row core groups); B = resident weight slab ky of
+// [kx*Cout + co][ci].  3 * CK/16 MMAs per tile instead of 9 * CK/16, each with 3x the columns.
+template <int CK, int BN, int EPI>
+__global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int kRowBytes = CK * 2;
+  constexpr int NM = kx_mma_n(BN, EPI);       // MMA N extent
+  constexpr int kBBytes = NM * kRowBytes;     // one vertical tap's weight slab
+  constexpr int kPatchBytes = 8 * 18 * kRowBytes;
+  constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;
+  constexpr int G = kx_groups(BN, EPI);
+  constexpr int kStride = kx_acc_stride(BN, EPI);
+  constexpr uint32_t kTmemCols = kx_tmem_cols(BN, EPI);
+  static_assert(kBBytes % 1024 == 0 && kPatchBytes % 1024 == 0, "operand slabs must keep 1024B alignment");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_bar;
+  __shared__ uint64_t full_bar[kHaloMaxStages];
+  __shared__ uint64_t empty_bar[kHaloMaxStages];
+  __shared__ uint64_t acc_full_bar[kMaxAccStages];
+  __shared__ uint64_t acc_empty_bar[kMaxAccStages];
+  __shared__ uint64_t turn_bar[2];  // MMA issuer ping-pong token
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float red_smem[kMaxAccStages][4][3];
+  __shared__ __align__(16) float s_bias[kMaxBias];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;                               // 3 weight slabs, resident for the CTA's lifetime
+  uint8_t* s_a = smem + 3 * kBBytes;                 // ring of input patches
+  uint8_t* stg = s_a + a.halo_stages * kPatchBytes;  // epilogue staging
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapB);
+    if (a.tma_store) tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < a.halo_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&turn_bar[0], 1);
+    mbar_init(&turn_bar[1], 1);
+    for (int i = 0; i < kMaxAccStages; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kTmemCols>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += 128 + 128 * G) s_bias[i] = a.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&w_bar, 3u * kBBytes);
+      for (int ky = 0; ky < 3; ++ky) tma_load_2d(s_w + ky * kBBytes, &a.mapB, &w_bar, ky * a.w_ctap, 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    int pn = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a), ++pn) {
+      const TileCoord t = ti.coord(a, BN);
+      if (lane == 0) tl_stamp(a, 0, pn, 0);
+      mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+      if (lane == 0) tl_stamp(a, 0, pn, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], kPatchBytes);
+        tma_load_5d(s_a + stage * kPatchBytes, &a.mapA0, &full_bar[stage], 0, t.w0 - 1, t.h0 - 1, a.tA0, t.b0);
+      }
+      __syncwarp();
+      if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================================================================== MMA issuers (alternate tiles)
+    const int mi = warp == 1 ? 0 : 1;
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, NM);
+    const uint64_t da_hi = umma_smem_desc(0, 8 * kRowBytes, kLayout);
+    const uint64_t db0 = umma_smem_desc(smem_u32(s_w), 8 * kRowBytes, kLayout);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    mbar_wait(&w_bar, 0, 5);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      if (!a.dual_mma && mi == 1) break;
+      if (!a.dual_mma || (it & 1) == mi) {
+        const int as = it % G;
+        if (lane == 0) tl_stamp(a, 1, it, 0);
+        mbar_wait(&acc_empty_bar[as], ((it / G) & 1) ^ 1u, 3);
+        if (lane == 0) tl_stamp(a, 1, it, 1);
+        mbar_wait(&full_bar[stage], phase, 2);
+        // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
+        // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
+        // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
+        if (a.dual_mma && it > 0) mbar_wait(&turn_bar[mi], static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
+        if (lane == 0) tl_stamp(a, 1, it, 2);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kStride);
+          const uint32_t sa16 = (smem_u32(s_a + stage * kPatchBytes) & 0x3FFFF) >> 4;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint64_t da = da_hi | static_cast<uint64_t>(sa16 + ((ky * 8 * kRowBytes) >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>((ky * kBBytes) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < CK / 16; ++kk)
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (ky > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&acc_full_bar[as]);
+          if (a.dual_mma) mbar_arrive(&turn_bar[mi ^ 1]);
+        }
+        __syncwarp();
+        if (lane == 0) tl_stamp(a, 1, it, 3);
+      }
+      if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    epilogue_loop<BN, EPI, G, 3, kStride>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
   }
 
   tc_fence_before();
@@ -827,11 +1060,12 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   __shared__ uint64_t empty_bar[kFirstStages];
   __shared__ uint64_t acc_full_bar[kMaxAccStages];
   __shared__ uint64_t acc_empty_bar[kMaxAccStages];
+  __shared__ uint64_t turn_bar[2];  // MMA issuer ping-pong token
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_smem[4][4][3];
+  __shared__ float red_smem[kMaxAccStages][4][3];
   __shared__ __align__(16) float s_bias[kMaxBias];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;                                   // [32 n][32 k] bf16, 64B-swizzled (2 KB slot)
@@ -850,6 +1084,8 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       mbar_init(&full_bar[i], 4);
       mbar_init(&empty_bar[i], 1);
     }
+    mbar_init(&turn_bar[0], 1);
+    mbar_init(&turn_bar[1], 1);
     for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);
@@ -903,6 +1139,10 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
         mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
         if (lane == 0) tl_stamp(a, 1, it, 1);
         mbar_wait(&full_bar[stage], phase, 2);
+        // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
+        // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
+        // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
+        if (a.dual_mma && it > 0) mbar_wait(&turn_bar[mi], static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
@@ -912,6 +1152,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
           umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
           umma_commit(&empty_bar[stage]);
           umma_commit(&acc_full_bar[as]);
+          if (a.dual_mma) mbar_arrive(&turn_bar[mi ^ 1]);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);
@@ -1082,6 +1323,52 @@ int launch_conv_halo(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaS
 #define X(ck, bn, epi) \
   if (CK == ck && BN == bn && EPI == epi) return launch_halo_one<ck, bn, epi>(a, grid, stream);
   VAD_HALO_CASES(X)
+#undef X
+  return VAD_ERR_UNSUPPORTED;
+}
+
+template <int CK, int BN, int EPI>
+static constexpr int kx_fixed_bytes() {
+  return 1024 + 3 * kx_mma_n(BN, EPI) * CK * 2 + kx_groups(BN, EPI) * staging_group_bytes(BN, EPI);
+}
+
+template <int CK, int BN, int EPI>
+static int launch_kx_one(const ConvArgs& a, int grid, cudaStream_t stream) {
+  const int smem = kx_fixed_bytes<CK, BN, EPI>() + a.halo_stages * (8 * 18 * CK * 2);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_kx_kernel<CK, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = smem;
+  }
+  conv_kx_kernel<CK, BN, EPI><<<grid, 128 + 128 * kx_groups(BN, EPI), smem, stream>>>(a);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+#define VAD_KX_CASES(X)                \
+  X(32, 32, VAD_EPI_STORE)             \
+  X(32, 32, VAD_EPI_POOL)              \
+  X(32, 64, VAD_EPI_STORE)             \
+  X(32, 64, VAD_EPI_POOL)              \
+  X(64, 64, VAD_EPI_STORE)             \
+  X(64, 64, VAD_EPI_POOL)              \
+  X(32, 16, VAD_EPI_TANH_SCORE)
+
+// dynamic smem of the kx kernel without the patch ring (0: configuration not instantiated)
+int kx_fixed_smem_bytes(int CK, int BN, int EPI) {
+#define X(ck, bn, epi) \
+  if (CK == ck && BN == bn && EPI == epi) return kx_fixed_bytes<ck, bn, epi>();
+  VAD_KX_CASES(X)
+#undef X
+  return 0;
+}
+int kx_mma_columns(int BN, int EPI) { return kx_mma_n(BN, EPI); }
+
+int launch_conv_kx(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
+#define X(ck, bn, epi) \
+  if (CK == ck && BN == bn && EPI == epi) return launch_kx_one<ck, bn, epi>(a, grid, stream);
+  VAD_KX_CASES(X)
 #undef X
   return VAD_ERR_UNSUPPORTED;
 }

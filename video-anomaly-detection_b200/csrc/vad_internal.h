@@ -22,6 +22,8 @@ struct alignas(64) ConvArgs {
   int B, H, W;
   int lgTW, lgTH, lgTN;
   int tiles_w, tiles_h, tiles_b;
+  int w_step;    // columns between consecutive tiles (1 << lgTW, or 6 for the kx-merged kernel)
+  int tw_valid;  // valid output columns per tile row (1 << lgTW, or 6)
   int n_tiles;
   int total_tiles;
   const float* bias;
@@ -64,6 +66,9 @@ TileGeom pick_tile_geometry(int B, int H, int W, bool single_frame_tiles);
 
 int launch_conv_umma(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_conv_halo(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
+int launch_conv_kx(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
+int kx_fixed_smem_bytes(int CK, int BN, int EPI);
+int kx_mma_columns(int BN, int EPI);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 // dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)
 int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);

@@ -72,6 +72,54 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// ---- variants taking the barrier's 32-bit shared address.  The address of a __shared__ object costs an S2UR
+// (CTA rank in the cluster window) plus uniform ALU ops every time it is formed; hot loops form it once
+// (smem_addr_once) and index from there.
+__device__ __forceinline__ uint32_t smem_addr_once(const void* p) {
+  uint32_t a = smem_u32(p);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));  // opaque: keeps the compiler from rematerialising the S2UR sequence
+  return a;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t tag) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) {
+      if (g_vad_trap_slot) {
+        g_vad_trap_slot[0] = tag;
+        g_vad_trap_slot[1] = blockIdx.x;
+        g_vad_trap_slot[2] = threadIdx.x;
+        g_vad_trap_slot[3] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+// fast path = one try_wait (which itself blocks for a while in hardware); the bounded slow path is out of line so
+// that it does not bloat the role loops
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+  if (mbar_try_wait_a(bar, parity)) return;
+  if (mbar_try_wait_a(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
+}
+
 // (Measured: letting one lane poll and parking the other 31 at __syncwarp is SLOWER than all 32 lanes polling —
 // 1307 vs 1033 cycles per tile on the halo kernel — so every role warp waits with all its lanes.)
 
@@ -91,6 +139,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
       "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_a(uint32_t smem_dst, const void* desc, uint32_t bar, int c0, int c1,
+                                              int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1,
@@ -199,6 +255,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

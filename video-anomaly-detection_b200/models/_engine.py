@@ -67,12 +67,12 @@ class _Buffers:
         return t
 
 
-def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: int, slope: float,
+def _gemm_desc(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: int, slope: float,
                 out: Optional[torch.Tensor], *, c0: int = 0, T0: int = 1, t0: int = 0, src1: Optional[torch.Tensor] = None,
                 c1: int = 0, T1: int = 1, t1: int = 0, out_frame_stride: int = 0, out_cpitch: int = 0,
                 out_offset_elems: int = 0, c_state: Optional[torch.Tensor] = None, lstm_first: bool = False,
                 x: Optional[torch.Tensor] = None, recon: Optional[torch.Tensor] = None,
-                heat: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None, what: str = "") -> None:
+                heat: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None) -> "nat.ConvDesc":
     d = nat.ConvDesc()
     d.src0 = src.data_ptr()
     d.src1 = nat.ptr(src1)
@@ -82,6 +82,7 @@ def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: 
     d.B, d.H, d.W = B, H, W
     d.ntaps = w.ntaps
     d.weight = w.w.data_ptr()
+    d.weight_kx = nat.ptr(w.w_kx)
     d.bias = w.bias.data_ptr()
     d.w_ctap = w.ctap
     d.n_total = w.n_total
@@ -95,7 +96,28 @@ def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: 
     d.c_state = nat.ptr(c_state)
     d.lstm_first = 1 if lstm_first else 0
     d.x, d.recon, d.heat, d.partials = nat.ptr(x), nat.ptr(recon), nat.ptr(heat), nat.ptr(partials)
+    return d
+
+
+def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: int, slope: float,
+                out: Optional[torch.Tensor], *, what: str = "", **kw) -> None:
+    d = _gemm_desc(w, src, B, H, W, epi, slope, out, **kw)
     _timed(what or "vad_conv_layer", lambda: nat.conv_layer(d, what or "vad_conv_layer"))
+
+
+def _score_layer(w: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int, epi: int, x: torch.Tensor,
+                 want_recon: bool, want_heat: bool, Ho: int, Wo: int, bufs: "_Buffers", what: str) -> "ScoreOutputs":
+    """Last decoder layer with the fused tanh + (x - recon)^2 reduction, then the per-frame finalisation."""
+    dev = x.device
+    recon = torch.empty(frames, 3, Ho, Wo, dtype=torch.float32, device=dev) if want_recon else None
+    heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
+    d = _gemm_desc(w, src, frames, H, W, epi, IDENT, None, x=x, recon=recon, heat=heat, partials=x)
+    tiles = nat.layer_tiles(d)  # the tiling (and so the number of per-tile partials) is the library's choice
+    partials = bufs.get("partials", (tiles, 4), torch.float32, dev)
+    d.partials = partials.data_ptr()
+    _timed(what, lambda: nat.conv_layer(d, what))
+    score, minmax = _finalize(partials, frames, tiles // frames, Ho, Wo, bufs, dev)
+    return ScoreOutputs(score, minmax, heat, recon)
 
 
 FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
@@ -191,14 +213,8 @@ class ImageEngine:
                 nxt = g(f"{blk}b", (B, h, w, wc.n_total))
                 _conv(wc, cur, B, h, w, nxt, RELU, what=f"{blk}.3")
                 cur = nxt
-        tiles = nat.m_tiles(B, H, W, True)
-        partials = self.bufs.get("partials", (tiles, 4), torch.float32, dev)
-        recon = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
-        heat = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_heat else None
-        _gemm_layer(p["dec4.3"], cur, B, H, W, nat.EPI_TANH_SCORE, IDENT, None, x=x, recon=recon, heat=heat,
-                    partials=partials, what="dec4.3+score")
-        score, minmax = _finalize(partials, B, tiles // B, H, W, self.bufs, dev)
-        return ScoreOutputs(score, minmax, heat, recon)
+        return _score_layer(p["dec4.3"], cur, B, H, W, nat.EPI_TANH_SCORE, x, want_recon, want_heat, H, W, self.bufs,
+                            "dec4.3+score")
 
 
 class VideoEngine:
@@ -276,11 +292,5 @@ class VideoEngine:
         seq = self.convlstm(z.view(B, T, h, w, z.shape[-1]), B, T, h, w)
         zp = self.project(seq.view(F, h, w, seq.shape[-1]), F, h, w)
         d, hd, wd = self.decode_to(zp, F, h, w)
-        tiles = nat.m_tiles(F, hd, wd, True)
-        partials = self.bufs.get("partials", (tiles, 4), torch.float32, dev)
-        recon = torch.empty(F, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
-        heat = torch.empty(F, H, W, dtype=torch.float32, device=dev) if want_heat else None
-        _gemm_layer(self.p["dec.9"], d, F, hd, wd, nat.EPI_CONVT_TANH_SCORE, IDENT, None, x=x4, recon=recon,
-                    heat=heat, partials=partials, what="decoder.9+score")
-        score, minmax = _finalize(partials, F, tiles // F, H, W, self.bufs, dev)
-        return ScoreOutputs(score, minmax, heat, recon)
+        return _score_layer(self.p["dec.9"], d, F, hd, wd, nat.EPI_CONVT_TANH_SCORE, x4, want_recon, want_heat, H, W,
+                            self.bufs, "decoder.9+score")

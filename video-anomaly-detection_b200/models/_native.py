@@ -17,7 +17,7 @@ EPI_STORE, EPI_POOL, EPI_CONVT, EPI_LSTM, EPI_TANH_SCORE, EPI_CONVT_TANH_SCORE =
 
 # every symbol include/vad_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_conv_layer", "vad_convlstm_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
+    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convlstm_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8",
 )
@@ -40,6 +40,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_frame_stride", C.c_longlong), ("out_cpitch", C.c_int),
         ("c_state", C.c_void_p), ("lstm_first", C.c_int),
         ("x", C.c_void_p), ("recon", C.c_void_p), ("heat", C.c_void_p), ("partials", C.c_void_p),
+        ("weight_kx", C.c_void_p),
     ]
 
 
@@ -60,7 +61,9 @@ def load() -> C.CDLL:
     lib.vad_version.restype = C.c_int
     lib.vad_launch_count.restype = C.c_ulonglong
     lib.vad_debug_set_timeline.argtypes = [C.c_void_p]
+    lib.vad_debug_set_kx.argtypes = [C.c_int]
     lib.vad_conv_layer.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
+    lib.vad_conv_layer_tiles.argtypes = [C.POINTER(ConvDesc)]
     lib.vad_convlstm_sequence.argtypes = [C.POINTER(ConvDesc), C.c_int, C.c_void_p]
     lib.vad_conv_m_tiles.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.vad_first_conv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
@@ -103,6 +106,14 @@ def launch_count() -> int:
 
 def conv_layer(desc: ConvDesc, what: str = "vad_conv_layer") -> None:
     check(load().vad_conv_layer(C.byref(desc), stream_ptr()), what)
+
+
+def layer_tiles(desc: ConvDesc) -> int:
+    """M tiles vad_conv_layer will use for `desc` (rows of the per-tile partials of a *_SCORE layer)."""
+    n = load().vad_conv_layer_tiles(C.byref(desc))
+    if n <= 0:
+        check(n if n < 0 else -1, "vad_conv_layer_tiles")
+    return n
 
 
 def m_tiles(B: int, H: int, W: int, single_frame: bool) -> int:

@@ -26,6 +26,9 @@ class GemmWeights:
     ctap: int      # input channels per tap (weight columns per tap)
     n_total: int
     cout: int      # real output channels
+    # narrow 3x3 layers only: the same weights as [kx*Cout + co (zero rows up to a multiple of 16)][ky*Cin + ci], the
+    # layout of the kernel that folds the horizontal taps into the GEMM N extent (include/vad_b200.h `weight_kx`)
+    w_kx: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -76,7 +79,20 @@ def pack_conv3x3(w: torch.Tensor, b: torch.Tensor, pad_n_to: int = 0) -> GemmWei
     if n_total > cout:
         wk = torch.cat([wk, wk.new_zeros(n_total - cout, 9 * cin)], 0)
         b = torch.cat([b, b.new_zeros(n_total - cout)], 0)
-    return GemmWeights(wk.to(torch.bfloat16).contiguous(), b.float().contiguous(), 9, cin, n_total, cout)
+    gw = GemmWeights(wk.to(torch.bfloat16).contiguous(), b.float().contiguous(), 9, cin, n_total, cout)
+    if cout <= 64 and cin in (32, 64):
+        gw.w_kx = pack_conv3x3_kx(w)
+    return gw
+
+
+def pack_conv3x3_kx(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,3,3] -> bf16 [3*Cout padded to a multiple of 16, 3*Cin]: row = kx*Cout + co, column = ky*Cin + ci."""
+    cout, cin = w.shape[0], w.shape[1]
+    wk = w.permute(3, 0, 2, 1).reshape(3 * cout, 3 * cin)  # [kx, co, ky, ci]
+    rows = (3 * cout + 15) // 16 * 16
+    if rows > 3 * cout:
+        wk = torch.cat([wk, wk.new_zeros(rows - 3 * cout, 3 * cin)], 0)
+    return wk.to(torch.bfloat16).contiguous()
 
 
 def pack_conv1x1(w: torch.Tensor, b: torch.Tensor) -> GemmWeights:
@@ -171,5 +187,7 @@ def to_device(packed: Dict[str, object], device) -> Dict[str, object]:
             v.bias = v.bias.to(device)
             if isinstance(v, FirstConvWeights) and v.w_tc is not None:
                 v.w_tc = v.w_tc.to(device)
+            if isinstance(v, GemmWeights) and v.w_kx is not None:
+                v.w_kx = v.w_kx.to(device)
         res[k] = v
     return res
