@@ -646,30 +646,32 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
   // Role loops are executed by the WHOLE warp (uniform control flow); one elected lane issues the TMA / MMA.
   if (warp == 0) {
     // ===================================================================== TMA producer
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t smem0 = smem_addr_once(smem);
     int stage = 0;
     uint32_t phase = 0;
     for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
       const TileCoord t = ti.coord(a, BN);
+      int dy = (a.ntaps == 9) ? -1 : 0, dx = dy;
       for (int tap = 0; tap < a.ntaps; ++tap) {
         int kcol = tap * a.w_ctap;
-        const int dy = (a.ntaps == 9) ? (tap / 3 - 1) : 0;
-        const int dx = (a.ntaps == 9) ? (tap % 3 - 1) : 0;
         for (int c = 0; c < chunks; ++c) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+          mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
           if (elect_one()) {
-            uint8_t* sa = smem + stage * C::kStageBytes;
-            uint8_t* sb = sa + C::kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            const uint32_t sa = smem0 + stage * C::kStageBytes;
+            const uint32_t fb = full0 + stage * 8;
+            mbar_arrive_expect_tx_a(fb, tx_bytes);
             if (c < a.chunks0)
-              tma_load_5d(sa, &a.mapA0, &full_bar[stage], c * CK, t.w0 + dx, t.h0 + dy, a.tA0, t.b0);
+              tma_load_5d_a(sa, &a.mapA0, fb, c * CK, t.w0 + dx, t.h0 + dy, a.tA0, t.b0);
             else
-              tma_load_5d(sa, &a.mapA1, &full_bar[stage], (c - a.chunks0) * CK, t.w0 + dx, t.h0 + dy, a.tA1, t.b0);
-            tma_load_2d(sb, &a.mapB, &full_bar[stage], kcol, t.n0);
+              tma_load_5d_a(sa, &a.mapA1, fb, (c - a.chunks0) * CK, t.w0 + dx, t.h0 + dy, a.tA1, t.b0);
+            tma_load_2d_a(sa + C::kABytes, &a.mapB, fb, kcol, t.n0);
           }
           __syncwarp();
           kcol += CK;
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
+        if (++dx == 2) { dx = -1; ++dy; }  // next tap (3x3: row-major over (dy, dx) in -1..1)
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -680,6 +682,10 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
     const bool dual = a.dual_mma && k_iters < C::kStages;
     const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(smem), C::kSBO, C::kLayout);
+    const uint64_t db_base = umma_smem_desc(smem_u32(smem + C::kABytes), C::kSBO, C::kLayout);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -692,24 +698,24 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
         continue;
       }
       const int as = it % kAS;
-      mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
+      mbar_wait_a(acce0 + as * 8, ((it / kAS) & 1) ^ 1u, 3);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
       for (int k = 0; k < k_iters; ++k) {
-        mbar_wait(&full_bar[stage], phase, 2);
+        mbar_wait_a(full0 + stage * 8, phase, 2);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t da = umma_smem_desc(sa, C::kSBO, C::kLayout);
-          const uint64_t db = umma_smem_desc(sa + C::kABytes, C::kSBO, C::kLayout);
+          const uint64_t soff = static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+          const uint64_t da = da_base + soff;
+          const uint64_t db = db_base + soff;
 #pragma unroll
           for (int kk = 0; kk < CK / 16; ++kk) {
             // advance 16 bf16 = 32 B inside the swizzle span: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
                       (k > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
-          if (k == k_iters - 1) umma_commit(&acc_full_bar[as]);  // accumulator ready for the epilogue
+          umma_commit_a(empty0 + stage * 8);                       // frees the smem slot when these MMAs retire
+          if (k == k_iters - 1) umma_commit_a(accf0 + as * 8);      // accumulator ready for the epilogue
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -958,17 +964,19 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
       for (int ky = 0; ky < 3; ++ky) tma_load_2d(s_w + ky * kBBytes, &a.mapB, &w_bar, ky * a.w_ctap, 0);
     }
     __syncwarp();
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t sa0 = smem_addr_once(s_a);
     int stage = 0;
     uint32_t phase = 0;
     int pn = 0;
     for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a), ++pn) {
       const TileCoord t = ti.coord(a, BN);
       if (lane == 0) tl_stamp(a, 0, pn, 0);
-      mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
       if (lane == 0) tl_stamp(a, 0, pn, 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full_bar[stage], kPatchBytes);
-        tma_load_5d(s_a + stage * kPatchBytes, &a.mapA0, &full_bar[stage], 0, t.w0 - 1, t.h0 - 1, a.tA0, t.b0);
+        mbar_arrive_expect_tx_a(full0 + stage * 8, kPatchBytes);
+        tma_load_5d_a(sa0 + stage * kPatchBytes, &a.mapA0, full0 + stage * 8, 0, t.w0 - 1, t.h0 - 1, a.tA0, t.b0);
       }
       __syncwarp();
       if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
@@ -979,27 +987,32 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, NM);
     const uint64_t da_hi = umma_smem_desc(0, 8 * kRowBytes, kLayout);
     const uint64_t db0 = umma_smem_desc(smem_u32(s_w), 8 * kRowBytes, kLayout);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint32_t turn0 = smem_addr_once(&turn_bar[0]);
+    const uint32_t sa16_0 = (smem_u32(s_a) & 0x3FFFF) >> 4;
+    const bool dual = a.dual_mma != 0;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      if (!a.dual_mma && mi == 1) break;
-      if (!a.dual_mma || (it & 1) == mi) {
+      if (!dual && mi == 1) break;
+      if (!dual || (it & 1) == mi) {
         const int as = it % G;
         if (lane == 0) tl_stamp(a, 1, it, 0);
-        mbar_wait(&acc_empty_bar[as], ((it / G) & 1) ^ 1u, 3);
+        mbar_wait_a(acce0 + as * 8, ((it / G) & 1) ^ 1u, 3);
         if (lane == 0) tl_stamp(a, 1, it, 1);
-        mbar_wait(&full_bar[stage], phase, 2);
+        mbar_wait_a(full0 + stage * 8, phase, 2);
         // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
         // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
         // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
-        if (a.dual_mma && it > 0) mbar_wait(&turn_bar[mi], static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
+        if (dual && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kStride);
-          const uint32_t sa16 = (smem_u32(s_a + stage * kPatchBytes) & 0x3FFFF) >> 4;
+          const uint32_t sa16 = sa16_0 + stage * (kPatchBytes >> 4);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
             const uint64_t da = da_hi | static_cast<uint64_t>(sa16 + ((ky * 8 * kRowBytes) >> 4));
@@ -1009,9 +1022,9 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
               umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
                         (ky > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&acc_full_bar[as]);
-          if (a.dual_mma) mbar_arrive(&turn_bar[mi ^ 1]);
+          umma_commit_a(empty0 + stage * 8);
+          umma_commit_a(accf0 + as * 8);
+          if (dual) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);
@@ -1038,8 +1051,10 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
 // the same as everywhere else.  Replaces models/autoencoder.py:39-41 and models/video_autoencoder.py:193-196 (with
 // the 2x2 max-pool fused for the video encoder).
 constexpr int kFirstStages = 6;
-constexpr int kFirstThreads = 128 + 256 + 256;  // roles | two epilogue groups | two groups of four converter warps
-constexpr int kFirstConvWarp0 = 12;
+constexpr int kFirstGroupsC = 4;                // epilogue groups
+constexpr int kConvWarps = 4;                   // converter warps; each converts whole tiles (every 4th)
+constexpr int kFirstConvWarp0 = 4 + 4 * kFirstGroupsC;
+constexpr int kFirstThreads = 32 * (kFirstConvWarp0 + kConvWarps);  // roles | epilogue groups | converters
 // fp32 patch: 24 columns x 10 rows x 3 channels starting at column w0-4: TMA needs the box's first byte 16-byte
 // aligned in the innermost dimension, so the 1-pixel left halo is fetched as part of an aligned group of four
 constexpr int kPatchW = 24, kPatchH = 10, kPatchX0 = 4;
@@ -1049,7 +1064,7 @@ constexpr int kPatchStride = 3072;                             // ring pitch
 template <int EPI>
 __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int BN = 32;
-  constexpr int kFirstGroups = 2;       // 16 warps are already spoken for (roles, converters): two epilogue groups
+  constexpr int kFirstGroups = kFirstGroupsC;
   constexpr int kAS = acc_stages_for(kFirstGroups);
   constexpr int kABytes = kTileM * 64;  // 128 rows x 32 bf16
   constexpr uint32_t kTmemCols = tmem_cols_for(BN, kFirstGroups);
@@ -1080,8 +1095,8 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kFirstStages; ++i) {
       mbar_init(&patch_full[i], 1);
-      mbar_init(&patch_empty[i], 4);  // one arrive per converter warp
-      mbar_init(&full_bar[i], 4);
+      mbar_init(&patch_empty[i], 1);  // one arrive by the converter warp that consumed the patch
+      mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&turn_bar[0], 1);
@@ -1128,31 +1143,36 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
     const uint64_t db = umma_smem_desc(smem_u32(s_w), 512, 4u);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint32_t turn0 = smem_addr_once(&turn_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 512, 4u);
+    const bool dual = a.dual_mma != 0;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      if (!a.dual_mma && mi == 1) break;
-      if (!a.dual_mma || (it & 1) == mi) {
+      if (!dual && mi == 1) break;
+      if (!dual || (it & 1) == mi) {
         const int as = it % kAS;
         if (lane == 0) tl_stamp(a, 1, it, 0);
-        mbar_wait(&acc_empty_bar[as], ((it / kAS) & 1) ^ 1u, 3);
+        mbar_wait_a(acce0 + as * 8, ((it / kAS) & 1) ^ 1u, 3);
         if (lane == 0) tl_stamp(a, 1, it, 1);
-        mbar_wait(&full_bar[stage], phase, 2);
+        mbar_wait_a(full0 + stage * 8, phase, 2);
         // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
         // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
         // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
-        if (a.dual_mma && it > 0) mbar_wait(&turn_bar[mi], static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
+        if (dual && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-          const uint64_t da = umma_smem_desc(smem_u32(s_a + stage * kABytes), 512, 4u);
+          const uint64_t da = da_base + static_cast<uint64_t>(stage * (kABytes >> 4));
           umma_bf16(d_tmem, da, db, idesc, 0u);
           umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&acc_full_bar[as]);
-          if (a.dual_mma) mbar_arrive(&turn_bar[mi ^ 1]);
+          umma_commit_a(empty0 + stage * 8);
+          umma_commit_a(accf0 + as * 8);
+          if (dual) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);
@@ -1161,47 +1181,74 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     }
   } else if (warp >= kFirstConvWarp0) {
     // ===================================================================== converters: fp32 patch -> bf16 im2col rows
-    // two groups of four warps take alternate tiles (the conversion is latency-bound: LDS -> pack -> STS -> fence)
-    const int cg = (warp - kFirstConvWarp0) >> 2;
-    const int r = ((warp - kFirstConvWarp0) & 3) * 32 + lane;  // pixel slot = A row
-    const int ww = r & 15, hh = r >> 4;                        // tile = 8 rows x 16 columns of one frame
+    // One warp converts a whole tile; a lane owns four horizontally adjacent pixels of one row so that the patch is
+    // read with 27 LDS.128 per lane (instead of 108 scalar loads for the same four pixels).  K order
+    // k = (ky*3 + kx)*3 + ci; the 16-byte chunks of a pixel's A row (8 k-values each) are written as soon as the
+    // vertical tap that completes them has been loaded, which keeps the live register set small.
+    const int cw = warp - kFirstConvWarp0;
+    const int row = lane >> 2, jg = lane & 3;  // tile = 8 rows x 16 columns; this lane: row, columns 4*jg .. 4*jg+3
+    const int r0 = row * 16 + 4 * jg;          // A row of the lane's first pixel
+    const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != cg) continue;
+      if ((it & (kConvWarps - 1)) != cw) continue;
       const int stage = it % kFirstStages;
       const uint32_t phase = (it / kFirstStages) & 1;
-      const bool tl = (warp == kFirstConvWarp0 + 4 * cg && lane == 0);
-      if (tl) tl_stamp(a, 0, it, 0);
-      mbar_wait(&patch_full[stage], phase, 6);
-      if (tl) tl_stamp(a, 0, it, 1);
-      const float* pp = reinterpret_cast<const float*>(s_p + stage * kPatchStride) + hh * kPatchW + ww + (kPatchX0 - 1);
-      float v[27];  // k = (ky*3 + kx)*3 + ci
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-          for (int ci = 0; ci < 3; ++ci)
-            v[(ky * 3 + kx) * 3 + ci] = (a.dbg & 2) ? 0.f : pp[ci * (kPatchH * kPatchW) + ky * kPatchW + kx];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&patch_empty[stage]);  // patch slot may be refilled
-      uint32_t p[16];
-#pragma unroll
-      for (int j = 0; j < 13; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      p[13] = pack_bf16x2(v[26], 0.f);
-      p[14] = 0u;
-      p[15] = 0u;
-      if (tl) tl_stamp(a, 0, it, 2);
-      mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-      if (tl) tl_stamp(a, 0, it, 3);
+      if (lane == 0) tl_stamp(a, 0, it, 0);
+      mbar_wait_a(pfull0 + stage * 8, phase, 6);
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
+      if (lane == 0) tl_stamp(a, 0, it, 1);
+      // patch column of pixel ww, tap kx: ww + (kPatchX0 - 1) + kx; the lane reads columns 4*jg .. 4*jg + 11
+      const float* pp = reinterpret_cast<const float*>(s_p + stage * kPatchStride) + row * kPatchW + 4 * jg;
       uint8_t* sa = s_a + stage * kABytes;
+      float carry[4][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(sa + staged_off(r, j, 32)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+      for (int ky = 0; ky < 3; ++ky) {
+        float f[3][12];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float4* q = reinterpret_cast<const float4*>(pp + ci * (kPatchH * kPatchW) + ky * kPatchW);
+          const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+          f[ci][0] = q0.x; f[ci][1] = q0.y; f[ci][2] = q0.z; f[ci][3] = q0.w;
+          f[ci][4] = q1.x; f[ci][5] = q1.y; f[ci][6] = q1.z; f[ci][7] = q1.w;
+          f[ci][8] = q2.x; f[ci][9] = q2.y; f[ci][10] = q2.z; f[ci][11] = q2.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float w9[9];  // this vertical tap's nine k-values of pixel i: index kx*3 + ci
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) w9[kx * 3 + ci] = f[ci][i + (kPatchX0 - 1) + kx];
+          const int r = r0 + i;
+          if (ky == 0) {         // k 0..7
+            *reinterpret_cast<uint4*>(sa + staged_off(r, 0, 32)) =
+                make_uint4(pack_bf16x2(w9[0], w9[1]), pack_bf16x2(w9[2], w9[3]), pack_bf16x2(w9[4], w9[5]),
+                           pack_bf16x2(w9[6], w9[7]));
+            carry[i][0] = w9[8];
+          } else if (ky == 1) {  // k 8..15 = carry, w9[0..6]
+            *reinterpret_cast<uint4*>(sa + staged_off(r, 1, 32)) =
+                make_uint4(pack_bf16x2(carry[i][0], w9[0]), pack_bf16x2(w9[1], w9[2]), pack_bf16x2(w9[3], w9[4]),
+                           pack_bf16x2(w9[5], w9[6]));
+            carry[i][0] = w9[7];
+            carry[i][1] = w9[8];
+          } else {               // k 16..23 = carry[0..1], w9[0..5]; k 24..26 = w9[6..8], then zeros
+            *reinterpret_cast<uint4*>(sa + staged_off(r, 2, 32)) =
+                make_uint4(pack_bf16x2(carry[i][0], carry[i][1]), pack_bf16x2(w9[0], w9[1]), pack_bf16x2(w9[2], w9[3]),
+                           pack_bf16x2(w9[4], w9[5]));
+            *reinterpret_cast<uint4*>(sa + staged_off(r, 3, 32)) =
+                make_uint4(pack_bf16x2(w9[6], w9[7]), pack_bf16x2(w9[8], 0.f), 0u, 0u);
+          }
+        }
+      }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
-      if (tl) tl_stamp(a, 0, it, 4);
+      if (lane == 0) {
+        mbar_arrive_a(pempty0 + stage * 8);  // patch slot may be refilled
+        mbar_arrive_a(full0 + stage * 8);    // A tile ready for the MMA
+      }
+      if (lane == 0) tl_stamp(a, 0, it, 4);
     }
   } else if (warp >= kEpiWarp0) {
     epilogue_loop<BN, EPI, kFirstGroups>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
@@ -1217,7 +1264,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
 
 template <int EPI>
 static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
-  constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI, 2);
+  constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI, kFirstGroupsC);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_first_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
