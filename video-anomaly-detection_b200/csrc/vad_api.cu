@@ -503,6 +503,9 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
     const int patch = 8 * 18 * CK * 2;
     int stages = 8;
     while (stages >= 2 && kx_fixed_smem_bytes(CK, BN, epi) + stages * patch > 227 * 1024 - 4096) --stages;
+    // (An odd ring depth is fine although the two MMA issuers then alternate on a slot: the turn token orders their
+    // issues, so an issuer reaches the wait for use k+1 of a slot only after use k has been issued — it can never be
+    // two barrier phases ahead.  The first conv's free-running converter warps have no such ordering; see there.)
     if (stages < 2) {
       use_kx = false;
       g = pick_tile_geometry(d->B, d->H, d->W, is_score);
@@ -733,6 +736,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   std::memset(&a, 0, sizeof(a));
   a.lgTW = 4; a.lgTH = 3; a.lgTN = 0;  // 8 x 16 pixel tiles inside one frame
   a.w_step = 16; a.tw_valid = 16;
+  a.row_perm = 1;
   a.tiles_w = (W + 15) / 16;
   a.tiles_h = (H + 7) / 8;
   a.tiles_b = B;

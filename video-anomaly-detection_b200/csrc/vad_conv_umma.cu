@@ -173,6 +173,38 @@ __device__ __forceinline__ uint32_t staged_off(int row, int c16, int out_chunk) 
 
 // ---------------------------------------------------------------------------------------------------- epilogue
 // Runs on the four epilogue warps for one finished accumulator tile.  `stg_i` counts staged chunks (ring index).
+// Tile-invariant facts about one epilogue lane (= one accumulator row), computed once before the tile loop so that
+// the per-tile code does not redo the index arithmetic.
+struct EpiLane {
+  int ww, hh, bb;  // pixel of this accumulator row inside the tile (column, row, frame)
+  int srow;        // row of this pixel in a staged [frame][h][w] output tile
+  int mx, my;      // lane xor masks that reach the horizontal / vertical neighbour pixel (2x2 pooling)
+  bool row_ok;     // the row belongs to the tile at all
+};
+__device__ __forceinline__ EpiLane make_epi_lane(const ConvArgs& a, int q, int lane) {
+  const int r = q * 32 + lane;
+  const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
+  EpiLane L;
+  if (a.row_perm) {
+    // first conv (8 x 16 tiles): A row = (hh >> 1)*32 + (ww & 3)*8 + (hh & 1)*4 + (ww >> 2) — the order in which the
+    // im2col converter can write its rows without shared-memory bank conflicts
+    L.hh = ((r >> 5) << 1) | ((r >> 2) & 1);
+    L.ww = ((r & 3) << 2) | ((r >> 3) & 3);
+    L.bb = 0;
+    L.mx = 8;
+    L.my = 4;
+  } else {
+    L.ww = r & (TW - 1);
+    L.hh = (r >> a.lgTW) & (TH - 1);
+    L.bb = r >> (a.lgTW + a.lgTH);
+    L.mx = 1;
+    L.my = TW;
+  }
+  L.srow = ((L.bb << a.lgTH) + L.hh) * TW + L.ww;
+  L.row_ok = (r < (1 << (a.lgTW + a.lgTH + a.lgTN))) && (L.ww < a.tw_valid);
+  return L;
+}
+
 // 32 accumulator columns [lc, lc+32) of this thread's row.  KX == 3: the three kx column groups (BN columns apart) are
 // combined across neighbouring rows: out[ww] = D[ww][kx=0] + D[ww+1][kx=1] + D[ww+2][kx=2] (rows = lanes).
 template <int BN, int KX>
@@ -199,8 +231,9 @@ __device__ __forceinline__ void load_acc32(uint32_t tacc, int lc, uint32_t (&v)[
 }
 
 template <int BN, int EPI, int KX = 1>
-__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& t, uint32_t tacc, int q, int lane,
-                                              uint8_t* stg, const float* s_bias, float (*red_smem)[3], int& stg_i,
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord& t, const EpiLane& L, uint32_t tacc,
+                                              int q, int lane, uint8_t* stg, const float* s_bias,
+                                              float (*red_smem)[3], int& stg_i,
                                               uint32_t bar_id, const float* xpre, uint32_t acc_empty, int tl_role = -1,
                                               int tl_n = 0) {
   auto stamp = [&](int ev) {
@@ -215,14 +248,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
     __syncwarp();
     if (lane == 0) mbar_arrive_a(acc_empty);
   };
-  const int r = q * 32 + lane;  // accumulator row = pixel slot in the tile
-  const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
-  const int ww = r & (TW - 1);
-  const int hh = (r >> a.lgTW) & (TH - 1);
-  const int bb = r >> (a.lgTW + a.lgTH);
-  const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);
+  const int TW = 1 << a.lgTW;
+  const int ww = L.ww, hh = L.hh, bb = L.bb;
   const int fb = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
-  const bool valid = (r < rows_valid) && (fb < a.B) && (h < a.H) && (w < a.W) && (ww < a.tw_valid);
+  const bool valid = L.row_ok && (fb < a.B) && (h < a.H) && (w < a.W);
   const bool leader = (q == 0 && lane == 0);
   constexpr int kBufs = staging_bufs(BN, EPI);
 
@@ -257,13 +286,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float lo = __uint_as_float(v[j]), hi = __uint_as_float(v[j + 16]);
-              const float recv = __shfl_xor_sync(0xffffffffu, up1 ? lo : hi, 1);
+              const float recv = __shfl_xor_sync(0xffffffffu, up1 ? lo : hi, L.mx);
               g[j] = fmaxf(up1 ? hi : lo, recv);
             }
             float m[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float recv = __shfl_xor_sync(0xffffffffu, up2 ? g[j] : g[j + 8], TW);
+              const float recv = __shfl_xor_sync(0xffffffffu, up2 ? g[j] : g[j + 8], L.my);
               m[j] = fmaxf(up2 ? g[j + 8] : g[j], recv);
             }
             const int part = (up1 ? 2 : 0) + (up2 ? 1 : 0);  // channels [8*part, 8*part+8) of this 32-column chunk
@@ -288,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
               p[2 * j + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * j + 2]) + bv.z, a.slope),
                                          act_fn(__uint_as_float(v[4 * j + 3]) + bv.w, a.slope));
             }
-            const int srow = (KX == 3) ? hh * kKxValid + ww : r;
+            const int srow = (KX == 3) ? hh * kKxValid + ww : L.srow;
             if (KX == 1 || ww < kKxValid) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -331,8 +360,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         if constexpr (EPI == VAD_EPI_POOL) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], TW));
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], L.mx));
+            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], L.my));
           }
         }
 #pragma unroll
@@ -424,7 +453,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         *reinterpret_cast<float4*>(cptr + s * 8 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
         if (!a.tma_store) *reinterpret_cast<uint4*>(hptr + s * 8) = hv;
       }
-      if (a.tma_store) *reinterpret_cast<uint4*>(buf + staged_off(r, s, 32)) = hv;
+      if (a.tma_store) *reinterpret_cast<uint4*>(buf + staged_off(L.srow, s, 32)) = hv;
     }
     if (a.tma_store) {
       fence_proxy_async_smem();
@@ -516,13 +545,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
 // Loads the model-input pixels a score epilogue will compare against (issued before the accumulator wait so the HBM
 // latency overlaps the MMAs of the tile).
 template <int EPI>
-__device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t, int q, int lane, float* xpre) {
+__device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t, const EpiLane& L, float* xpre) {
   if constexpr (EPI == VAD_EPI_TANH_SCORE || EPI == VAD_EPI_CONVT_TANH_SCORE) {
-    const int r = q * 32 + lane;
-    const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
-    const int fb = t.b0 + (r >> (a.lgTW + a.lgTH)), h = t.h0 + ((r >> a.lgTW) & (TH - 1)), w = t.w0 + (r & (TW - 1));
-    const bool valid = (r < (1 << (a.lgTW + a.lgTH + a.lgTN))) && (fb < a.B) && (h < a.H) && (w < a.W) &&
-                       ((r & (TW - 1)) < a.tw_valid);
+    const int fb = t.b0 + L.bb, h = t.h0 + L.hh, w = t.w0 + L.ww;
+    const bool valid = L.row_ok && (fb < a.B) && (h < a.H) && (w < a.W);
     if constexpr (EPI == VAD_EPI_TANH_SCORE) {
       const long long plane = static_cast<long long>(a.H) * a.W;
       const long long off = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(h) * a.W + w;
@@ -558,24 +584,25 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
   // group g walks tiles g, g+G, ... of this CTA; the x pixels a score epilogue needs are fetched one tile ahead
   TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x);
   const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+  const EpiLane L = make_epi_lane(a, q, lane);
   float xcur[12], xnext[12];
-  if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xcur);
+  if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), L, xcur);
   for (int n = 0; ti.tile < a.total_tiles; ++n) {
     const int as = (G >= 2) ? g : (n & 1);
     const uint32_t aphase = (G >= 2) ? (n & 1) : ((n >> 1) & 1);
     const TileCoord t = ti.coord(a, BN);
     ti.next(a);
-    if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), q, lane, xnext);
+    if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), L, xnext);
     // timeline rows 2/3: leaders of groups 0/1, or (VAD_DBG & 4) warps 0 and 3 of group 0
     const bool tl = lane == 0 && ((a.dbg & 4) ? (g == 0 && (q == 0 || q == 3)) : (g < 2 && q == 0));
     const int tl_row = (a.dbg & 4) ? (q == 0 ? 2 : 3) : 2 + g;
     if (tl) tl_stamp(a, tl_row, n, 0);
-    mbar_wait_a(accf0 + as * 8, aphase, 4);
+    mbar_wait_a(accf0 + as * 8, aphase, 4u | (static_cast<uint32_t>(n) << 8) | (static_cast<uint32_t>(g) << 28));
     if (tl) tl_stamp(a, tl_row, n, 1);
     tc_fence_after();
     if (tl) tl_stamp(a, tl_row, n, 8);
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * STRIDE);
-    epilogue_tile<BN, EPI, KX>(a, t, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xcur, acce0 + as * 8,
+    epilogue_tile<BN, EPI, KX>(a, t, L, tacc, q, lane, my_stg, s_bias, red_smem[g], stg_i, 1u + g, xcur, acce0 + as * 8,
                                tl ? tl_row : -1, n);
     if (tl) tl_stamp(a, tl_row, n, 2);
 #pragma unroll
@@ -1050,11 +1077,14 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
 // immediate offsets per pixel); the MMA (two K=16 steps against the resident 32x32 weight tile) and the epilogue are
 // the same as everywhere else.  Replaces models/autoencoder.py:39-41 and models/video_autoencoder.py:193-196 (with
 // the 2x2 max-pool fused for the video encoder).
-constexpr int kFirstStages = 6;
+constexpr int kFirstStages = 8;
 constexpr int kFirstGroupsC = 4;                // epilogue groups
 constexpr int kConvWarps = 4;                   // converter warps; each converts whole tiles (every 4th)
 constexpr int kFirstConvWarp0 = 4 + 4 * kFirstGroupsC;
 constexpr int kFirstThreads = 32 * (kFirstConvWarp0 + kConvWarps);  // roles | epilogue groups | converters
+// Every use of a ring slot must be waited for by the SAME warp (a warp that is two phases ahead of a barrier passes
+// its parity wait spuriously): slot = tile % kFirstStages, converter = tile % kConvWarps, MMA issuer = tile % 2.
+static_assert(kFirstStages % kConvWarps == 0 && kFirstStages % 2 == 0, "ring slots must map to fixed warps");
 // fp32 patch: 24 columns x 10 rows x 3 channels starting at column w0-4: TMA needs the box's first byte 16-byte
 // aligned in the innermost dimension, so the 1-pixel left halo is fetched as part of an aligned group of four
 constexpr int kPatchW = 24, kPatchH = 10, kPatchX0 = 4;
@@ -1086,7 +1116,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   uint8_t* s_w = smem;                                   // [32 n][32 k] bf16, 64B-swizzled (2 KB slot)
   uint8_t* s_a = smem + 2048;                            // ring of A tiles
   uint8_t* s_p = s_a + kFirstStages * kABytes;           // ring of fp32 input patches
-  uint8_t* stg = s_p + kFirstStages * kPatchStride;      // epilogue staging (1024-aligned: 6*3072 = 18 KB)
+  uint8_t* stg = s_p + kFirstStages * kPatchStride;      // epilogue staging (1024-aligned: 8*3072 = 24 KB)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.mapA0);
@@ -1187,7 +1217,9 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     // vertical tap that completes them has been loaded, which keeps the live register set small.
     const int cw = warp - kFirstConvWarp0;
     const int row = lane >> 2, jg = lane & 3;  // tile = 8 rows x 16 columns; this lane: row, columns 4*jg .. 4*jg+3
-    const int r0 = row * 16 + 4 * jg;          // A row of the lane's first pixel
+    // A row of the lane's pixel i (see make_epi_lane): (row >> 1)*32 + i*8 + (row & 1)*4 + jg — the eight lanes that
+    // store together (a quarter warp: two rows x four column groups) then hit eight different 16-byte bank groups
+    const int r0 = (row >> 1) * 32 + (row & 1) * 4 + jg;
     const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
     const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
     int it = 0;
@@ -1205,6 +1237,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       float carry[4][2];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
+        if (a.dbg & 256) break;  // ablation: no conversion work
         float f[3][12];
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci) {
@@ -1221,7 +1254,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
           for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) w9[kx * 3 + ci] = f[ci][i + (kPatchX0 - 1) + kx];
-          const int r = r0 + i;
+          const int r = r0 + i * 8;
           if (ky == 0) {         // k 0..7
             *reinterpret_cast<uint4*>(sa + staged_off(r, 0, 32)) =
                 make_uint4(pack_bf16x2(w9[0], w9[1]), pack_bf16x2(w9[2], w9[3]), pack_bf16x2(w9[4], w9[5]),

@@ -24,6 +24,7 @@ struct alignas(64) ConvArgs {
   int tiles_w, tiles_h, tiles_b;
   int w_step;    // columns between consecutive tiles (1 << lgTW, or 6 for the kx-merged kernel)
   int tw_valid;  // valid output columns per tile row (1 << lgTW, or 6)
+  int row_perm;  // 1: accumulator rows are in the first conv's permuted pixel order (make_epi_lane)
   int n_tiles;
   int total_tiles;
   const float* bias;
