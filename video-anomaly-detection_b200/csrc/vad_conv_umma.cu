@@ -42,7 +42,8 @@ __host__ __device__ constexpr int acc_stages_for(int groups) { return groups < 2
 __host__ __device__ constexpr int block_threads(int bn) { return 128 + 128 * epi_groups(bn); }
 // staged-output buffers per epilogue group
 __host__ __device__ constexpr int staging_bufs(int bn, int epi) {
-  return !epi_uses_staging(epi) ? 0 : ((bn >= 256 || bn == 64) ? 1 : 2);  // N=64 runs 4 groups: one 16 KB buffer each
+  // the narrow N=32 tiles and the ConvLSTM epilogue (8 KB chunks) double-buffer, everything else has one 16 KB buffer
+  return !epi_uses_staging(epi) ? 0 : (epi == VAD_EPI_LSTM ? 2 : ((bn >= 128 || bn == 64) ? 1 : 2));
 }
 // one staged chunk: 128 rows x (64 ch = 128 B | 32 ch = 64 B)
 __host__ __device__ constexpr int staging_buf_bytes(int bn, int epi) {
@@ -1386,9 +1387,11 @@ static int launch_halo_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   X(32, 32, VAD_EPI_STORE)             \
   X(32, 64, VAD_EPI_STORE)             \
   X(64, 64, VAD_EPI_STORE)             \
+  X(64, 128, VAD_EPI_STORE)            \
   X(32, 32, VAD_EPI_POOL)              \
   X(32, 64, VAD_EPI_POOL)              \
   X(64, 64, VAD_EPI_POOL)              \
+  X(64, 128, VAD_EPI_POOL)             \
   X(32, 16, VAD_EPI_TANH_SCORE)
 
 int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages) {
