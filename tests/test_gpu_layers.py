@@ -64,6 +64,9 @@ CONV_CASES = [
     (128, 128, 1, 6, 10),     # H, W not powers of two, smaller than a tile
     (32, 32, 2, 48, 80),      # kx-merged tiles: 80 = 13 x 6 + 2 (partial last tile), three tile rows
     (32, 32, 1, 16, 256),     # full-width rows: 43 tiles of 6 columns, the last one clipped to 4
+    (128, 128, 3, 40, 32),    # patch + streamed-weights kernel: tile pairs, partial tile row (40 = 2*16 + 8), odd frames
+    (128, 256, 2, 32, 64),    # same kernel, two N tiles of 128
+    (256, 128, 1, 16, 48),    # four channel chunks
 ]
 
 

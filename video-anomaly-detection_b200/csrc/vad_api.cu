@@ -150,6 +150,12 @@ static int kx_setting() {
   static int v = env_int("VAD_KX", 1);
   return g_kx_override >= 0 ? g_kx_override : v;
 }
+// VAD_HS: 0 = off | 1 (default) = wide 3x3 layers (Cin >= 128, N multiple of 128) use the patch + streamed-weights kernel
+// | 2 = also Cin = 64
+static int hs_setting() {
+  static int v = env_int("VAD_HS", 1);
+  return v;
+}
 static int tma_store_setting() {
   static int v = env_int("VAD_TMA_STORE", 1);
   return v;
@@ -434,9 +440,11 @@ struct ConvLaunch {
   int CK, BN, epi, grid;
   bool use_halo;
   bool use_kx;
+  bool use_hs;
 };
 
 int launch_built(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.use_hs) return launch_conv_hs(L.epi, L.a, L.grid, stream);
   if (L.use_kx) return launch_conv_kx(L.CK, L.BN, L.epi, L.a, L.grid, stream);
   if (L.use_halo) return launch_conv_halo(L.CK, L.BN, L.epi, L.a, L.grid, stream);
   return launch_conv_umma(L.CK, L.BN, L.epi, L.a, L.grid, stream);
@@ -514,9 +522,22 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
     }
   }
 
+  // ---- patch + streamed-weights kernel for wide 3x3 layers: pairs of 8x16 tiles, N tiles of 128
+  bool use_hs = hs_setting() != 0 && d->ntaps == 9 && d->c1 == 0 && d->c0 % 64 == 0 &&
+                d->c0 >= (hs_setting() >= 2 ? 64 : 128) && d->n_total % 128 == 0 && (d->T0 <= 1) && d->H >= 8 &&
+                d->W % 16 == 0 && (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL) && hs_patch_stages(epi) >= 2;
+  if (use_hs) {
+    BN = 128;
+    g.lgTW = 3; g.lgTH = 4; g.lgTN = 0;
+    g.tiles_w = d->W >> 3;
+    g.tiles_h = (d->H + 15) >> 4;
+    g.tiles_b = d->B;
+    a.halo_stages = hs_patch_stages(epi);
+  }
+
   // ---- halo kernel: 3x3 conv, one source of 32/64 channels, all of N in one tile, frames of at least one tile
   const int halo_mode = halo_mode_setting();
-  bool use_halo = !use_kx && halo_mode != 0 && d->ntaps == 9 && d->c1 == 0 && (d->c0 == 32 || d->c0 == 64) &&
+  bool use_halo = !use_kx && !use_hs && halo_mode != 0 && d->ntaps == 9 && d->c1 == 0 && (d->c0 == 32 || d->c0 == 64) &&
                   d->n_total == BN && (d->T0 <= 1) && d->H >= 16 && d->W >= 16 &&
                   (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_TANH_SCORE);
   int halo_box_w = 0, halo_box_h = 0;
@@ -552,7 +573,9 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   }
 
   int rc;
-  if (use_kx) {
+  if (use_hs) {
+    rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, 64, 18, 18, 1);
+  } else if (use_kx) {
     rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, CK, 8, 18, 1);
   } else if (use_halo) {
     TileGeom box = g;  // box {CK, PW, PH, 1, 1}: PW/PH need not be powers of two
@@ -580,6 +603,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   a.chunks1 = d->c1 / CK;
   a.ntaps = d->ntaps;
   a.w_ctap = use_kx ? d->c0 : w_ctap;
+  a.pair = use_hs ? 2 : 1;
   a.w_step = use_kx ? 6 : (1 << g.lgTW);
   a.tw_valid = use_kx ? 6 : (1 << g.lgTW);
   a.tA0 = d->t0;
@@ -646,11 +670,13 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   a.dbg = env_int("VAD_DBG", 0);
   a.dual_mma = (dual_mma_setting() & ((use_halo || use_kx) ? 1 : 4)) != 0;
   L.use_kx = use_kx;
+  L.use_hs = use_hs;
   L.CK = CK;
   L.BN = BN;
   L.epi = epi;
   L.use_halo = use_halo;
   L.grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  if (use_hs) L.grid = (a.total_tiles >> 1) < sm_count() ? (a.total_tiles >> 1) : sm_count();
   return VAD_OK;
 }
 }  // namespace
@@ -737,6 +763,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   a.lgTW = 4; a.lgTH = 3; a.lgTN = 0;  // 8 x 16 pixel tiles inside one frame
   a.w_step = 16; a.tw_valid = 16;
   a.row_perm = 1;
+  a.pair = 1;
   a.tiles_w = (W + 15) / 16;
   a.tiles_h = (H + 7) / 8;
   a.tiles_b = B;

@@ -124,26 +124,33 @@ __device__ __forceinline__ void tl_stamp(const ConvArgs& a, int role, int n, int
 // per-tile cost is a handful of adds instead of three division sequences per role.
 struct TileIter {
   int tile, step;
-  int n_t, tw, th, tb;
-  int dn, dw, dh, db;
+  int m, n_t, tw, th, tb;  // tw counts tile PAIRS when a.pair == 2
+  int dm, dn, dw, dh, db;
   __device__ __forceinline__ TileIter(const ConvArgs& a, int first, int step_) : tile(first), step(step_) {
+    const int tiles_wp = a.tiles_w / a.pair;
     int v = first;
+    m = v % a.pair; v /= a.pair;
     n_t = v % a.n_tiles; v /= a.n_tiles;
-    tw = v % a.tiles_w; v /= a.tiles_w;
+    tw = v % tiles_wp; v /= tiles_wp;
     th = v % a.tiles_h; tb = v / a.tiles_h;
     v = step_;
+    dm = v % a.pair; v /= a.pair;
     dn = v % a.n_tiles; v /= a.n_tiles;
-    dw = v % a.tiles_w; v /= a.tiles_w;
+    dw = v % tiles_wp; v /= tiles_wp;
     dh = v % a.tiles_h; db = v / a.tiles_h;
   }
   __device__ __forceinline__ void next(const ConvArgs& a) {
     tile += step;
-    n_t += dn;
-    int c = n_t >= a.n_tiles;
+    m += dm;
+    int c = m >= a.pair;
+    m -= c ? a.pair : 0;
+    n_t += dn + c;
+    c = n_t >= a.n_tiles;
     n_t -= c ? a.n_tiles : 0;
     tw += dw + c;
-    c = tw >= a.tiles_w;
-    tw -= c ? a.tiles_w : 0;
+    const int tiles_wp = a.pair == 2 ? a.tiles_w >> 1 : a.tiles_w;
+    c = tw >= tiles_wp;
+    tw -= c ? tiles_wp : 0;
     th += dh + c;
     c = th >= a.tiles_h;
     th -= c ? a.tiles_h : 0;
@@ -151,11 +158,12 @@ struct TileIter {
   }
   __device__ __forceinline__ TileCoord coord(const ConvArgs& a, int bn) const {
     TileCoord t;
+    const int twi = tw * a.pair + m;
     t.n0 = n_t * bn;
-    t.w0 = tw * a.w_step;
+    t.w0 = twi * a.w_step;
     t.h0 = th << a.lgTH;
     t.b0 = tb << a.lgTN;
-    t.m_tile = (tb * a.tiles_h + th) * a.tiles_w + tw;
+    t.m_tile = (tb * a.tiles_h + th) * a.tiles_w + twi;
     return t;
   }
 };
@@ -574,7 +582,9 @@ __device__ __forceinline__ void prefetch_x(const ConvArgs& a, const TileCoord& t
 
 // Shared body of the epilogue warps.  Group g (warps 4+4g .. 7+4g) handles this CTA's tiles g, g+G, g+2G, ...;
 // with G = 2 each group owns one TMEM accumulator stage.
-template <int BN, int EPI, int G = epi_groups(BN), int KX = 1, int STRIDE = BN>
+// PAIR: the CTA works on pairs of horizontally adjacent tiles (tile indices 2u, 2u+1); group g takes half g of every
+// pair and alternates between the accumulator stages g and g+2.
+template <int BN, int EPI, int G = epi_groups(BN), int KX = 1, int STRIDE = BN, bool PAIR = false>
 __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_base, int warp, int lane, uint8_t* stg,
                                               const float* s_bias, float (*red_smem)[4][3], uint64_t* acc_full_bar,
                                               uint64_t* acc_empty_bar) {
@@ -583,14 +593,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
   uint8_t* my_stg = stg + g * staging_group_bytes(BN, EPI);
   int stg_i = 0;
   // group g walks tiles g, g+G, ... of this CTA; the x pixels a score epilogue needs are fetched one tile ahead
-  TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x);
+  TileIter ti(a, PAIR ? 2 * blockIdx.x + g : blockIdx.x + g * gridDim.x, PAIR ? 2 * gridDim.x : G * gridDim.x);
   const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
   const EpiLane L = make_epi_lane(a, q, lane);
   float xcur[12], xnext[12];
   if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), L, xcur);
   for (int n = 0; ti.tile < a.total_tiles; ++n) {
-    const int as = (G >= 2) ? g : (n & 1);
-    const uint32_t aphase = (G >= 2) ? (n & 1) : ((n >> 1) & 1);
+    const int as = PAIR ? g + 2 * (n & 1) : ((G >= 2) ? g : (n & 1));
+    const uint32_t aphase = (PAIR || G < 2) ? ((n >> 1) & 1) : (n & 1);
     const TileCoord t = ti.coord(a, BN);
     ti.next(a);
     if (ti.tile < a.total_tiles) prefetch_x<EPI>(a, ti.coord(a, BN), L, xnext);
@@ -1071,6 +1081,174 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- halo + streamed B
+// Wide 3x3 layers (Cin >= 128, N tile 128): the nine weight slabs of all channel chunks no longer fit in shared memory,
+// and the tap-per-stage streaming kernel re-reads every input pixel nine times from L2 (it runs at the L2 bandwidth
+// limit, not at the tensor pipe's).  Here a CTA works on PAIRS of 8x16 tiles (a 16x16 pixel block, M = 256): per
+// 64-channel chunk ONE TMA patch of 18x18 pixels serves all nine taps of both tiles through shifted descriptors, and
+// every streamed [128 x 64] weight tile is used by both tiles before its ring slot is released — per 128 output
+// pixels 185 KB of operand traffic instead of 576 KB.
+constexpr int kHsBRing = 4;                       // weight tiles in flight (16 KB each); 6 + two patch slots is slower
+constexpr int kHsPatchBytes = 18 * 18 * 128;      // 41472: one chunk's patch, rows = pixels (y*18 + x), 128 B each
+constexpr int kHsPatchPitch = 41984;              // 1024-aligned ring pitch
+constexpr int kHsBBytes = 128 * 128;              // [128 n][64 k] bf16
+
+template <int EPI>
+__global__ void __launch_bounds__(128 + 256, 1) conv_hs_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int BN = 128;
+  constexpr int kRowBytes = 128;
+  constexpr uint32_t kLayout = 2u;  // SWIZZLE_128B
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t p_full[4], p_empty[4];
+  __shared__ uint64_t b_full[kHsBRing], b_empty[kHsBRing];
+  __shared__ uint64_t acc_full_bar[kMaxAccStages];
+  __shared__ uint64_t acc_empty_bar[kMaxAccStages];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float red_smem[kMaxAccStages][4][3];
+  __shared__ __align__(16) float s_bias[kMaxBias];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_b = smem;                                 // weight ring
+  uint8_t* s_p = smem + kHsBRing * kHsBBytes;          // patch ring (a.halo_stages slots)
+  uint8_t* stg = s_p + a.halo_stages * kHsPatchPitch;  // epilogue staging
+  const int chunks = a.chunks0;
+  const int units = a.total_tiles >> 1;                // (tile pair, n tile) work items
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapB);
+    if (a.tma_store) tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < kHsBRing; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxAccStages; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < a.n_tiles * BN && i < kMaxBias; i += 384) s_bias[i] = a.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    // two streams over the same (unit, chunk) sequence: patches run one step ahead of the weight tiles so that a
+    // chunk's patch is already in flight while the previous chunk's nine weight tiles are being issued
+    const uint32_t pf0 = smem_addr_once(&p_full[0]), pe0 = smem_addr_once(&p_empty[0]);
+    const uint32_t bf0 = smem_addr_once(&b_full[0]), be0 = smem_addr_once(&b_empty[0]);
+    const uint32_t sp0 = smem_addr_once(s_p), sb0 = smem_addr_once(s_b);
+    TileIter tp(a, 2 * blockIdx.x, 2 * gridDim.x);  // patch stream position (unit) ...
+    int cp = 0;                                     // ... and chunk
+    int ps = 0;
+    uint32_t pphase = 0;
+    int bs = 0;
+    uint32_t bphase = 0;
+    auto issue_patch = [&]() {
+      const TileCoord t = tp.coord(a, BN);
+      mbar_wait_a(pe0 + ps * 8, pphase ^ 1u, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(pf0 + ps * 8, kHsPatchBytes);
+        tma_load_5d_a(sp0 + ps * kHsPatchPitch, &a.mapA0, pf0 + ps * 8, cp * 64, t.w0 - 1, t.h0 - 1, a.tA0, t.b0);
+      }
+      __syncwarp();
+      if (++ps == a.halo_stages) { ps = 0; pphase ^= 1u; }
+      if (++cp == chunks) { cp = 0; tp.next(a); }
+    };
+    if (tp.tile < a.total_tiles) issue_patch();
+    for (TileIter tb_(a, 2 * blockIdx.x, 2 * gridDim.x); tb_.tile < a.total_tiles; tb_.next(a)) {
+      const int n0 = tb_.n_t * BN;
+      for (int c = 0; c < chunks; ++c) {
+        if (tp.tile < a.total_tiles) issue_patch();
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait_a(be0 + bs * 8, bphase ^ 1u, 9);
+          if (elect_one()) {
+            mbar_arrive_expect_tx_a(bf0 + bs * 8, kHsBBytes);
+            tma_load_2d_a(sb0 + bs * kHsBBytes, &a.mapB, bf0 + bs * 8, tap * a.w_ctap + c * 64, n0);
+          }
+          __syncwarp();
+          if (++bs == kHsBRing) { bs = 0; bphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint32_t pf0 = smem_addr_once(&p_full[0]), pe0 = smem_addr_once(&p_empty[0]);
+    const uint32_t bf0 = smem_addr_once(&b_full[0]), be0 = smem_addr_once(&b_empty[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_p), 18 * kRowBytes, kLayout);  // 8-row groups one patch row apart
+    const uint64_t db_base = umma_smem_desc(smem_u32(s_b), 8 * kRowBytes, kLayout);
+    int ps = 0;
+    uint32_t pphase = 0;
+    int bs = 0;
+    uint32_t bphase = 0;
+    int j = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++j) {
+      const int as0 = 2 * (j & 1);
+      const uint32_t aph = static_cast<uint32_t>(((j >> 1) & 1) ^ 1);
+      mbar_wait_a(acce0 + as0 * 8, aph, 3);
+      mbar_wait_a(acce0 + (as0 + 1) * 8, aph, 3);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + static_cast<uint32_t>(as0 * BN);
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait_a(pf0 + ps * 8, pphase, 2);
+        const uint64_t da_c = da_base + static_cast<uint64_t>(ps * (kHsPatchPitch >> 4));
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait_a(bf0 + bs * 8, bphase, 10);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t db = db_base + static_cast<uint64_t>(bs * (kHsBBytes >> 4));
+            const uint64_t da_t = da_c + static_cast<uint64_t>(((ky * 18 + kx) * kRowBytes) >> 4);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(d0 + static_cast<uint32_t>(m * BN), da_t + static_cast<uint64_t>(m * ((8 * kRowBytes) >> 4) + kk * 2),
+                          db + static_cast<uint64_t>(kk * 2), idesc, (c > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit_a(be0 + bs * 8);
+            if (tap == 8) umma_commit_a(pe0 + ps * 8);
+            if (tap == 8 && c == chunks - 1) {
+              umma_commit_a(accf0 + as0 * 8);
+              umma_commit_a(accf0 + (as0 + 1) * 8);
+            }
+          }
+          __syncwarp();
+          if (++bs == kHsBRing) { bs = 0; bphase ^= 1u; }
+          if (++kx == 3) { kx = 0; ++ky; }
+        }
+        if (++ps == a.halo_stages) { ps = 0; pphase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    epilogue_loop<BN, EPI, 2, 1, BN, true>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- first conv
 // 3 -> 32 channel 3x3 conv straight from the fp32 NCHW model input.  K = 27 (padded to 32).  TMA brings the fp32
 // input patch of a tile (3 channels x 10 rows x 24 columns, zero-filled outside the frame = conv padding) into smem;
@@ -1453,6 +1631,33 @@ int launch_conv_kx(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStr
   if (CK == ck && BN == bn && EPI == epi) return launch_kx_one<ck, bn, epi>(a, grid, stream);
   VAD_KX_CASES(X)
 #undef X
+  return VAD_ERR_UNSUPPORTED;
+}
+
+template <int EPI>
+static int launch_hs_one(const ConvArgs& a, int grid, cudaStream_t stream) {
+  const int smem = 1024 + kHsBRing * kHsBBytes + a.halo_stages * kHsPatchPitch + 2 * staging_group_bytes(128, EPI);
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_hs_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = smem;
+  }
+  conv_hs_kernel<EPI><<<grid, 384, smem, stream>>>(a);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// patch ring slots that fit next to the weight ring and the staging buffers
+int hs_patch_stages(int EPI) {
+  const int fixed = 1024 + kHsBRing * kHsBBytes + 2 * staging_group_bytes(128, EPI);
+  int n = (kSmemBudget - fixed) / kHsPatchPitch;
+  return n > 4 ? 4 : n;
+}
+
+int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
+  if (EPI == VAD_EPI_STORE) return launch_hs_one<VAD_EPI_STORE>(a, grid, stream);
+  if (EPI == VAD_EPI_POOL) return launch_hs_one<VAD_EPI_POOL>(a, grid, stream);
   return VAD_ERR_UNSUPPORTED;
 }
 

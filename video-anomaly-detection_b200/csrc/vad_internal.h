@@ -24,6 +24,7 @@ struct alignas(64) ConvArgs {
   int tiles_w, tiles_h, tiles_b;
   int w_step;    // columns between consecutive tiles (1 << lgTW, or 6 for the kx-merged kernel)
   int tw_valid;  // valid output columns per tile row (1 << lgTW, or 6)
+  int pair;      // 1, or 2: tiles are enumerated (and processed) as horizontally adjacent pairs
   int row_perm;  // 1: accumulator rows are in the first conv's permuted pixel order (make_epi_lane)
   int n_tiles;
   int total_tiles;
@@ -70,6 +71,8 @@ int launch_conv_halo(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaS
 int launch_conv_kx(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int kx_fixed_smem_bytes(int CK, int BN, int EPI);
 int kx_mma_columns(int BN, int EPI);
+int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
+int hs_patch_stages(int EPI);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 // dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)
 int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);
