@@ -37,9 +37,12 @@ __host__ __device__ constexpr bool epi_uses_staging(int epi) {
 // and owns TMEM accumulator stage g.  The narrowest tiles (N <= 32: full-resolution layers, thousands of tiny tiles
 // per SM; N <= 64) are bound by epilogue latency and get four groups, 128-wide tiles two, and 256-wide tiles (MMA-bound) one
 // group plus the smem for a deeper operand ring.
-__host__ __device__ constexpr int epi_groups(int bn) { return bn >= 256 ? 1 : (bn <= 64 ? 4 : 2); }
+// (transposed convolutions have K <= 256: a couple of MMAs per tile against a 128-column epilogue -> four groups too)
+__host__ __device__ constexpr int epi_groups(int bn, int epi = -1) {
+  return bn >= 256 ? 1 : ((bn <= 64 || epi == VAD_EPI_CONVT) ? 4 : 2);
+}
 __host__ __device__ constexpr int acc_stages_for(int groups) { return groups < 2 ? 2 : groups; }
-__host__ __device__ constexpr int block_threads(int bn) { return 128 + 128 * epi_groups(bn); }
+__host__ __device__ constexpr int block_threads(int bn, int epi = -1) { return 128 + 128 * epi_groups(bn, epi); }
 // staged-output buffers per epilogue group
 __host__ __device__ constexpr int staging_bufs(int bn, int epi) {
   // the narrow N=32 tiles and the ConvLSTM epilogue (8 KB chunks) double-buffer, everything else has one 16 KB buffer
@@ -53,10 +56,10 @@ __host__ __device__ constexpr int staging_group_bytes(int bn, int epi) {
   return staging_bufs(bn, epi) * staging_buf_bytes(bn, epi);
 }
 __host__ __device__ constexpr int staging_bytes(int bn, int epi, int groups = 0) {
-  return (groups ? groups : epi_groups(bn)) * staging_group_bytes(bn, epi);
+  return (groups ? groups : epi_groups(bn, epi)) * staging_group_bytes(bn, epi);
 }
-__host__ __device__ constexpr uint32_t tmem_cols_for(int bn, int groups = 0) {
-  const int c = acc_stages_for(groups ? groups : epi_groups(bn)) * bn;
+__host__ __device__ constexpr uint32_t tmem_cols_for(int bn, int groups = 0, int epi = -1) {
+  const int c = acc_stages_for(groups ? groups : epi_groups(bn, epi)) * bn;
   return (c <= 32) ? 32u : (c <= 64) ? 64u : (c <= 128) ? 128u : (c <= 256) ? 256u : 512u;
 }
 
@@ -96,7 +99,7 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024;  // +1024 alignment slack
   static constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;                        // SWIZZLE_128B : SWIZZLE_64B
   static constexpr uint32_t kSBO = 8 * kRowBytes;                                  // bytes between 8-row groups
-  static constexpr uint32_t kTmemCols = tmem_cols_for(BN);
+  static constexpr uint32_t kTmemCols = tmem_cols_for(BN, 0, EPI);
   static_assert(CK == 64 || CK == 32, "K chunk must be one 128B or 64B swizzle span");
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
   static_assert(kStages >= 2, "pipeline too shallow");
@@ -624,14 +627,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
 
 template <int BN>
 __device__ __forceinline__ void load_bias_smem(const ConvArgs& a, float* s_bias, int n_total) {
-  for (int i = threadIdx.x; i < n_total && i < kMaxBias; i += block_threads(BN)) s_bias[i] = a.bias[i];
+  for (int i = threadIdx.x; i < n_total && i < kMaxBias; i += blockDim.x) s_bias[i] = a.bias[i];
 }
 
 // ---------------------------------------------------------------------------------------------------- streaming
 template <int CK, int BN, int EPI>
-__global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   using C = Cfg<CK, BN, EPI>;
-  constexpr int kAS = acc_stages_for(epi_groups(BN));
+  constexpr int kAS = acc_stages_for(epi_groups(BN, EPI));
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[C::kStages];
   __shared__ uint64_t empty_bar[C::kStages];
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_umma_kernel(const _
       }
     }
   } else if (warp >= kEpiWarp0) {
-    epilogue_loop<BN, EPI>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
+    epilogue_loop<BN, EPI, epi_groups(BN, EPI)>(a, tmem_base, warp, lane, stg, s_bias, red_smem, acc_full_bar, acc_empty_bar);
   }
 
   tc_fence_before();
@@ -1509,7 +1512,7 @@ static int launch_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_umma_kernel<CK, BN, EPI><<<grid, block_threads(BN), C::kSmemBytes, stream>>>(a);
+  conv_umma_kernel<CK, BN, EPI><<<grid, block_threads(BN, EPI), C::kSmemBytes, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
