@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the anomaly-scoring hot path (recon + heat map + score) — prints ONE JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1..cfg5] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json configs[1]
 (cfg2): image ConvAutoencoder, 256 x 3x256x256, random-init weights (torch.manual_seed(0)), fp32 input in [-1,1].
@@ -33,6 +33,11 @@ WORKLOADS = {
     "cfg1": ("image", 32, 1, 256, 256, 8.1118, "image AE, synthetic 256x256 RGB, batch 32"),
     "cfg2": ("image", 256, 1, 256, 256, 8.1118, "image AE, MVTec-bottle-shaped synthetic 256x256, batch 256"),
     "cfg3": ("video", 64, 16, 128, 128, 0.75288, "ConvLSTM video AE, 16-frame 128x128 clips, batch 64"),
+    # 720p: one 64-frame window of one stream per step and GPU (708 MB of fp32 input); under torchrun this is cfg5's
+    # shape — windows sharded over the GPUs, per-frame scores gathered to rank 0 inside the step
+    "cfg4": ("video", 1, 64, 720, 1280, 42.349, "ConvLSTM video AE, synthetic 720p stream, one 64-frame window"),
+    "cfg5": ("video", 1, 64, 720, 1280, 42.349, "720p clips sharded over the GPUs (one 64-frame clip per GPU and step), "
+                                                  "per-frame score gather"),
 }
 
 
@@ -164,6 +169,8 @@ def cpu_baseline(kind, T, H, W, budget_s=12.0):
     m = build_model(kind, "cpu")
     sd = vad_oracle.cpu_sd(m.state_dict())
     nb = 8 if kind == "image" else 2
+    if H * W > 256 * 256:  # 720p: one window of 8 frames (the per-frame cost does not depend on T)
+        nb, T = 1, min(T, 8)
     x = synth_input(kind, nb, T, H, W, "cpu")
     fn = (lambda: vad_oracle.image_reconstruction_error(sd, x)) if kind == "image" else \
          (lambda: vad_oracle.video_reconstruction_error(sd, x, per_frame=True))
@@ -297,7 +304,7 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": round(byts / (avg_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s"}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01b_dram_traffic.json")
     if os.path.exists(tpath):  # measured once with ncu --set full at this exact shape (see profiles/)
         traffic = json.load(open(tpath)).get(args.workload, {}).get(top["rep"])
     roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": traffic, "kernel": top_name,
