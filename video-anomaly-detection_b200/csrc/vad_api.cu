@@ -719,7 +719,9 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   }
   const int chunks1 = a.chunks1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  static const int pdl = env_int("VAD_PDL", 1);  // 0: plain stream order between the steps
   for (int t = 0; t < T; ++t) {
+    a.pdl = pdl ? (t == 0 ? 1 : 2) : 0;
     a.tA0 = t;
     a.tA1 = t > 0 ? t - 1 : 0;
     a.chunks1 = t > 0 ? chunks1 : 0;  // step 0: h_{-1} = 0, skip the h half of K

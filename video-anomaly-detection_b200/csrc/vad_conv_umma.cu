@@ -417,6 +417,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
   } else if constexpr (EPI == VAD_EPI_LSTM) {
     // columns of this tile: [gate g in i,f,g,o][32 hidden channels j0..j0+31]; weights/bias pre-permuted on host
     static_assert(EPI != VAD_EPI_LSTM || BN == 128, "LSTM tile is 4 gates x 32 channels");
+    if (a.pdl == 2) pdl_wait();  // the cell state below was written by the previous step's launch (cheap once satisfied)
     const int hid = a.cout;
     const int j0 = (t.n0 >> 7) * 32;
     const long long pix = (static_cast<long long>(fb) * a.H + h) * a.W + w;
@@ -679,6 +680,13 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
     tmem_relinquish();
   }
   load_bias_smem<BN>(a, s_bias, a.n_tiles * BN);
+  // Programmatic dependent launch (a.pdl != 0: launched with the stream-serialisation attribute).  Everything above
+  // touches only constants (weights' tensor maps, bias); from here on the previous kernel's output is read.
+  //   pdl == 1: wait here.   pdl == 2 (ConvLSTM step t >= 1): only the h_{t-1} loads and the cell state depend on the
+  //   previous launch — the producer waits before its first h tile, the epilogue before it reads c; the x half of the
+  //   K loop (loaded and multiplied first) overlaps the previous step's tail.
+  if (a.pdl) pdl_launch_dependents();
+  if (a.pdl == 1) pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -691,28 +699,37 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
     const uint32_t smem0 = smem_addr_once(smem);
     int stage = 0;
     uint32_t phase = 0;
+    // K order: source-major (all taps of source 0, then all taps of source 1) — the weight tile of (tap, chunk) is
+    // addressed explicitly, so any order is valid, and this one puts everything that does not depend on the previous
+    // ConvLSTM step first
+    bool waited = a.pdl != 2;
     for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
       const TileCoord t = ti.coord(a, BN);
-      int dy = (a.ntaps == 9) ? -1 : 0, dx = dy;
-      for (int tap = 0; tap < a.ntaps; ++tap) {
-        int kcol = tap * a.w_ctap;
-        for (int c = 0; c < chunks; ++c) {
-          mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
-          if (elect_one()) {
-            const uint32_t sa = smem0 + stage * C::kStageBytes;
-            const uint32_t fb = full0 + stage * 8;
-            mbar_arrive_expect_tx_a(fb, tx_bytes);
-            if (c < a.chunks0)
-              tma_load_5d_a(sa, &a.mapA0, fb, c * CK, t.w0 + dx, t.h0 + dy, a.tA0, t.b0);
-            else
-              tma_load_5d_a(sa, &a.mapA1, fb, (c - a.chunks0) * CK, t.w0 + dx, t.h0 + dy, a.tA1, t.b0);
-            tma_load_2d_a(sa + C::kABytes, &a.mapB, fb, kcol, t.n0);
+      for (int src = 0; src < 2; ++src) {
+        const int c_lo = src == 0 ? 0 : a.chunks0, c_hi = src == 0 ? a.chunks0 : chunks;
+        if (c_lo == c_hi) continue;
+        if (src == 1 && !waited) { pdl_wait(); waited = true; }
+        int dy = (a.ntaps == 9) ? -1 : 0, dx = dy;
+        for (int tap = 0; tap < a.ntaps; ++tap) {
+          int kcol = tap * a.w_ctap + c_lo * CK;
+          for (int c = c_lo; c < c_hi; ++c) {
+            mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
+            if (elect_one()) {
+              const uint32_t sa = smem0 + stage * C::kStageBytes;
+              const uint32_t fb = full0 + stage * 8;
+              mbar_arrive_expect_tx_a(fb, tx_bytes);
+              if (src == 0)
+                tma_load_5d_a(sa, &a.mapA0, fb, c * CK, t.w0 + dx, t.h0 + dy, a.tA0, t.b0);
+              else
+                tma_load_5d_a(sa, &a.mapA1, fb, (c - a.chunks0) * CK, t.w0 + dx, t.h0 + dy, a.tA1, t.b0);
+              tma_load_2d_a(sa + C::kABytes, &a.mapB, fb, kcol, t.n0);
+            }
+            __syncwarp();
+            kcol += CK;
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          kcol += CK;
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (++dx == 2) { dx = -1; ++dy; }  // next tap (3x3: row-major over (dy, dx) in -1..1)
         }
-        if (++dx == 2) { dx = -1; ++dy; }  // next tap (3x3: row-major over (dy, dx) in -1..1)
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -1511,6 +1528,20 @@ static int launch_one(const ConvArgs& a, int grid, cudaStream_t stream) {
                                          C::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
+  }
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block_threads(BN, EPI));
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_umma_kernel<CK, BN, EPI>, a));
   }
   conv_umma_kernel<CK, BN, EPI><<<grid, block_threads(BN, EPI), C::kSmemBytes, stream>>>(a);
   count_launch();

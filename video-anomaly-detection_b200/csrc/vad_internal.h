@@ -24,6 +24,7 @@ struct alignas(64) ConvArgs {
   int tiles_w, tiles_h, tiles_b;
   int w_step;    // columns between consecutive tiles (1 << lgTW, or 6 for the kx-merged kernel)
   int tw_valid;  // valid output columns per tile row (1 << lgTW, or 6)
+  int pdl;       // programmatic dependent launch: 0 off, 1 wait before the first global read, 2 ConvLSTM step t >= 1
   int pair;      // 1, or 2: tiles are enumerated (and processed) as horizontally adjacent pairs
   int row_perm;  // 1: accumulator rows are in the first conv's permuted pixel order (make_epi_lane)
   int n_tiles;
