@@ -53,6 +53,9 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.vad_error_string(0) == b"ok"
     assert b"unsupported" in lib.vad_error_string(-2).lower() or b"shape" in lib.vad_error_string(-2).lower()
     assert lib.vad_conv_layer(None, None) == -1
+    assert lib.vad_conv_layer_tiles(None) == -1
+    prev = lib.vad_debug_set_kx(0)
+    assert lib.vad_debug_set_kx(-1) == 0 and lib.vad_debug_set_kx(-1) == prev
     assert lib.vad_conv_m_tiles(0, 16, 16, 0) == -1
     assert lib.vad_conv_m_tiles(2, 256, 256, 1) == 2 * 512
     assert lib.vad_score_scratch_bytes(0, 16, 16) == 0

@@ -151,3 +151,43 @@ def test_lstm_row_permutation_is_a_permutation():
         assert perm[:32].tolist() == list(range(0, 32)) and perm[32:64].tolist() == list(range(hid, hid + 32))
     with pytest.raises(ValueError):
         prep.lstm_row_permutation(48)
+
+
+def test_kx_merged_weight_layout():
+    """`w_kx` (the layout of the kernel that folds the horizontal taps into N, include/vad_b200.h `weight_kx`) holds the
+    same weights as `w`: row kx*Cout + co, column ky*Cin + ci; zero rows up to a multiple of 16; only narrow layers."""
+    g = torch.Generator().manual_seed(3)
+    for cout, cin, pad in ((32, 32, 0), (3, 32, 16), (64, 64, 0)):
+        w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64)
+        pk = prep.pack_conv3x3(w, torch.zeros(cout, dtype=torch.float64), pad_n_to=pad)
+        assert pk.w_kx is not None
+        rows = (3 * cout + 15) // 16 * 16
+        assert tuple(pk.w_kx.shape) == (rows, 3 * cin)
+        wk = pk.w_kx.float().view(rows, 3, cin)
+        for kx in range(3):
+            for ky in range(3):
+                assert torch.equal(wk[kx * cout:(kx + 1) * cout, ky], w[:, :, ky, kx].to(torch.bfloat16).float())
+                # ... and it is the same number the tap-major layout holds at K = (ky*3+kx)*Cin + ci
+                k0 = (ky * 3 + kx) * cin
+                assert torch.equal(pk.w.float()[:cout, k0:k0 + cin], wk[kx * cout:(kx + 1) * cout, ky])
+        assert float(wk[3 * cout:].abs().max() if rows > 3 * cout else 0.0) == 0.0
+    wide = prep.pack_conv3x3(torch.randn(128, 128, 3, 3, generator=g, dtype=torch.float64),
+                             torch.zeros(128, dtype=torch.float64))
+    assert wide.w_kx is None
+
+
+def test_kx_merged_gemm_reproduces_conv():
+    """Emulates the kx kernel's arithmetic on the packed operand: D[q][kx][co] = sum_{ky,ci} in[q + ky rows][ci] *
+    w_kx[kx*Cout+co][ky*Cin+ci], out[x] = D[x-1][0] + D[x][1] + D[x+1][2] — equals conv3x3 with zero padding."""
+    g = torch.Generator().manual_seed(5)
+    cout, cin, H, W = 3, 32, 6, 9
+    w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(1, H, W, cin, generator=g, dtype=torch.float64)
+    pk = prep.pack_conv3x3(w, torch.zeros(cout, dtype=torch.float64), pad_n_to=16)
+    wq = pk.w_kx.double()[:9]                                   # [kx*3+co][ky*cin+ci]
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))                           # halo columns and rows
+    rows3 = torch.cat([xp[:, ky:ky + H, :, :] for ky in range(3)], dim=-1)   # [1,H,W+2,3*cin] (q = padded column)
+    D = rows3 @ wq.t()                                          # [1,H,W+2,9]
+    out = D[:, :, 0:W, 0:3] + D[:, :, 1:W + 1, 3:6] + D[:, :, 2:W + 2, 6:9]
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, rtol=1e-9, atol=1e-9)
