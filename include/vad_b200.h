@@ -89,7 +89,7 @@ typedef struct vad_conv_desc {
   const float* x;             /* *_SCORE: fp32 [B,3,Ho,Wo] model input */
   float* recon;               /* *_SCORE: optional fp32 [B,3,Ho,Wo] */
   float* heat;                /* *_SCORE: optional fp32 [B,Ho,Wo] per-pixel channel-mean squared error */
-  float* partials;            /* *_SCORE: fp32 [m_tiles][4] per-tile (sum of squares, min, max, -) */
+  float* partials;            /* *_SCORE: fp32 [m_tiles][4 warps][4]: per tile and 32-row quarter (sum of squares, min, max, -) */
   /* optional second layout of the same 3x3 weights for narrow layers (Cout <= 64, one source of 32/64 channels):
    * bf16 [3*Cout rows, zero-padded to a multiple of 16][3*Cin], row = kx*Cout + co, column = ky*Cin + ci
    * (*_SCORE: Cout = 3 -> 9 rows padded to 16).  When present the library may fold the horizontal taps into the
@@ -122,7 +122,8 @@ int vad_first_conv_tc(const float* x, const void* weight_bf16, const float* bias
 
 /* ---- scoring reduction ----------------------------------------------------------------------------------------
  * reference models/autoencoder.py:214-221, models/video_autoencoder.py:371-384, evaluate_video.py:56 (min/max) */
-/* finalize per-tile partials of a fused *_SCORE layer: score[f] = sum/(3*H*W), minmax[f] = {min,max} of the map */
+/* finalize the partials of a fused *_SCORE layer (tiles_per_frame = 4 x the frame's tiles: one entry per tile quarter)
+ * or of vad_score: score[f] = sum/(3*H*W), minmax[f] = {min,max} of the map */
 int vad_score_finalize(const float* partials, int frames, int tiles_per_frame, int H, int W, float* score,
                        float* minmax /* nullable [frames][2] */, vad_stream_t stream);
 /* standalone (unfused) scoring pass: x, recon fp32 [N,3,H,W]; scratch >= vad_score_scratch_bytes(N,H,W) */

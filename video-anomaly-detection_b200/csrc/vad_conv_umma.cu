@@ -535,23 +535,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         }
       }
     }
-    // tile reduction in a fixed order (deterministic): lanes -> warps -> one writer
+    // reduction in a fixed order (deterministic): lanes of a warp here, the four warp partials of a tile and the tiles
+    // of a frame in score_finalize_kernel — no cross-warp traffic or barrier in the tile loop
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
       smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
       smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
     }
-    if (lane == 0) { red_smem[q][0] = ssum; red_smem[q][1] = smin; red_smem[q][2] = smax; }
-    named_bar_sync(bar_id, 128);
-    if (leader) {
-      const float s = (red_smem[0][0] + red_smem[1][0]) + (red_smem[2][0] + red_smem[3][0]);
-      const float mn = fminf(fminf(red_smem[0][1], red_smem[1][1]), fminf(red_smem[2][1], red_smem[3][1]));
-      const float mx = fmaxf(fmaxf(red_smem[0][2], red_smem[1][2]), fmaxf(red_smem[2][2], red_smem[3][2]));
-      *reinterpret_cast<float4*>(a.partials + static_cast<long long>(t.m_tile) * 4) =
-          make_float4(s, mn * (1.f / 3.f), mx * (1.f / 3.f), 0.f);
-    }
-    named_bar_sync(bar_id, 128);  // red_smem is reused by the next tile
+    if (lane == 0)
+      *reinterpret_cast<float4*>(a.partials + (static_cast<long long>(t.m_tile) * 4 + q) * 4) =
+          make_float4(ssum, smin * (1.f / 3.f), smax * (1.f / 3.f), 0.f);
   }
 }
 

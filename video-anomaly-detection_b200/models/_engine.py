@@ -113,10 +113,10 @@ def _score_layer(w: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int,
     heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
     d = _gemm_desc(w, src, frames, H, W, epi, IDENT, None, x=x, recon=recon, heat=heat, partials=x)
     tiles = nat.layer_tiles(d)  # the tiling (and so the number of per-tile partials) is the library's choice
-    partials = bufs.get("partials", (tiles, 4), torch.float32, dev)
+    partials = bufs.get("partials", (tiles, 4, 4), torch.float32, dev)  # one (sum, min, max, -) per tile and warp quarter
     d.partials = partials.data_ptr()
     _timed(what, lambda: nat.conv_layer(d, what))
-    score, minmax = _finalize(partials, frames, tiles // frames, Ho, Wo, bufs, dev)
+    score, minmax = _finalize(partials, frames, 4 * (tiles // frames), Ho, Wo, bufs, dev)
     return ScoreOutputs(score, minmax, heat, recon)
 
 
