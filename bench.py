@@ -184,6 +184,32 @@ def cpu_baseline(kind, T, H, W, budget_s=12.0):
                       f"oracle/vad_oracle.py (torch {torch.__version__} CPU ops)"}
 
 
+def gpu_library_baseline(kind, B, T, H, W, dev, x):
+    """The reference's own GPU path — the same torch ops in eager mode on cuDNN (fp32, TF32 allowed as by default) —
+    timed with CUDA events on this GPU: the library bar the hand-written kernels are measured against.
+    Uses the oracle's restatement of the reference forward on CUDA tensors; scores only (one forward)."""
+    from oracle import vad_oracle
+    m = build_model(kind, "cpu")
+    sd = {k: v.to(dev) for k, v in vad_oracle.cpu_sd(m.state_dict()).items()}
+    nb = min(B, 64 if kind == "image" else 8)  # eager fp32 activations of the full batch would not all fit comfortably
+    xs = x[:nb]
+    fn = (lambda: vad_oracle.image_reconstruction_error(sd, xs)) if kind == "image" else \
+         (lambda: vad_oracle.video_reconstruction_error(sd, xs, per_frame=True))
+    with torch.no_grad():
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 10
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": round(nb * T / (ms * 1e-3), 1), "unit": "frames/s", "kind": "torch eager + cuDNN on the same GPU",
+            "sample": f"{nb} x {'%dx' % T if kind == 'video' else ''}3x{H}x{W} fp32, scores only, torch {torch.__version__}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +218,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-library-baseline", action="store_true",
+                    help="also time the reference's torch/cuDNN eager path on this GPU (extra key, rank 0, N=1)")
     args = ap.parse_args()
     kind, B, T, H, W, gflop_per_frame, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -361,6 +389,47 @@ def main():
             "e2e": {"value": round(frames / e2e_s, 1), "unit": "frames/s", "h2d_bytes_per_step": x.numel() * 4,
                     "d2h_bytes_per_step": B * T * 4, "note": "pinned host -> device copies double-buffered on a side stream"},
             "gpu_launches": int(launches)}
+    # extra: the same end-to-end loop fed with the decoder's uint8 HWC frames, normalised on the device
+    # (a quarter of the PCIe bytes of the fp32 tensors the reference callers upload)
+    if world == 1:
+        from runtime import frames as fr
+        u8h = ((xh.reshape(-1, 3, H, W).permute(0, 2, 3, 1) * 0.5 + 0.5).clamp_(0, 1) * 255).to(torch.uint8).contiguous().pin_memory()
+        ubufs = [torch.empty_like(u8h, device=dev) for _ in range(2)]
+
+        def e2e_u8(n):
+            main_stream = torch.cuda.current_stream()
+            for i in range(n):
+                b = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[b])
+                    ubufs[b].copy_(u8h, non_blocking=True)
+                    ready[b].record(copy_stream)
+                main_stream.wait_event(ready[b])
+                xin = fr.normalize_u8(ubufs[b]).view(x.shape)
+                s_ = model.get_reconstruction_error(xin, per_frame=True) if kind == "video" else \
+                    model.get_reconstruction_error(xin)
+                freed[b].record(main_stream)
+                sh.copy_(s_.reshape(-1), non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_u8(3)
+        t0 = time.perf_counter()
+        e2e_u8(args.steps)
+        line["e2e_u8_frames"] = {"value": round(B * T * args.steps / (time.perf_counter() - t0), 1), "unit": "frames/s",
+                                 "h2d_bytes_per_step": u8h.numel(),
+                                 "note": "uint8 HWC frames uploaded, ToTensor+Normalize on the device (runtime/frames.py)"}
+    # apples-to-apples extra: scores only (no heat map written), the one output the reference computes per forward
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run_model(model, kind, x, want_heat=False)
+    e0.record()
+    for _ in range(min(args.steps, 10)):
+        run_model(model, kind, x, want_heat=False)
+    e1.record()
+    torch.cuda.synchronize()
+    line["score_only"] = {"value": round(B * T * min(args.steps, 10) / (e0.elapsed_time(e1) * 1e-3), 1),
+                          "unit": "frames/s", "note": "rank 0, per GPU; heat map not materialised"}
+    if args.gpu_library_baseline and world == 1:
+        line["gpu_library_baseline"] = gpu_library_baseline(kind, B, T, H, W, dev, x)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(kind, T, H, W)
     print(json.dumps(line))

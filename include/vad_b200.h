@@ -140,6 +140,16 @@ int vad_nchw_f32_to_nhwc_bf16(const float* src, int N, int C, int H, int W, void
 int vad_heatmap_u8(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
                    vad_stream_t stream);
 
+/* ---- frame I/O either side of the path --------------------------------------------------- */
+/* uint8 HWC RGB [N,H,W,3] -> fp32 NCHW [N,3,H,W] in [-1,1]: ToTensor + Normalize(.5,.5) — utils/dataset.py:65-70,
+ * utils/video_dataset.py:62-66,356-360 (the resize stays with the decoder); H*W multiple of 4 */
+int vad_u8_hwc_to_f32_nchw(const uint8_t* src, int frames, int H, int W, float* dst, vad_stream_t stream);
+/* fp32 NCHW [-1,1] -> uint8 HWC: `denormalize` — evaluate_video.py:40-49 */
+int vad_f32_nchw_to_u8_hwc(const float* src, int frames, int H, int W, uint8_t* dst, vad_stream_t stream);
+/* per-frame normalised error map -> JET-coloured RGB uint8 [N,H,W,3]: `create_heatmap` — evaluate_video.py:52-66 */
+int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
+                        vad_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

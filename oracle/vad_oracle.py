@@ -160,7 +160,7 @@ def convlstm(sd: Mapping[str, Tensor], x: Tensor, prefix: str = "convlstm.") -> 
     for layer in range(n_layers):
         key = f"{prefix}cells.{layer}"
         hid = sd[key + ".conv.weight"].shape[0] // 4
-        h = torch.zeros(b, hid, *x.shape[3:], dtype=x.dtype)
+        h = torch.zeros(b, hid, *x.shape[3:], dtype=x.dtype, device=x.device)  # `_init_hidden(..., device)` :174-179
         c = torch.zeros_like(h)
         outs = []
         for ti in range(t):

@@ -72,3 +72,19 @@ def test_no_cpu_fallback():
         m.get_reconstruction_error(torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError, match="CUDA-only"):
         m(torch.zeros(1, 3, 32, 32))
+
+
+def test_jet_table_in_library_matches_golden_and_cv2():
+    """The colour table compiled into vad_api.cu == tests/golden/jet_lut_rgb.npy (== cv2.COLORMAP_JET when cv2 is here)."""
+    import numpy as np
+    src = open(os.path.join(ROOT, "video-anomaly-detection_b200", "csrc", "vad_api.cu")).read()
+    body = src[src.index("c_jet_rgb[256] = {"):]
+    body = body[:body.index("};")]
+    vals = [int(v, 16) for v in re.findall(r"0x([0-9a-f]{6})u", body)]
+    assert len(vals) == 256
+    table = np.array([[v & 255, (v >> 8) & 255, (v >> 16) & 255] for v in vals], dtype=np.uint8)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "jet_lut_rgb.npy"))
+    assert np.array_equal(table, golden)
+    cv2 = pytest.importorskip("cv2")
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_JET)
+    assert np.array_equal(cv2.cvtColor(lut, cv2.COLOR_BGR2RGB).reshape(256, 3), golden)

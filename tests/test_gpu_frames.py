@@ -1,0 +1,67 @@
+"""GPU: frame I/O kernels either side of the path against the reference's host formulas."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_normalize_u8_matches_totensor_normalize(cuda_device):
+    from runtime import frames
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (2, 3, 48, 64, 3), generator=g, dtype=torch.uint8)  # [B, T, H, W, 3]
+    got = frames.normalize_u8(u8.to(cuda_device))
+    torch.cuda.synchronize()
+    # torchvision ToTensor (HWC uint8 -> CHW float / 255) + Normalize(mean .5, std .5): utils/dataset.py:65-70
+    ref = (u8.permute(0, 1, 4, 2, 3).float().div(255) - 0.5) / 0.5
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert torch.equal(got.cpu(), ref)  # bit-exact: same fp32 operations in the same order
+
+
+def test_denormalize_u8_matches_reference(cuda_device):
+    from runtime import frames
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(5, 3, 32, 40, generator=g) * 2.4 - 1.2  # outside [-1,1] too: the clamp matters
+    got = frames.denormalize_u8(x.to(cuda_device))
+    torch.cuda.synchronize()
+    t = torch.clamp(x * 0.5 + 0.5, 0, 1)                    # evaluate_video.py:40-49
+    ref = (t.permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_render_heatmap_matches_create_heatmap(cuda_device):
+    from runtime import frames
+    g = torch.Generator().manual_seed(2)
+    heat = torch.rand(4, 64, 48, generator=g) ** 3
+    heat[3] = 0.25                                          # constant frame: (e-min)/(0+1e-8) = 0 everywhere
+    hd = heat.to(cuda_device)
+    minmax = torch.stack([hd.amin((1, 2)), hd.amax((1, 2))], 1)
+    got = frames.render_heatmap(hd, minmax).cpu().numpy()
+    lut = np.load(os.path.join(GOLDEN, "jet_lut_rgb.npy"))  # cv2.COLORMAP_JET as RGB (tests/golden/make_jet_lut.py)
+    for f in range(4):
+        e = heat[f].numpy()
+        norm = (e - e.min()) / (e.max() - e.min() + 1e-8)   # evaluate_video.py:56-57
+        idx = (norm * 255).astype(np.uint8)
+        ref = lut[idx]
+        diff = got[f].astype(np.int32) - ref.astype(np.int32)
+        # fp32 rounding of the normalisation may move a pixel across one LUT bin
+        assert (np.abs(diff).max(axis=-1) > 0).mean() < 2e-3
+        idx_got_ok = np.abs(diff).max() <= 8                 # neighbouring JET entries differ by at most 4 per channel
+        assert idx_got_ok
+
+
+def test_scoring_from_u8_frames_end_to_end(cuda_device):
+    """uint8 frames -> device normalisation -> scoring == scoring of the host-normalised fp32 tensor."""
+    from models import ConvAutoencoder
+    from runtime import frames
+    torch.manual_seed(0)
+    m = ConvAutoencoder().eval().to(cuda_device)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 64, 64, 3), generator=g, dtype=torch.uint8)
+    x_host = (u8.permute(0, 3, 1, 2).float().div(255) - 0.5) / 0.5
+    a = m.get_reconstruction_error(frames.normalize_u8(u8.to(cuda_device)))
+    b = m.get_reconstruction_error(x_host.to(cuda_device))
+    assert torch.equal(a, b)

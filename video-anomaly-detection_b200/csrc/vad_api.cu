@@ -386,6 +386,99 @@ __global__ void heatmap_u8_kernel(const float* __restrict__ heat, const float* _
   out[i] = static_cast<uint8_t>(norm * 255.f);
 }
 
+// ------------------------------------------------------------------------------------------------ frame I/O helpers
+// the host-side numpy / torchvision / cv2 steps either side of the scoring path.
+
+// uint8 HWC RGB frames -> fp32 NCHW in [-1,1]: torchvision ToTensor (x/255) + Normalize(mean .5, std .5)
+// (reference utils/dataset.py:65-70, utils/video_dataset.py:62-66,356-360).  One thread = 4 consecutive pixels of a row:
+// 12 input bytes, three float4 stores.
+__global__ void __launch_bounds__(256) u8_hwc_to_f32_nchw_kernel(const uint8_t* __restrict__ src, long long plane,
+                                                                 long long quads, float* __restrict__ dst) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;  // quad index over N * plane / 4
+  if (i >= quads) return;
+  const long long per_frame = plane >> 2;
+  const long long n = i / per_frame;
+  const long long p = (i - n * per_frame) << 2;
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + (n * plane + p) * 3);  // 12 bytes, 4-byte aligned
+  const uint32_t a = __ldg(s32), b = __ldg(s32 + 1), c = __ldg(s32 + 2);
+  const uint8_t px[12] = {uint8_t(a), uint8_t(a >> 8), uint8_t(a >> 16), uint8_t(a >> 24), uint8_t(b), uint8_t(b >> 8),
+                          uint8_t(b >> 16), uint8_t(b >> 24), uint8_t(c), uint8_t(c >> 8), uint8_t(c >> 16),
+                          uint8_t(c >> 24)};
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float4 v;
+    v.x = (static_cast<float>(px[ch]) / 255.f - 0.5f) / 0.5f;
+    v.y = (static_cast<float>(px[3 + ch]) / 255.f - 0.5f) / 0.5f;
+    v.z = (static_cast<float>(px[6 + ch]) / 255.f - 0.5f) / 0.5f;
+    v.w = (static_cast<float>(px[9 + ch]) / 255.f - 0.5f) / 0.5f;
+    *reinterpret_cast<float4*>(dst + (n * 3 + ch) * plane + p) = v;
+  }
+}
+
+// fp32 NCHW in [-1,1] -> uint8 HWC: `denormalize` (reference evaluate_video.py:40-49): x*0.5+0.5, clamp, *255, truncate
+__global__ void __launch_bounds__(256) f32_nchw_to_u8_hwc_kernel(const float* __restrict__ src, long long plane,
+                                                                 long long total_px, uint8_t* __restrict__ dst) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;  // pixel index over N * plane
+  if (i >= total_px) return;
+  const long long n = i / plane, p = i - n * plane;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = __ldg(src + (n * 3 + ch) * plane + p) * 0.5f + 0.5f;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    dst[i * 3 + ch] = static_cast<uint8_t>(v * 255.f);
+  }
+}
+
+// cv2.COLORMAP_JET as RGB (r | g << 8 | b << 16), generated with cv2.applyColorMap(arange(256)) — reference
+// create_heatmap (evaluate_video.py:52-66): normalise per frame, uint8 (truncation), JET, BGR -> RGB
+__constant__ uint32_t c_jet_rgb[256] = {
+    0x800000u, 0x840000u, 0x880000u, 0x8c0000u, 0x900000u, 0x940000u, 0x980000u, 0x9c0000u,
+    0xa00000u, 0xa40000u, 0xa80000u, 0xac0000u, 0xb00000u, 0xb40000u, 0xb80000u, 0xbc0000u,
+    0xc00000u, 0xc40000u, 0xc80000u, 0xcc0000u, 0xd00000u, 0xd40000u, 0xd80000u, 0xdc0000u,
+    0xe00000u, 0xe40000u, 0xe80000u, 0xec0000u, 0xf00000u, 0xf40000u, 0xf80000u, 0xfc0000u,
+    0xff0000u, 0xff0400u, 0xff0800u, 0xff0c00u, 0xff1000u, 0xff1400u, 0xff1800u, 0xff1c00u,
+    0xff2000u, 0xff2400u, 0xff2800u, 0xff2c00u, 0xff3000u, 0xff3400u, 0xff3800u, 0xff3c00u,
+    0xff4000u, 0xff4400u, 0xff4800u, 0xff4c00u, 0xff5000u, 0xff5400u, 0xff5800u, 0xff5c00u,
+    0xff6000u, 0xff6400u, 0xff6800u, 0xff6c00u, 0xff7000u, 0xff7400u, 0xff7800u, 0xff7c00u,
+    0xff8000u, 0xff8400u, 0xff8800u, 0xff8c00u, 0xff9000u, 0xff9400u, 0xff9800u, 0xff9c00u,
+    0xffa000u, 0xffa400u, 0xffa800u, 0xffac00u, 0xffb000u, 0xffb400u, 0xffb800u, 0xffbc00u,
+    0xffc000u, 0xffc400u, 0xffc800u, 0xffcc00u, 0xffd000u, 0xffd400u, 0xffd800u, 0xffdc00u,
+    0xffe000u, 0xffe400u, 0xffe800u, 0xffec00u, 0xfff000u, 0xfff400u, 0xfff800u, 0xfffc00u,
+    0xfeff02u, 0xfaff06u, 0xf6ff0au, 0xf2ff0eu, 0xeeff12u, 0xeaff16u, 0xe6ff1au, 0xe2ff1eu,
+    0xdeff22u, 0xdaff26u, 0xd6ff2au, 0xd2ff2eu, 0xceff32u, 0xcaff36u, 0xc6ff3au, 0xc2ff3eu,
+    0xbeff42u, 0xbaff46u, 0xb6ff4au, 0xb2ff4eu, 0xaeff52u, 0xaaff56u, 0xa6ff5au, 0xa2ff5eu,
+    0x9eff62u, 0x9aff66u, 0x96ff6au, 0x92ff6eu, 0x8eff72u, 0x8aff76u, 0x86ff7au, 0x82ff7eu,
+    0x7eff82u, 0x7aff86u, 0x76ff8au, 0x72ff8eu, 0x6eff92u, 0x6aff96u, 0x66ff9au, 0x62ff9eu,
+    0x5effa2u, 0x5affa6u, 0x56ffaau, 0x52ffaeu, 0x4effb2u, 0x4affb6u, 0x46ffbau, 0x42ffbeu,
+    0x3effc2u, 0x3affc6u, 0x36ffcau, 0x32ffceu, 0x2effd2u, 0x2affd6u, 0x26ffdau, 0x22ffdeu,
+    0x1effe2u, 0x1affe6u, 0x16ffeau, 0x12ffeeu, 0x0efff2u, 0x0afff6u, 0x06fffau, 0x01fffeu,
+    0x00fcffu, 0x00f8ffu, 0x00f4ffu, 0x00f0ffu, 0x00ecffu, 0x00e8ffu, 0x00e4ffu, 0x00e0ffu,
+    0x00dcffu, 0x00d8ffu, 0x00d4ffu, 0x00d0ffu, 0x00ccffu, 0x00c8ffu, 0x00c4ffu, 0x00c0ffu,
+    0x00bcffu, 0x00b8ffu, 0x00b4ffu, 0x00b0ffu, 0x00acffu, 0x00a8ffu, 0x00a4ffu, 0x00a0ffu,
+    0x009cffu, 0x0098ffu, 0x0094ffu, 0x0090ffu, 0x008cffu, 0x0088ffu, 0x0084ffu, 0x0080ffu,
+    0x007cffu, 0x0078ffu, 0x0074ffu, 0x0070ffu, 0x006cffu, 0x0068ffu, 0x0064ffu, 0x0060ffu,
+    0x005cffu, 0x0058ffu, 0x0054ffu, 0x0050ffu, 0x004cffu, 0x0048ffu, 0x0044ffu, 0x0040ffu,
+    0x003cffu, 0x0038ffu, 0x0034ffu, 0x0030ffu, 0x002cffu, 0x0028ffu, 0x0024ffu, 0x0020ffu,
+    0x001cffu, 0x0018ffu, 0x0014ffu, 0x0010ffu, 0x000cffu, 0x0008ffu, 0x0004ffu, 0x0000ffu,
+    0x0000fcu, 0x0000f8u, 0x0000f4u, 0x0000f0u, 0x0000ecu, 0x0000e8u, 0x0000e4u, 0x0000e0u,
+    0x0000dcu, 0x0000d8u, 0x0000d4u, 0x0000d0u, 0x0000ccu, 0x0000c8u, 0x0000c4u, 0x0000c0u,
+    0x0000bcu, 0x0000b8u, 0x0000b4u, 0x0000b0u, 0x0000acu, 0x0000a8u, 0x0000a4u, 0x0000a0u,
+    0x00009cu, 0x000098u, 0x000094u, 0x000090u, 0x00008cu, 0x000088u, 0x000084u, 0x000080u,
+};
+
+__global__ void __launch_bounds__(256) heatmap_jet_kernel(const float* __restrict__ heat, const float* __restrict__ minmax,
+                                                          long long plane, long long total, uint8_t* __restrict__ out) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i >= total) return;
+  const long long f = i / plane;
+  const float mn = minmax[2 * f], mx = minmax[2 * f + 1];
+  const float norm = (heat[i] - mn) / (mx - mn + 1e-8f);
+  const uint32_t c = c_jet_rgb[static_cast<uint8_t>(norm * 255.f)];
+  out[i * 3 + 0] = static_cast<uint8_t>(c);
+  out[i * 3 + 1] = static_cast<uint8_t>(c >> 8);
+  out[i * 3 + 2] = static_cast<uint8_t>(c >> 16);
+}
+
 }  // namespace vad
 
 // ================================================================================================ C ABI
@@ -887,4 +980,38 @@ int vad_heatmap_u8(const float* heat, const float* minmax, int frames, int H, in
   return static_cast<int>(cudaGetLastError());
 }
 
+int vad_u8_hwc_to_f32_nchw(const uint8_t* src, int frames, int H, int W, float* dst, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const long long plane = static_cast<long long>(H) * W;
+  if (plane % 4 != 0 || reinterpret_cast<uintptr_t>(src) % 4 != 0 || reinterpret_cast<uintptr_t>(dst) % 16 != 0)
+    return VAD_ERR_SHAPE;
+  const long long quads = plane / 4 * frames;
+  u8_hwc_to_f32_nchw_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, stream>>>(src, plane, quads, dst);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vad_f32_nchw_to_u8_hwc(const float* src, int frames, int H, int W, uint8_t* dst, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = plane * frames;
+  f32_nchw_to_u8_hwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src, plane, total, dst);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
+                        vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!heat || !minmax || !out || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = plane * frames;
+  heatmap_jet_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(heat, minmax, plane, total, out);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // extern "C"
+
