@@ -812,6 +812,13 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   }
   const int chunks1 = a.chunks1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // One persistent launch for the whole sequence when every tile gets its own resident CTA (cell state in registers,
+  // grid-wide step counter); VAD_LSTM_SEQ=0 keeps one launch per step.
+  static const int seq = env_int("VAD_LSTM_SEQ", 1);
+  if (seq && a.tma_store && a.total_tiles <= sm_count() && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
+    a.out = d->out;
+    return launch_convlstm_seq(L.CK, a, T, a.total_tiles, stream);
+  }
   static const int pdl = env_int("VAD_PDL", 1);  // 0: plain stream order between the steps
   for (int t = 0; t < T; ++t) {
     a.pdl = pdl ? (t == 0 ? 1 : 2) : 0;

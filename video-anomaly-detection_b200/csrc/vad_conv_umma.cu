@@ -1263,6 +1263,226 @@ __global__ void __launch_bounds__(128 + 256, 1) conv_hs_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- ConvLSTM sequence
+// One launch for all T steps of a ConvLSTM layer (reference ConvLSTM.forward time loop, models/video_autoencoder.py:
+// 153-167) when every (pixel tile, 32-channel tile) fits one CTA per SM: the CTA keeps its tile for the whole sequence,
+// the CELL STATE LIVES IN REGISTERS (32 fp32 per epilogue thread) and only h_t goes to memory (it is the next step's
+// MMA operand for this CTA and its neighbours, and the layer's output).  Steps are separated by a grid-wide counter:
+// a CTA publishes h_t (TMA store complete -> release-add), the producer of every CTA acquires `t * gridDim.x` before
+// its first h_{t-1} load.  The x half of step t+1's K loop (input sequence, independent of the recurrence) is loaded
+// and multiplied while step t's epilogue and the exchange are still in flight.
+template <int CK>
+__global__ void __launch_bounds__(256, 1) convlstm_seq_kernel(const __grid_constant__ ConvArgs a, int T,
+                                                              unsigned int* __restrict__ step_counter) {
+  constexpr int BN = 128;
+  using C = Cfg<CK, BN, VAD_EPI_LSTM>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[C::kStages];
+  __shared__ uint64_t empty_bar[C::kStages];
+  __shared__ uint64_t acc_full_bar[2];
+  __shared__ uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[BN];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + C::kStages * C::kStageBytes;  // one 8 KB staged h tile
+
+  const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);
+  const uint32_t tx_bytes = static_cast<uint32_t>(rows_valid * C::kRowBytes + C::kBBytes);
+  const TileCoord tc = TileIter(a, blockIdx.x, gridDim.x).coord(a, BN);  // this CTA's tile, for every step
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapA1);
+    tma_prefetch_desc(&a.mapB);
+    tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<256>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += 256) s_bias[i] = a.bias[tc.n0 + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t smem0 = smem_addr_once(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int src = 0; src < 2; ++src) {
+        if (src == 1) {
+          if (t == 0) break;  // h_{-1} = 0: the h half of K is skipped
+          // every CTA has published h_{t-1} (the 3x3 halo reaches into the neighbours' tiles)
+          const unsigned int target = static_cast<unsigned int>(t) * gridDim.x;
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(step_counter) < target) {
+              if (clock64() - t0 > 2000000000LL) {
+                if (g_vad_trap_slot) {
+                  g_vad_trap_slot[0] = 11;
+                  g_vad_trap_slot[1] = blockIdx.x;
+                  g_vad_trap_slot[2] = static_cast<unsigned long long>(t);
+                  g_vad_trap_slot[3] = target;
+                  __threadfence_system();
+                }
+                __trap();
+              }
+            }
+          }
+          __syncwarp();
+          fence_proxy_async_all();  // the acquired data is read through the async proxy (TMA) below
+        }
+        const int n_chunks = src == 0 ? a.chunks0 : a.chunks1;
+        const int kbase = src == 0 ? 0 : a.chunks0 * CK;
+        int dy = -1, dx = -1;
+        for (int tap = 0; tap < 9; ++tap) {
+          int kcol = tap * a.w_ctap + kbase;
+          for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
+            if (elect_one()) {
+              const uint32_t sa = smem0 + stage * C::kStageBytes;
+              const uint32_t fb = full0 + stage * 8;
+              mbar_arrive_expect_tx_a(fb, tx_bytes);
+              if (src == 0)
+                tma_load_5d_a(sa, &a.mapA0, fb, c * CK, tc.w0 + dx, tc.h0 + dy, t, tc.b0);
+              else
+                tma_load_5d_a(sa, &a.mapA1, fb, c * CK, tc.w0 + dx, tc.h0 + dy, t - 1, tc.b0);
+              tma_load_2d_a(sa + C::kABytes, &a.mapB, fb, kcol, tc.n0);
+            }
+            __syncwarp();
+            kcol += CK;
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+          if (++dx == 2) { dx = -1; ++dy; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(smem), C::kSBO, C::kLayout);
+    const uint64_t db_base = umma_smem_desc(smem_u32(smem + C::kABytes), C::kSBO, C::kLayout);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < T; ++t) {
+      const int k_iters = 9 * (a.chunks0 + (t > 0 ? a.chunks1 : 0));
+      const int as = t & 1;
+      mbar_wait_a(acce0 + as * 8, static_cast<uint32_t>(((t >> 1) & 1) ^ 1), 3);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait_a(full0 + stage * 8, phase, 2);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t soff = static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+#pragma unroll
+          for (int kk = 0; kk < CK / 16; ++kk)
+            umma_bf16(d_tmem, da_base + soff + static_cast<uint64_t>(kk * 2), db_base + soff + static_cast<uint64_t>(kk * 2),
+                      idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_a(empty0 + stage * 8);
+          if (k == k_iters - 1) umma_commit_a(accf0 + as * 8);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue: gates, c (registers), h
+    const int q = warp & 3;
+    const EpiLane L = make_epi_lane(a, q, lane);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const bool leader = (q == 0 && lane == 0);
+    const int fb = tc.b0 + L.bb, h = tc.h0 + L.hh, w = tc.w0 + L.ww;
+    const bool valid = L.row_ok && (fb < a.B) && (h < a.H) && (w < a.W);
+    const int j0 = (tc.n0 >> 7) * 32;  // first hidden channel of this tile
+    float c[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) c[e] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int as = t & 1;
+      mbar_wait_a(accf0 + as * 8, static_cast<uint32_t>((t >> 1) & 1), 4u | (static_cast<uint32_t>(t) << 8));
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      // (the staging buffer is free: the leader waited for the previous store's completion before publishing h_{t-1},
+      //  and every warp passed the barrier below after that)
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t gi[8], gf[8], gg[8], go[8];
+        tmem_ld_x8(tacc + 0 + s * 8, gi);
+        tmem_ld_x8(tacc + 32 + s * 8, gf);
+        tmem_ld_x8(tacc + 64 + s * 8, gg);
+        tmem_ld_x8(tacc + 96 + s * 8, go);
+        tmem_ld_wait();
+        if (s == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce0 + as * 8);
+        }
+        float hn[8];
+        const float* bp = s_bias + s * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xi = __uint_as_float(gi[e]) + bp[e];
+          const float xf = __uint_as_float(gf[e]) + bp[32 + e];
+          const float xg = __uint_as_float(gg[e]) + bp[64 + e];
+          const float xo = __uint_as_float(go[e]) + bp[96 + e];
+          const float cn = sigmoid_fn(xf) * c[s * 8 + e] + sigmoid_fn(xi) * tanh_fn(xg);
+          c[s * 8 + e] = cn;
+          hn[e] = sigmoid_fn(xo) * tanh_fn(cn);
+        }
+        *reinterpret_cast<uint4*>(stg + staged_off(L.srow, s, 32)) =
+            make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
+                       pack_bf16x2(hn[6], hn[7]));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (leader) {
+        tma_store_5d(&a.mapOut, stg, j0, tc.w0, tc.h0, t, tc.b0);
+        bulk_commit_group();
+        bulk_wait_group_read<0>();
+      }
+      named_bar_sync(1, 128);  // nobody overwrites the staging buffer before the store has read it
+      if (leader) {
+        bulk_wait_group<0>();  // h_t of this tile is in global memory ...
+        __threadfence();
+        red_release_gpu_add(step_counter, 1u);  // ... and published
+      }
+    }
+    if (valid && a.c_state != nullptr) {  // final cell state (ConvLSTM.forward returns it; VideoAutoencoder drops it)
+      float* cptr = a.c_state + ((static_cast<long long>(fb) * a.H + h) * a.W + w) * a.cout + j0;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(cptr + e) = make_float4(c[e], c[e + 1], c[e + 2], c[e + 3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- first conv
 // 3 -> 32 channel 3x3 conv straight from the fp32 NCHW model input.  K = 27 (padded to 32).  TMA brings the fp32
 // input patch of a tile (3 channels x 10 rows x 24 columns, zero-filled outside the frame = conv padding) into smem;
@@ -1686,6 +1906,38 @@ int hs_patch_stages(int EPI) {
 int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
   if (EPI == VAD_EPI_STORE) return launch_hs_one<VAD_EPI_STORE>(a, grid, stream);
   if (EPI == VAD_EPI_POOL) return launch_hs_one<VAD_EPI_POOL>(a, grid, stream);
+  return VAD_ERR_UNSUPPORTED;
+}
+
+// per-call step counters of the persistent ConvLSTM kernel (a rotating pool so that calls on different streams do not
+// share one; each call zeroes its slot on its own stream first)
+__device__ unsigned int g_lstm_counters[64];
+
+template <int CK>
+static int launch_lstm_seq_one(const ConvArgs& a, int T, int grid, cudaStream_t stream) {
+  using C = Cfg<CK, 128, VAD_EPI_LSTM>;
+  constexpr int smem = C::kStages * C::kStageBytes + 8192 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  static unsigned int next_slot = 0;
+  unsigned int* base = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm_counters);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  unsigned int* counter = base + (next_slot++ & 63u);
+  e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  convlstm_seq_kernel<CK><<<grid, 256, smem, stream>>>(a, T, counter);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t stream) {
+  if (CK == 64) return launch_lstm_seq_one<64>(a, T, grid, stream);
+  if (CK == 32) return launch_lstm_seq_one<32>(a, T, grid, stream);
   return VAD_ERR_UNSUPPORTED;
 }
 
