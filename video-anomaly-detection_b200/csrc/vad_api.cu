@@ -864,7 +864,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   std::memset(&a, 0, sizeof(a));
   a.lgTW = 4; a.lgTH = 3; a.lgTN = 0;  // 8 x 16 pixel tiles inside one frame
   a.w_step = 16; a.tw_valid = 16;
-  a.row_perm = 1;
+  a.row_perm = 0;
   a.pair = 1;
   a.tiles_w = (W + 15) / 16;
   a.tiles_h = (H + 7) / 8;

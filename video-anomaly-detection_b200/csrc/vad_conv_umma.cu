@@ -1624,15 +1624,13 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     }
   } else if (warp >= kFirstConvWarp0) {
     // ===================================================================== converters: fp32 patch -> bf16 im2col rows
-    // One warp converts a whole tile; a lane owns four horizontally adjacent pixels of one row so that the patch is
-    // read with 27 LDS.128 per lane (instead of 108 scalar loads for the same four pixels).  K order
-    // k = (ky*3 + kx)*3 + ci; the 16-byte chunks of a pixel's A row (8 k-values each) are written as soon as the
-    // vertical tap that completes them has been loaded, which keeps the live register set small.
+    // One warp converts a whole tile (8 rows x 16 columns).  A lane owns one column and four rows, {0,1,4,5} + 2*rg:
+    // rows 2 apart are 48 floats apart in the patch (pitch 24), so the two half-warps read disjoint banks (scalar LDS,
+    // one wavefront each), and at every store the eight lanes of a quarter warp write eight consecutive A rows, which
+    // the 64-byte swizzle spreads over all bank groups: 72 + 64 shared-memory wavefronts per tile (the earlier
+    // 4-pixels-in-a-row layout needed ~450 because of 4-way store conflicts).  K order k = (ky*3 + kx)*3 + ci.
     const int cw = warp - kFirstConvWarp0;
-    const int row = lane >> 2, jg = lane & 3;  // tile = 8 rows x 16 columns; this lane: row, columns 4*jg .. 4*jg+3
-    // A row of the lane's pixel i (see make_epi_lane): (row >> 1)*32 + i*8 + (row & 1)*4 + jg — the eight lanes that
-    // store together (a quarter warp: two rows x four column groups) then hit eight different 16-byte bank groups
-    const int r0 = (row >> 1) * 32 + (row & 1) * 4 + jg;
+    const int col = lane & 15, rg = lane >> 4;
     const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
     const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
     int it = 0;
@@ -1644,48 +1642,39 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       mbar_wait_a(pfull0 + stage * 8, phase, 6);
       mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
       if (lane == 0) tl_stamp(a, 0, it, 1);
-      // patch column of pixel ww, tap kx: ww + (kPatchX0 - 1) + kx; the lane reads columns 4*jg .. 4*jg + 11
-      const float* pp = reinterpret_cast<const float*>(s_p + stage * kPatchStride) + row * kPatchW + 4 * jg;
       uint8_t* sa = s_a + stage * kABytes;
-      float carry[4][2];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
+      for (int hb = 0; hb < 2; ++hb) {
         if (a.dbg & 256) break;  // ablation: no conversion work
-        float f[3][12];
+        const int base_row = 4 * hb + 2 * rg;  // tile rows base_row, base_row + 1 <- patch rows base_row .. base_row + 3
+        // patch column of pixel `col`, tap kx: col + (kPatchX0 - 1) + kx
+        const float* pp = reinterpret_cast<const float*>(s_p + stage * kPatchStride) + base_row * kPatchW + col +
+                          (kPatchX0 - 1);
+        float f[3][4][3];  // [ci][patch row][kx]
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float4* q = reinterpret_cast<const float4*>(pp + ci * (kPatchH * kPatchW) + ky * kPatchW);
-          const float4 q0 = q[0], q1 = q[1], q2 = q[2];
-          f[ci][0] = q0.x; f[ci][1] = q0.y; f[ci][2] = q0.z; f[ci][3] = q0.w;
-          f[ci][4] = q1.x; f[ci][5] = q1.y; f[ci][6] = q1.z; f[ci][7] = q1.w;
-          f[ci][8] = q2.x; f[ci][9] = q2.y; f[ci][10] = q2.z; f[ci][11] = q2.w;
-        }
+        for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float w9[9];  // this vertical tap's nine k-values of pixel i: index kx*3 + ci
+          for (int pr = 0; pr < 4; ++pr)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
+            for (int kx = 0; kx < 3; ++kx) f[ci][pr][kx] = pp[ci * (kPatchH * kPatchW) + pr * kPatchW + kx];
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) w9[kx * 3 + ci] = f[ci][i + (kPatchX0 - 1) + kx];
-          const int r = r0 + i * 8;
-          if (ky == 0) {         // k 0..7
-            *reinterpret_cast<uint4*>(sa + staged_off(r, 0, 32)) =
-                make_uint4(pack_bf16x2(w9[0], w9[1]), pack_bf16x2(w9[2], w9[3]), pack_bf16x2(w9[4], w9[5]),
-                           pack_bf16x2(w9[6], w9[7]));
-            carry[i][0] = w9[8];
-          } else if (ky == 1) {  // k 8..15 = carry, w9[0..6]
-            *reinterpret_cast<uint4*>(sa + staged_off(r, 1, 32)) =
-                make_uint4(pack_bf16x2(carry[i][0], w9[0]), pack_bf16x2(w9[1], w9[2]), pack_bf16x2(w9[3], w9[4]),
-                           pack_bf16x2(w9[5], w9[6]));
-            carry[i][0] = w9[7];
-            carry[i][1] = w9[8];
-          } else {               // k 16..23 = carry[0..1], w9[0..5]; k 24..26 = w9[6..8], then zeros
-            *reinterpret_cast<uint4*>(sa + staged_off(r, 2, 32)) =
-                make_uint4(pack_bf16x2(carry[i][0], carry[i][1]), pack_bf16x2(w9[0], w9[1]), pack_bf16x2(w9[2], w9[3]),
-                           pack_bf16x2(w9[4], w9[5]));
-            *reinterpret_cast<uint4*>(sa + staged_off(r, 3, 32)) =
-                make_uint4(pack_bf16x2(w9[6], w9[7]), pack_bf16x2(w9[8], 0.f), 0u, 0u);
-          }
+        for (int j = 0; j < 2; ++j) {
+          float v[28];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = f[ci][j + ky][kx];
+          v[27] = 0.f;
+          const int r = (base_row + j) * 16 + col;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<uint4*>(sa + staged_off(r, c, 32)) =
+                make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                           pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+          *reinterpret_cast<uint4*>(sa + staged_off(r, 3, 32)) =
+              make_uint4(pack_bf16x2(v[24], v[25]), pack_bf16x2(v[26], 0.f), 0u, 0u);
         }
       }
       fence_proxy_async_smem();
