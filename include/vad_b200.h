@@ -41,6 +41,10 @@ int vad_debug_last_trap(unsigned long long out[4]);
  * given: 0 none, 1 the 3-channel score layer (default), 2 also Cout = 32, 3 also Cout = 64; -1 restores the VAD_KX
  * environment setting.  Returns the previous mode. */
 int vad_debug_set_kx(int mode);
+/* Tuning / test aid for vad_convlstm_sequence: 0 = one launch per time step (chained with programmatic dependent
+ * launch), 1 = one persistent launch per layer when the tiles fit the SMs (default), -1 = VAD_LSTM_SEQ environment
+ * setting.  Returns the previous override. */
+int vad_debug_set_lstm_mode(int mode);
 /* Bring-up aid: when set, CTA 0 of every vad_conv_layer kernel stamps clock64 at role events of its first 64 tiles
  * into device_buf[4 roles][64][16] (role 0 TMA producer, 1 MMA issuer, 2/3 epilogue group 0/1).  NULL disables. */
 int vad_debug_set_timeline(long long* device_buf);

@@ -139,11 +139,14 @@ def test_first_conv(cuda_device, pool, B, H, W):
     _assert_close(out, _nhwc(ref), f"first conv pool={pool}", atol=1e-3)
 
 
-@pytest.mark.parametrize("B,T,H,W", [(2, 3, 8, 8), (3, 2, 6, 10)])
-def test_convlstm_sequence(cuda_device, B, T, H, W):
-    """ConvLSTM over a short sequence vs the torch formulation of video_autoencoder.py:64-85 (one layer)."""
+@pytest.mark.parametrize("B,T,H,W", [(2, 3, 8, 8), (3, 2, 6, 10), (1, 5, 24, 40)])
+@pytest.mark.parametrize("persistent", [1, 0])
+def test_convlstm_sequence(cuda_device, B, T, H, W, persistent):
+    """ConvLSTM over a short sequence vs the torch formulation of video_autoencoder.py:64-85 (one layer), with the
+    persistent sequence kernel (cell state in registers) and with one launch per step (cell state in memory)."""
     eng, nat, prep = _mods()
     dev = cuda_device
+    nat.load().vad_debug_set_lstm_mode(persistent)
     cin = hid = 128
     g = torch.Generator().manual_seed(11)
     w = torch.randn(4 * hid, cin + hid, 3, 3, generator=g) * (1.0 / (9 * (cin + hid))) ** 0.5
@@ -167,6 +170,32 @@ def test_convlstm_sequence(cuda_device, B, T, H, W):
         _assert_close(out[:, t], _nhwc(h), f"convlstm h at t={t}", atol=1e-2)
     cst = ve.bufs.get("c0", (B, H, W, hid), torch.float32, dev)
     _assert_close(cst, _nhwc(c), "convlstm final c", rtol=1e-2, atol=1e-2)
+    nat.load().vad_debug_set_lstm_mode(-1)
+
+
+def test_convlstm_persistent_equals_per_step(cuda_device):
+    """Both ConvLSTM paths run the same MMAs in the same order: hidden sequence and final cell state are bit-identical."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    B, T, H, W, cin, hid = 4, 6, 8, 8, 128, 128
+    g = torch.Generator().manual_seed(31)
+    w = torch.randn(4 * hid, cin + hid, 3, 3, generator=g) * (1.0 / (9 * (cin + hid))) ** 0.5
+    b = torch.randn(4 * hid, generator=g) * 0.1
+    seq = _rand_nhwc(B * T, H, W, cin, dev, seed=5).view(B, T, H, W, cin)
+    outs = []
+    for mode in (1, 0):
+        packed = {"lstm.0": _dev(prep.pack_lstm(w.double(), b.double(), hid), dev), "lstm_layers": 1}
+        ve = eng.VideoEngine(packed)
+        nat.load().vad_debug_set_lstm_mode(mode)
+        try:
+            out = ve.convlstm(seq, B, T, H, W).clone()
+            cst = ve.bufs.get("c0", (B, H, W, hid), torch.float32, dev).clone()
+        finally:
+            nat.load().vad_debug_set_lstm_mode(-1)
+        torch.cuda.synchronize()
+        outs.append((out, cst))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 48), (1, 48, 256)])

@@ -514,6 +514,13 @@ int vad_debug_set_kx(int mode) {  // -1 = back to the VAD_KX environment setting
   return prev;
 }
 
+static int g_lstm_mode_override = -1;  // vad_debug_set_lstm_mode
+int vad_debug_set_lstm_mode(int mode) {  // 0 one launch per step, 1 persistent sequence kernel, -1 environment default
+  const int prev = g_lstm_mode_override;
+  g_lstm_mode_override = mode;
+  return prev;
+}
+
 int vad_debug_last_trap(unsigned long long out[4]) {
   if (!g_trap_host || !out) return VAD_ERR_ARG;
   for (int i = 0; i < 4; ++i) out[i] = g_trap_host[i];
@@ -814,7 +821,8 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // One persistent launch for the whole sequence when every tile gets its own resident CTA (cell state in registers,
   // grid-wide step counter); VAD_LSTM_SEQ=0 keeps one launch per step.
-  static const int seq = env_int("VAD_LSTM_SEQ", 1);
+  static const int seq_env = env_int("VAD_LSTM_SEQ", 1);
+  const int seq = g_lstm_mode_override >= 0 ? g_lstm_mode_override : seq_env;
   if (seq && a.tma_store && a.total_tiles <= sm_count() && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
     a.out = d->out;
     return launch_convlstm_seq(L.CK, a, T, a.total_tiles, stream);
