@@ -156,6 +156,15 @@ static int hs_setting() {
   static int v = env_int("VAD_HS", 1);
   return v;
 }
+// VAD_TOKEN bit mask: the two MMA issuers pass a token (strict tile order) — 1 halo kernel, 2 first conv, 8 kx (score)
+// kernel.  Default: on for tiles with a long MMA sequence (64-channel chunks: 36 MMAs, where an ordered, uninterrupted
+// stream matters), off for the short ones (free-running issuers overlap their per-tile latencies better).  The token is
+// forced on when the patch ring has an odd number of slots: a slot is then waited for by both issuers in turn, and
+// only the token's ordering keeps either from being two barrier phases ahead.
+static int token_setting() {
+  static int v = env_int("VAD_TOKEN", 0);
+  return v;
+}
 static int tma_store_setting() {
   static int v = env_int("VAD_TMA_STORE", 1);
   return v;
@@ -769,6 +778,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   a.timeline = g_timeline;
   a.dbg = env_int("VAD_DBG", 0);
   a.dual_mma = (dual_mma_setting() & ((use_halo || use_kx) ? 1 : 4)) != 0;
+  a.token = (token_setting() & (use_kx ? 8 : 1)) != 0 || ((use_halo || use_kx) && ((a.halo_stages & 1) || CK == 64));
   L.use_kx = use_kx;
   L.use_hs = use_hs;
   L.CK = CK;
@@ -888,6 +898,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   a.w_first = weight;
   a.dbg = env_int("VAD_DBG", 0);
   a.dual_mma = (dual_mma_setting() & 2) != 0;
+  a.token = (token_setting() & 2) != 0;
   a.timeline = g_timeline;
   a.out = out;
   a.cout = 32;

@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
         mbar_wait_a(acce0 + as * 8, ((it / kAS) & 1) ^ 1u, 3);
         if (lane == 0) tl_stamp(a, 1, it, 1);
         mbar_wait_a(full0 + stage * 8, phase, 2);
-        if (dual && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
+        if (dual && a.token && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
           }
           umma_commit_a(empty0 + stage * 8);
           umma_commit_a(accf0 + as * 8);
-          if (dual) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
+          if (dual && a.token) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);
@@ -1059,7 +1059,7 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
         // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
         // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
         // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
-        if (dual && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
+        if (dual && a.token && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
           }
           umma_commit_a(empty0 + stage * 8);
           umma_commit_a(accf0 + as * 8);
-          if (dual) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
+          if (dual && a.token) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);
@@ -1567,19 +1567,25 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 2) {
     // ===================================================================== TMA: fp32 input patches
-    int stage = 0;
-    uint32_t phase = 0;
-    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+    // two producer warps take alternate tiles (warp 2 is free once TMEM is allocated): the per-tile loop of a single
+    // producer (tile walk, one barrier wait, one TMA issue: ~400 cycles of scalar latency) would otherwise cap the
+    // whole kernel.  Ring slots alternate with the tiles, so each slot always belongs to the same producer.
+    const int pi = warp == 0 ? 0 : 1;
+    const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
+    const uint32_t sp0 = smem_addr_once(s_p);
+    int it = pi;
+    for (TileIter ti(a, blockIdx.x + pi * gridDim.x, 2 * gridDim.x); ti.tile < a.total_tiles; ti.next(a), it += 2) {
       const TileCoord t = ti.coord(a, BN);
-      mbar_wait(&patch_empty[stage], phase ^ 1u, 7);
-      if (elect_one() && !(a.dbg & 1)) {
-        mbar_arrive_expect_tx(&patch_full[stage], kPatchBytes);
-        tma_load_4d(s_p + stage * kPatchStride, &a.mapA0, &patch_full[stage], t.w0 - kPatchX0, t.h0 - 1, 0, t.b0);
+      const int stage = it % kFirstStages;
+      const uint32_t phase = (it / kFirstStages) & 1;
+      mbar_wait_a(pempty0 + stage * 8, phase ^ 1u, 7);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(pfull0 + stage * 8, kPatchBytes);
+        tma_load_4d_a(sp0 + stage * kPatchStride, &a.mapA0, pfull0 + stage * 8, t.w0 - kPatchX0, t.h0 - 1, 0, t.b0);
       }
       __syncwarp();
-      if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1 || warp == 3) {
     // ===================================================================== MMA issuers (two warps, alternate tiles)
@@ -1605,7 +1611,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
         // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
         // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
         // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
-        if (dual && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
+        if (dual && a.token && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
         if (lane == 0) tl_stamp(a, 1, it, 2);
         tc_fence_after();
         if (elect_one()) {
@@ -1615,7 +1621,7 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
           umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
           umma_commit_a(empty0 + stage * 8);
           umma_commit_a(accf0 + as * 8);
-          if (dual) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
+          if (dual && a.token) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
         }
         __syncwarp();
         if (lane == 0) tl_stamp(a, 1, it, 3);

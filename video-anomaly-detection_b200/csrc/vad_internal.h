@@ -43,6 +43,7 @@ struct alignas(64) ConvArgs {
   float* partials;
   int dbg;              // bring-up switches (VAD_DBG environment variable)
   int dual_mma;         // 1: two MMA-issuer warps take alternate tiles
+  int token;            // 1: the two issuers pass a token (strict tile order on the tensor pipe)
   long long* timeline;  // optional [role 0..3][64 tiles][8 events] clock64 stamps of CTA 0 (vad_debug_set_timeline)
   const void* w_first;  // first conv: bf16 [32 n][32 k] weights, k = (ky*3+kx)*3+ci (27 real + 5 zero)
   // epilogue staging / TMA store
