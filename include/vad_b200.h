@@ -154,6 +154,15 @@ int vad_f32_nchw_to_u8_hwc(const float* src, int frames, int H, int W, uint8_t* 
 int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
                         vad_stream_t stream);
 
+/* ---- SSIM as an alternative anomaly score ----------------------------------------------------- */
+/* SSIMLoss.forward — utils/losses.py:51-93 — per frame: loss[f] = 1 - mean over (3,H,W) of the SSIM map between
+ * pred[f] and target[f] (fp32 NCHW, 3 channels; 11x11 Gaussian window, sigma 1.5, zero padding).  The reference's batch
+ * value is the mean of loss[]; CombinedLoss (:116-121) = (1-alpha)*MSE + alpha*loss with the MSE from vad_score.
+ * ssim_map (nullable) receives the per-pixel map [frames,3,H,W]; scratch >= vad_ssim_scratch_bytes(frames,H,W). */
+size_t vad_ssim_scratch_bytes(int frames, int H, int W);
+int vad_ssim_loss(const float* pred, const float* target, int frames, int H, int W, float* loss, float* ssim_map,
+                  void* scratch, vad_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,6 +216,44 @@ def video_reconstruction_error(
 
 
 # --------------------------------------------------------------------------------------
+# SSIM / combined loss as an alternative score — utils/losses.py
+# --------------------------------------------------------------------------------------
+def ssim_window(size: int = 11, sigma: float = 1.5) -> Tensor:
+    """SSIMLoss._create_gaussian_window — utils/losses.py:35-49: normalised 1-D Gaussian, outer product."""
+    coords = torch.arange(size, dtype=torch.float32) - size // 2
+    gauss = torch.exp(-coords ** 2 / (2 * sigma ** 2))
+    gauss = gauss / gauss.sum()
+    return gauss.unsqueeze(1) @ gauss.unsqueeze(0)
+
+
+def ssim_map(pred: Tensor, target: Tensor, window_size: int = 11) -> Tensor:
+    """SSIMLoss.forward up to `ssim_map` — utils/losses.py:65-90 (depthwise Gaussian statistics, zero padding)."""
+    c = pred.shape[1]
+    win = ssim_window(window_size).to(pred.device).expand(c, 1, window_size, window_size).contiguous()
+    pad = window_size // 2
+    conv = lambda t: torch.nn.functional.conv2d(t, win, padding=pad, groups=c)
+    mu_p, mu_t = conv(pred), conv(target)
+    mu_pp, mu_tt, mu_pt = mu_p ** 2, mu_t ** 2, mu_p * mu_t
+    s_pp = conv(pred ** 2) - mu_pp
+    s_tt = conv(target ** 2) - mu_tt
+    s_pt = conv(pred * target) - mu_pt
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    return ((2 * mu_pt + c1) * (2 * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_pp + s_tt + c2))
+
+
+def ssim_loss(pred: Tensor, target: Tensor, per_frame: bool = False) -> Tensor:
+    """`1 - ssim_map.mean()` — utils/losses.py:92-93; per_frame=True: one value per leading index (the batch value is
+    their mean, all frames having the same size)."""
+    m = ssim_map(pred, target)
+    return 1 - (m.mean(dim=[1, 2, 3]) if per_frame else m.mean())
+
+
+def combined_loss(pred: Tensor, target: Tensor, alpha: float = 0.5) -> Tensor:
+    """CombinedLoss.forward — utils/losses.py:116-121: (1-alpha)*MSE + alpha*(1-SSIM)."""
+    return (1 - alpha) * torch.mean((pred - target) ** 2) + alpha * ssim_loss(pred, target)
+
+
+# --------------------------------------------------------------------------------------
 # consumers of the scores (they define the parity observables)
 # --------------------------------------------------------------------------------------
 def heatmap_u8(error_map: np.ndarray) -> np.ndarray:

@@ -65,3 +65,22 @@ def test_scoring_from_u8_frames_end_to_end(cuda_device):
     a = m.get_reconstruction_error(frames.normalize_u8(u8.to(cuda_device)))
     b = m.get_reconstruction_error(x_host.to(cuda_device))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_ssim_loss_matches_reference_golden_and_oracle(cuda_device, name):
+    """vad_ssim_loss vs the unmodified reference's SSIMLoss / CombinedLoss outputs (tests/golden/golden_ssim.npz) and the
+    oracle's per-pixel map.  fp32; the separable window reorders the sums: 1e-4 relative on the loss."""
+    from oracle import vad_oracle
+    from runtime import metrics
+    from test_oracle import _ssim_pair
+    gold = np.load(os.path.join(GOLDEN, "golden_ssim.npz"))
+    p, t = _ssim_pair(*gold[f"{name}_spec"])
+    loss, smap = metrics.ssim_loss(p.to(cuda_device), t.to(cuda_device), want_map=True)
+    comb = metrics.combined_loss(p.to(cuda_device), t.to(cuda_device))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss.cpu().numpy(), gold[f"{name}_ssim_loss_per_frame"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(float(loss.mean()), gold[f"{name}_ssim_loss"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(float(comb.mean()), gold[f"{name}_combined"], rtol=1e-4, atol=2e-6)
+    ref_map = vad_oracle.ssim_map(p, t)
+    assert float((smap.cpu() - ref_map).abs().max()) < 2e-4

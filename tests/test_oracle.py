@@ -150,3 +150,23 @@ def test_consumers_heatmap_flags_and_rank_helper():
     assert checked == 5 and bad == 0  # the near-tie pair is not compared
     checked, bad = vad_oracle.tie_aware_rank_agreement(ref, np.array([2.0, 1.0, 3.0, 3.0]))
     assert bad == 1
+
+
+# ---- SSIM / combined loss: oracle restatement vs the unmodified reference's outputs
+def _ssim_pair(seed, b, h, w, noise):
+    g = torch.Generator().manual_seed(int(seed))
+    t = (torch.rand(int(b), 3, int(h), int(w), generator=g) * 2 - 1)
+    t = torch.nn.functional.avg_pool2d(t, 5, 1, 2)
+    p = (t + noise * torch.randn(int(b), 3, int(h), int(w), generator=g)).clamp(-1, 1)
+    return p, t
+
+
+def test_ssim_oracle_matches_reference_golden():
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ssim.npz"))
+    for name in ("a", "b", "c"):
+        p, t = _ssim_pair(*gold[f"{name}_spec"])
+        np.testing.assert_allclose(float(vad_oracle.ssim_loss(p, t)), gold[f"{name}_ssim_loss"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(vad_oracle.ssim_loss(p, t, per_frame=True).numpy(), gold[f"{name}_ssim_loss_per_frame"],
+                                   rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(float(vad_oracle.combined_loss(p, t)), gold[f"{name}_combined"], rtol=1e-5, atol=1e-6)

@@ -488,6 +488,96 @@ __global__ void __launch_bounds__(256) heatmap_jet_kernel(const float* __restric
   out[i * 3 + 2] = static_cast<uint8_t>(c >> 16);
 }
 
+// ------------------------------------------------------------------------------------------------ SSIM
+// SSIMLoss.forward of the reference (utils/losses.py:51-93): Gaussian-weighted (11x11, sigma 1.5, zero padding) local
+// means / variances / covariance per channel, ssim = (2 mu_p mu_t + C1)(2 s_pt + C2) / ((mu_p^2 + mu_t^2 + C1)(s_pp +
+// s_tt + C2)).  The Gaussian is separable: one block = one 32x32 output tile of one (frame, channel) plane; the two
+// inputs come in with a 5-pixel halo, a horizontal pass forms the five row-filtered moments (p, t, p^2, t^2, p t) in
+// shared memory and the vertical pass finishes them.  HBM traffic = the two images once (+ halo) and the optional map.
+constexpr int kSsimTile = 32, kSsimR = 5, kSsimIn = kSsimTile + 2 * kSsimR;  // 42
+__constant__ float c_ssim_gauss[11];
+
+__global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                   int H, int W, int tiles_x, int tiles_y, float* __restrict__ map,
+                                                   float* __restrict__ partials) {
+  __shared__ float s_p[kSsimIn][kSsimIn + 1];
+  __shared__ float s_t[kSsimIn][kSsimIn + 1];
+  __shared__ float s_h[5][kSsimIn][kSsimTile + 1];
+  __shared__ float s_red[8];
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
+  const long long plane_idx = tile / (tiles_x * tiles_y);  // frame * 3 + channel
+  const long long plane = static_cast<long long>(H) * W;
+  const float* pp = pred + plane_idx * plane;
+  const float* tp = target + plane_idx * plane;
+  const int x0 = tx * kSsimTile - kSsimR, y0 = ty * kSsimTile - kSsimR;
+  for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
+    const int iy = i / kSsimIn, ix = i - iy * kSsimIn;
+    const int gy = y0 + iy, gx = x0 + ix;
+    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    s_p[iy][ix] = in ? __ldg(pp + static_cast<long long>(gy) * W + gx) : 0.f;
+    s_t[iy][ix] = in ? __ldg(tp + static_cast<long long>(gy) * W + gx) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSsimIn * kSsimTile; i += 256) {  // horizontal pass
+    const int iy = i / kSsimTile, ox = i - iy * kSsimTile;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = c_ssim_gauss[k], p = s_p[iy][ox + k], t = s_t[iy][ox + k];
+      a0 = fmaf(g, p, a0);
+      a1 = fmaf(g, t, a1);
+      a2 = fmaf(g, p * p, a2);
+      a3 = fmaf(g, t * t, a3);
+      a4 = fmaf(g, p * t, a4);
+    }
+    s_h[0][iy][ox] = a0; s_h[1][iy][ox] = a1; s_h[2][iy][ox] = a2; s_h[3][iy][ox] = a3; s_h[4][iy][ox] = a4;
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < kSsimTile * kSsimTile; i += 256) {  // vertical pass + SSIM
+    const int oy = i / kSsimTile, ox = i - oy * kSsimTile;
+    const int gy = ty * kSsimTile + oy, gx = tx * kSsimTile + ox;
+    float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = c_ssim_gauss[k];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) m[q] = fmaf(g, s_h[q][oy + k][ox], m[q]);
+    }
+    const float mu_pp = m[0] * m[0], mu_tt = m[1] * m[1], mu_pt = m[0] * m[1];
+    const float s_pp = m[2] - mu_pp, s_tt = m[3] - mu_tt, s_pt = m[4] - mu_pt;
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const float v = ((2.f * mu_pt + C1) * (2.f * s_pt + C2)) / ((mu_pp + mu_tt + C1) * (s_pp + s_tt + C2));
+    if (gy < H && gx < W) {
+      acc += v;
+      if (map) map[plane_idx * plane + static_cast<long long>(gy) * W + gx] = v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    partials[blockIdx.x] = s;
+  }
+}
+
+// loss[f] = 1 - (sum of the frame's 3 * tiles partials) / (3*H*W), in a fixed order
+__global__ void __launch_bounds__(128) ssim_finalize_kernel(const float* __restrict__ partials, int frames, int per_frame,
+                                                            float inv_count, float* __restrict__ loss) {
+  const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= frames) return;
+  float s = 0.f;
+  for (int i = lane; i < per_frame; i += 32) s += partials[static_cast<long long>(f) * per_frame + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) loss[f] = 1.f - s * inv_count;
+}
+
 }  // namespace vad
 
 // ================================================================================================ C ABI
@@ -1039,5 +1129,44 @@ int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int 
   return static_cast<int>(cudaGetLastError());
 }
 
+size_t vad_ssim_scratch_bytes(int frames, int H, int W) {
+  if (frames <= 0 || H <= 0 || W <= 0) return 0;
+  const size_t tiles = static_cast<size_t>((W + kSsimTile - 1) / kSsimTile) * ((H + kSsimTile - 1) / kSsimTile);
+  return tiles * 3 * static_cast<size_t>(frames) * sizeof(float);
+}
+
+int vad_ssim_loss(const float* pred, const float* target, int frames, int H, int W, float* loss, float* ssim_map,
+                  void* scratch, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!pred || !target || !loss || !scratch || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  static bool window_ready = false;
+  if (!window_ready) {  // the reference's window: normalised exp(-x^2 / (2 * 1.5^2)), x = -5..5 (utils/losses.py:38-41)
+    float g[11], sum = 0.f;
+    for (int i = 0; i < 11; ++i) {
+      const float x = static_cast<float>(i - 5);
+      g[i] = std::exp(-(x * x) / (2.f * 1.5f * 1.5f));
+      sum += g[i];
+    }
+    for (int i = 0; i < 11; ++i) g[i] /= sum;
+    cudaError_t e = cudaMemcpyToSymbol(c_ssim_gauss, g, sizeof(g));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    window_ready = true;
+  }
+  const int tiles_x = (W + kSsimTile - 1) / kSsimTile, tiles_y = (H + kSsimTile - 1) / kSsimTile;
+  const long long blocks = static_cast<long long>(tiles_x) * tiles_y * 3 * frames;
+  if (blocks > 0x7fffffffLL) return VAD_ERR_SHAPE;
+  ssim_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pred, target, H, W, tiles_x, tiles_y, ssim_map,
+                                                               reinterpret_cast<float*>(scratch));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const float inv = 1.0f / (3.0f * static_cast<float>(H) * static_cast<float>(W));
+  ssim_finalize_kernel<<<(frames + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const float*>(scratch), frames,
+                                                            tiles_x * tiles_y * 3, inv, loss);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // extern "C"
+
 

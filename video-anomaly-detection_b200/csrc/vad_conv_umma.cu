@@ -317,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
                 pack_bf16x2(act_fn(m[2] + b0.z, a.slope), act_fn(m[3] + b0.w, a.slope)),
                 pack_bf16x2(act_fn(m[4] + b1.x, a.slope), act_fn(m[5] + b1.y, a.slope)),
                 pack_bf16x2(act_fn(m[6] + b1.z, a.slope), act_fn(m[7] + b1.w, a.slope)));
-            if (KX == 1 || ww < kKxValid) *reinterpret_cast<uint4*>(buf + staged_off(prow, sub * 4 + part, OC)) = val;
+            if (KX == 1 || ww < kKxValid) sts128(buf + staged_off(prow, sub * 4 + part, OC), val);
           } else {
             const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + lc);
             uint32_t p[16];
@@ -333,8 +333,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
             if (KX == 1 || ww < kKxValid) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(buf + staged_off(srow, sub * 4 + j, OC)) =
-                    make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+                sts128(buf + staged_off(srow, sub * 4 + j, OC), make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
             }
           }
         }
@@ -466,7 +465,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         *reinterpret_cast<float4*>(cptr + s * 8 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
         if (!a.tma_store) *reinterpret_cast<uint4*>(hptr + s * 8) = hv;
       }
-      if (a.tma_store) *reinterpret_cast<uint4*>(buf + staged_off(L.srow, s, 32)) = hv;
+      if (a.tma_store) sts128(buf + staged_off(L.srow, s, 32), hv);
     }
     if (a.tma_store) {
       fence_proxy_async_smem();
@@ -1009,29 +1008,33 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (elect_one()) {
-      mbar_arrive_expect_tx(&w_bar, 3u * kBBytes);
-      for (int ky = 0; ky < 3; ++ky) tma_load_2d(s_w + ky * kBBytes, &a.mapB, &w_bar, ky * a.w_ctap, 0);
+  if (warp == 0 || (warp == 2 && (a.halo_stages & 1) == 0)) {
+    // ===================================================================== TMA producers
+    // warp 0, plus warp 2 (idle after the TMEM allocation) on alternate tiles when the ring depth is even (each slot
+    // then always belongs to the same producer)
+    const bool two = (a.halo_stages & 1) == 0;
+    const int pi = warp == 0 ? 0 : 1;
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&w_bar, 3u * kBBytes);
+        for (int ky = 0; ky < 3; ++ky) tma_load_2d(s_w + ky * kBBytes, &a.mapB, &w_bar, ky * a.w_ctap, 0);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
     const uint32_t sa0 = smem_addr_once(s_a);
-    int stage = 0;
-    uint32_t phase = 0;
-    int pn = 0;
-    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a), ++pn) {
+    const int pstep = two ? 2 : 1;
+    int it = pi;
+    for (TileIter ti(a, blockIdx.x + pi * gridDim.x, pstep * gridDim.x); ti.tile < a.total_tiles; ti.next(a), it += pstep) {
       const TileCoord t = ti.coord(a, BN);
-      if (lane == 0) tl_stamp(a, 0, pn, 0);
+      const int stage = it % a.halo_stages;
+      const uint32_t phase = static_cast<uint32_t>((it / a.halo_stages) & 1);
       mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
-      if (lane == 0) tl_stamp(a, 0, pn, 1);
       if (elect_one()) {
         mbar_arrive_expect_tx_a(full0 + stage * 8, kPatchBytes);
         tma_load_5d_a(sa0 + stage * kPatchBytes, &a.mapA0, full0 + stage * 8, 0, t.w0 - 1, t.h0 - 1, a.tA0, t.b0);
       }
       __syncwarp();
-      if (++stage == a.halo_stages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1 || warp == 3) {
     // ===================================================================== MMA issuers (alternate tiles)
@@ -1450,9 +1453,8 @@ __global__ void __launch_bounds__(256, 1) convlstm_seq_kernel(const __grid_const
           c[s * 8 + e] = cn;
           hn[e] = sigmoid_fn(xo) * tanh_fn(cn);
         }
-        *reinterpret_cast<uint4*>(stg + staged_off(L.srow, s, 32)) =
-            make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]), pack_bf16x2(hn[4], hn[5]),
-                       pack_bf16x2(hn[6], hn[7]));
+        sts128(stg + staged_off(L.srow, s, 32), make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                                            pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7])));
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
@@ -1676,11 +1678,10 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
           const int r = (base_row + j) * 16 + col;
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            *reinterpret_cast<uint4*>(sa + staged_off(r, c, 32)) =
-                make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                           pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-          *reinterpret_cast<uint4*>(sa + staged_off(r, 3, 32)) =
-              make_uint4(pack_bf16x2(v[24], v[25]), pack_bf16x2(v[26], 0.f), 0u, 0u);
+            sts128(sa + staged_off(r, c, 32),
+                   make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                              pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7])));
+          sts128(sa + staged_off(r, 3, 32), make_uint4(pack_bf16x2(v[24], v[25]), pack_bf16x2(v[26], 0.f), 0u, 0u));
         }
       }
       fence_proxy_async_smem();

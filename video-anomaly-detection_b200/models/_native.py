@@ -20,7 +20,7 @@ EXPORTS = (
     "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convlstm_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8", "vad_u8_hwc_to_f32_nchw", "vad_f32_nchw_to_u8_hwc",
-    "vad_heatmap_jet_rgb",
+    "vad_heatmap_jet_rgb", "vad_ssim_scratch_bytes", "vad_ssim_loss",
 )
 
 
@@ -84,6 +84,10 @@ def load() -> C.CDLL:
     lib.vad_u8_hwc_to_f32_nchw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.vad_f32_nchw_to_u8_hwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.vad_heatmap_jet_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.vad_ssim_scratch_bytes.restype = C.c_size_t
+    lib.vad_ssim_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.vad_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]
     _lib = lib
     return lib
 
