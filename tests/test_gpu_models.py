@@ -271,3 +271,28 @@ def test_submodule_calls(cuda_device):
     seq, (h_last, c_last) = v.convlstm(enc)
     assert tuple(seq.shape) == tuple(ref_seq.shape) and torch.equal(h_last, seq[:, -1])
     assert (seq.cpu() - ref_seq).abs().max() <= 0.05
+
+
+def test_streaming_scorer_equals_windowed_forward(cuda_device):
+    """runtime/streaming.py: cached per-frame encoder features + per-window ConvLSTM/decoder/score give
+    bit-identical outputs to scoring every overlapping window from scratch, with each frame encoded once."""
+    from models.video_autoencoder import VideoAutoencoder
+    from runtime.streaming import StreamingVideoScorer
+    torch.manual_seed(0)
+    m = VideoAutoencoder().eval().to(cuda_device)
+    g = torch.Generator().manual_seed(21)
+    n, T, stride = 22, 8, 3
+    video = (torch.rand(n, 3, 64, 48, generator=g) * 2 - 1).to(cuda_device)
+    sc = StreamingVideoScorer(m, seq_len=T, stride=stride, want_recon=True)
+    got = []
+    for chunk in (video[:5], video[5:6], video[6:19], video[19:]):   # ragged arrival
+        got += sc.push(chunk)
+    starts = list(range(0, n - T + 1, stride))
+    assert [s for s, _ in got] == starts
+    assert sc.frames_encoded == n                                    # vs len(starts) * T = 40 without the cache
+    for s, out in got:
+        ref = m.score_all(video[s:s + T].unsqueeze(0))
+        assert torch.equal(out.score, ref.score)
+        assert torch.equal(out.minmax, ref.minmax)
+        assert torch.equal(out.heat, ref.heat)
+        assert torch.equal(out.recon, ref.recon)
