@@ -42,8 +42,9 @@ int vad_debug_last_trap(unsigned long long out[4]);
  * environment setting.  Returns the previous mode. */
 int vad_debug_set_kx(int mode);
 /* Tuning / test aid for vad_convlstm_sequence: 0 = one launch per time step (chained with programmatic dependent
- * launch), 1 = one persistent launch per layer when the tiles fit the SMs (default), -1 = VAD_LSTM_SEQ environment
- * setting.  Returns the previous override. */
+ * launch), 1 = one persistent launch per layer when the tiles fit the SMs (default; the patch kernel where its tile
+ * shapes apply), 2 = the same but always the streaming sequence kernel, -1 = VAD_LSTM_SEQ environment setting.
+ * Returns the previous override. */
 int vad_debug_set_lstm_mode(int mode);
 /* Bring-up aid: when set, CTA 0 of every vad_conv_layer kernel stamps clock64 at role events of its first 64 tiles
  * into device_buf[4 roles][64][16] (role 0 TMA producer, 1 MMA issuer, 2/3 epilogue group 0/1).  NULL disables. */

@@ -923,6 +923,50 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   // grid-wide step counter); VAD_LSTM_SEQ=0 keeps one launch per step.
   static const int seq_env = env_int("VAD_LSTM_SEQ", 1);
   const int seq = g_lstm_mode_override >= 0 ? g_lstm_mode_override : seq_env;
+  // Patch variant (A operand through one patch per chunk, weights through their own ring): 8x8 frames (two per tile) or
+  // tiles of 8 x 16 pixels inside larger frames.  VAD_LSTM_SEQ=2 disables it (streaming sequence kernel instead).
+  if (seq == 1 && a.tma_store && L.CK == 64 && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
+    const bool geo1 = d->H == 8 && d->W == 8;
+    const bool geo2 = !geo1 && d->H >= 8 && d->W >= 8;
+    TileGeom g;
+    g.lgTW = 3;
+    g.lgTH = geo1 ? 3 : 4;
+    g.lgTN = geo1 ? 1 : 0;
+    g.tiles_w = (d->W + 7) >> 3;
+    g.tiles_h = (d->H + (1 << g.lgTH) - 1) >> g.lgTH;
+    g.tiles_b = (d->B + (1 << g.lgTN) - 1) >> g.lgTN;
+    if ((geo1 || geo2) && g.m_tiles() * a.n_tiles <= sm_count()) {
+      const long long cp = d->out_cpitch;
+      auto patch_map = [&](CUtensorMap* m, const void* base, int C) -> int {
+        if (!geo1) return encode_act_map_box(m, base, C, d->W, d->H, T, d->B, 64, 10, 18, 1);
+        // dims {C, W, B, H, T}: the frame index sits between W and H so that the patch lands as [y][frame][x]
+        cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)d->W, (cuuint64_t)d->B, (cuuint64_t)d->H, (cuuint64_t)T};
+        cuuint64_t st[4] = {(cuuint64_t)C * 2, (cuuint64_t)T * d->H * d->W * C * 2, (cuuint64_t)d->W * C * 2,
+                            (cuuint64_t)d->H * d->W * C * 2};
+        cuuint32_t box[5] = {64, 10, 2, 10, 1};
+        return encode_map5(m, base, dims, st, box, 64);
+      };
+      rc = patch_map(&a.mapA0, d->src0, d->c0);
+      if (rc == VAD_OK) rc = patch_map(&a.mapA1, d->src1, d->c1);
+      if (rc == VAD_OK) {
+        cuuint64_t dims[5] = {(cuuint64_t)d->cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)T, (cuuint64_t)d->B};
+        cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)d->W * cp * 2, (cuuint64_t)step_elems * 2,
+                            (cuuint64_t)d->out_frame_stride * 2};
+        cuuint32_t box[5] = {32, 8, 1u << g.lgTH, 1, 1u << g.lgTN};
+        rc = encode_map5(&a.mapOut, d->out, dims, st, box, 32);
+      }
+      if (rc == VAD_OK) {
+        a.lgTW = g.lgTW; a.lgTH = g.lgTH; a.lgTN = g.lgTN;
+        a.tiles_w = g.tiles_w; a.tiles_h = g.tiles_h; a.tiles_b = g.tiles_b;
+        a.total_tiles = g.m_tiles() * a.n_tiles;
+        a.w_step = 8; a.tw_valid = 8; a.pair = 1;
+        a.row_perm = geo1 ? 2 : 0;
+        a.out = d->out;
+        return launch_convlstm_patch(a, T, a.total_tiles, stream);
+      }
+      return rc;
+    }
+  }
   if (seq && a.tma_store && a.total_tiles <= sm_count() && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
     a.out = d->out;
     return launch_convlstm_seq(L.CK, a, T, a.total_tiles, stream);

@@ -197,7 +197,15 @@ __device__ __forceinline__ EpiLane make_epi_lane(const ConvArgs& a, int q, int l
   const int r = q * 32 + lane;
   const int TW = 1 << a.lgTW, TH = 1 << a.lgTH;
   EpiLane L;
-  if (a.row_perm) {
+  if (a.row_perm == 2) {
+    // ConvLSTM patch kernel on 8x8 frames, two frames per tile: row = ((y*2 + frame)*8 + x) — the order in which one
+    // patch [y][frame][x] serves all nine taps with a constant 8-row-group stride
+    L.ww = r & 7;
+    L.bb = (r >> 3) & 1;
+    L.hh = r >> 4;
+    L.mx = 1;
+    L.my = 16;
+  } else if (a.row_perm) {
     // first conv (8 x 16 tiles): A row = (hh >> 1)*32 + (ww & 3)*8 + (hh & 1)*4 + (ww >> 2) — the order in which the
     // im2col converter can write its rows without shared-memory bank conflicts
     L.hh = ((r >> 5) << 1) | ((r >> 2) & 1);
@@ -1485,6 +1493,266 @@ __global__ void __launch_bounds__(256, 1) convlstm_seq_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- ConvLSTM, patches
+// The sequence kernel above streams one (A tile, B tile) pair per tap and chunk: 1.15 MB per CTA and step, and with
+// ~190 KB of shared memory in flight against ~1.2 us of TMA latency that alone takes ~7 us per step (clusters that
+// multicast the weights did not help: the limit is bytes in flight per SM, not L2 reads).  Here the A side uses
+// patches like the other 3x3 kernels — per 64-channel chunk ONE TMA patch serves all nine taps through shifted
+// descriptors (A traffic 576 -> 102 KB per step) — and the weight tiles stream through their own 8-slot ring, fed
+// by a second producer warp that never waits for the recurrence (weights do not depend on it).
+//   geometry 1 (8x8 frames, two frames per tile): patch [y 10][frame 2][x 10], rows ((y*2+f)*8 + x), map dims
+//               {C, W, B, H, T};   geometry 2 (tile 8 wide x 16 tall inside one frame): patch [y 18][x 10].
+constexpr int kLpBRing = 8;
+constexpr int kLpPatchPitch = 26 * 1024;  // >= 200 rows x 128 B
+constexpr int kLpPatches = 3;
+
+__global__ void __launch_bounds__(384, 1) convlstm_patch_kernel(const __grid_constant__ ConvArgs a, int T,
+                                                                unsigned int* __restrict__ step_counter) {
+  constexpr int BN = 128, CK = 64;
+  constexpr int kRowBytes = 128;
+  constexpr int kBBytes = BN * kRowBytes;  // 16 KB
+  constexpr uint32_t kLayout = 2u;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t p_full[kLpPatches], p_empty[kLpPatches];
+  __shared__ uint64_t b_full[kLpBRing], b_empty[kLpBRing];
+  __shared__ uint64_t acc_full_bar[2];
+  __shared__ uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[BN];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_b = smem;
+  uint8_t* s_p = smem + kLpBRing * kBBytes;
+  uint8_t* stg = s_p + kLpPatches * kLpPatchPitch;
+
+  const bool geo1 = a.row_perm == 2;
+  const uint32_t patch_tx = static_cast<uint32_t>((geo1 ? 200 : 180) * kRowBytes);
+  const int ky_rows = geo1 ? 20 : 10;  // patch rows per image row
+  const TileCoord tc = TileIter(a, blockIdx.x, gridDim.x).coord(a, BN);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapA1);
+    tma_prefetch_desc(&a.mapB);
+    tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kLpPatches; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < kLpBRing; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 8);  // eight epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<256>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += 384) s_bias[i] = a.bias[tc.n0 + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== patch producer (x_t, then h_{t-1})
+    const uint32_t pf0 = smem_addr_once(&p_full[0]), pe0 = smem_addr_once(&p_empty[0]);
+    const uint32_t sp0 = smem_addr_once(s_p);
+    int ps = 0;
+    uint32_t pphase = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int src = 0; src < 2; ++src) {
+        if (src == 1) {
+          if (t == 0) break;
+          const unsigned int target = static_cast<unsigned int>(t) * gridDim.x;
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(step_counter) < target) {
+              if (clock64() - t0 > 2000000000LL) {
+                if (g_vad_trap_slot) {
+                  g_vad_trap_slot[0] = 12;
+                  g_vad_trap_slot[1] = blockIdx.x;
+                  g_vad_trap_slot[2] = static_cast<unsigned long long>(t);
+                  g_vad_trap_slot[3] = target;
+                  __threadfence_system();
+                }
+                __trap();
+              }
+            }
+          }
+          __syncwarp();
+          fence_proxy_async_all();
+        }
+        const int n_chunks = src == 0 ? a.chunks0 : a.chunks1;
+        const void* map = src == 0 ? static_cast<const void*>(&a.mapA0) : static_cast<const void*>(&a.mapA1);
+        const int tt = src == 0 ? t : t - 1;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait_a(pe0 + ps * 8, pphase ^ 1u, 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx_a(pf0 + ps * 8, patch_tx);
+            if (geo1)  // map dims {C, W, B, H, T}
+              tma_load_5d_a(sp0 + ps * kLpPatchPitch, map, pf0 + ps * 8, c * CK, tc.w0 - 1, tc.b0, tc.h0 - 1, tt);
+            else       // map dims {C, W, H, T, B}
+              tma_load_5d_a(sp0 + ps * kLpPatchPitch, map, pf0 + ps * 8, c * CK, tc.w0 - 1, tc.h0 - 1, tt, tc.b0);
+          }
+          __syncwarp();
+          if (++ps == kLpPatches) { ps = 0; pphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================================== weight producer (independent of the steps)
+    const uint32_t bf0 = smem_addr_once(&b_full[0]), be0 = smem_addr_once(&b_empty[0]);
+    const uint32_t sb0 = smem_addr_once(s_b);
+    int bs = 0;
+    uint32_t bphase = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int src = 0; src < 2; ++src) {
+        if (src == 1 && t == 0) break;
+        const int n_chunks = src == 0 ? a.chunks0 : a.chunks1;
+        const int kbase = src == 0 ? 0 : a.chunks0 * CK;
+        for (int c = 0; c < n_chunks; ++c) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait_a(be0 + bs * 8, bphase ^ 1u, 9);
+            if (elect_one()) {
+              mbar_arrive_expect_tx_a(bf0 + bs * 8, kBBytes);
+              tma_load_2d_a(sb0 + bs * kBBytes, &a.mapB, bf0 + bs * 8, tap * a.w_ctap + kbase + c * CK, tc.n0);
+            }
+            __syncwarp();
+            if (++bs == kLpBRing) { bs = 0; bphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint32_t pf0 = smem_addr_once(&p_full[0]), pe0 = smem_addr_once(&p_empty[0]);
+    const uint32_t bf0 = smem_addr_once(&b_full[0]), be0 = smem_addr_once(&b_empty[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_p), 10 * kRowBytes, kLayout);  // 8-row groups 10 patch rows apart
+    const uint64_t db_base = umma_smem_desc(smem_u32(s_b), 8 * kRowBytes, kLayout);
+    int ps = 0, bs = 0;
+    uint32_t pphase = 0, bphase = 0;
+    for (int t = 0; t < T; ++t) {
+      const int n_patches = a.chunks0 + (t > 0 ? a.chunks1 : 0);
+      const int as = t & 1;
+      mbar_wait_a(acce0 + as * 8, static_cast<uint32_t>(((t >> 1) & 1) ^ 1), 3);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int p = 0; p < n_patches; ++p) {
+        mbar_wait_a(pf0 + ps * 8, pphase, 2);
+        const uint64_t da_p = da_base + static_cast<uint64_t>(ps * (kLpPatchPitch >> 4));
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait_a(bf0 + bs * 8, bphase, 10);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = da_p + static_cast<uint64_t>(((ky * ky_rows + kx) * kRowBytes) >> 4);
+            const uint64_t db = db_base + static_cast<uint64_t>(bs * (kBBytes >> 4));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (p > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_a(be0 + bs * 8);
+            if (tap == 8) umma_commit_a(pe0 + ps * 8);
+            if (tap == 8 && p == n_patches - 1) umma_commit_a(accf0 + as * 8);
+          }
+          __syncwarp();
+          if (++bs == kLpBRing) { bs = 0; bphase ^= 1u; }
+          if (++kx == 3) { kx = 0; ++ky; }
+        }
+        if (++ps == kLpPatches) { ps = 0; pphase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue: gates, c (registers), h
+    // The epilogue sits on the recurrence's critical path (h_t must be published before any neighbour can start the
+    // h half of step t+1), so eight warps share it: warps 4-7 take hidden channels 0..15 of the tile, warps 8-11
+    // channels 16..31 (a warp may read the TMEM lane quarter warp_id % 4, any columns).
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;  // 0 | 1: which 16 channels
+    const EpiLane L = make_epi_lane(a, q, lane);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const bool leader = (warp == kEpiWarp0 && lane == 0);
+    const int fb = tc.b0 + L.bb, h = tc.h0 + L.hh, w = tc.w0 + L.ww;
+    const bool valid = L.row_ok && (fb < a.B) && (h < a.H) && (w < a.W);
+    const int j0 = (tc.n0 >> 7) * 32;
+    float c[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) c[e] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int as = t & 1;
+      mbar_wait_a(accf0 + as * 8, static_cast<uint32_t>((t >> 1) & 1), 4u | (static_cast<uint32_t>(t) << 8));
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int s = half * 2 + s2;  // 8-channel group of the tile
+        uint32_t gi[8], gf[8], gg[8], go[8];
+        tmem_ld_x8(tacc + 0 + s * 8, gi);
+        tmem_ld_x8(tacc + 32 + s * 8, gf);
+        tmem_ld_x8(tacc + 64 + s * 8, gg);
+        tmem_ld_x8(tacc + 96 + s * 8, go);
+        tmem_ld_wait();
+        if (s2 == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce0 + as * 8);
+        }
+        float hn[8];
+        const float* bp = s_bias + s * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xi = __uint_as_float(gi[e]) + bp[e];
+          const float xf = __uint_as_float(gf[e]) + bp[32 + e];
+          const float xg = __uint_as_float(gg[e]) + bp[64 + e];
+          const float xo = __uint_as_float(go[e]) + bp[96 + e];
+          const float cn = sigmoid_fn(xf) * c[s2 * 8 + e] + sigmoid_fn(xi) * tanh_fn(xg);
+          c[s2 * 8 + e] = cn;
+          hn[e] = sigmoid_fn(xo) * tanh_fn(cn);
+        }
+        sts128(stg + staged_off(L.srow, s, 32), make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                                            pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7])));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (leader) {
+        tma_store_5d(&a.mapOut, stg, j0, tc.w0, tc.h0, t, tc.b0);
+        bulk_commit_group();
+        bulk_wait_group_read<0>();
+      }
+      named_bar_sync(1, 256);
+      if (leader) {
+        bulk_wait_group<0>();
+        __threadfence();
+        red_release_gpu_add(step_counter, 1u);
+      }
+    }
+    if (valid && a.c_state != nullptr) {
+      float* cptr = a.c_state + ((static_cast<long long>(fb) * a.H + h) * a.W + w) * a.cout + j0 + half * 16;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(cptr + e) = make_float4(c[e], c[e + 1], c[e + 2], c[e + 3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- first conv
 // 3 -> 32 channel 3x3 conv straight from the fp32 NCHW model input.  K = 27 (padded to 32).  TMA brings the fp32
 // input patch of a tile (3 channels x 10 rows x 24 columns, zero-filled outside the frame = conv padding) into smem;
@@ -1935,6 +2203,27 @@ int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t
   if (CK == 64) return launch_lstm_seq_one<64>(a, T, grid, stream);
   if (CK == 32) return launch_lstm_seq_one<32>(a, T, grid, stream);
   return VAD_ERR_UNSUPPORTED;
+}
+
+int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t stream) {
+  constexpr int smem = kLpBRing * 128 * 128 + kLpPatches * kLpPatchPitch + 8192 + 1024;
+  static_assert(smem <= kSmemBudget, "ConvLSTM patch kernel shared memory");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convlstm_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  static unsigned int next_slot = 32;
+  unsigned int* base = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm_counters);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  unsigned int* counter = base + (next_slot++ & 63u);
+  e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  convlstm_patch_kernel<<<grid, 384, smem, stream>>>(a, T, counter);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace vad

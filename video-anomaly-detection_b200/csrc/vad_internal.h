@@ -76,6 +76,7 @@ int kx_mma_columns(int BN, int EPI);
 int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int hs_patch_stages(int EPI);
 int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t stream);
+int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t stream);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 // dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)
 int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);
