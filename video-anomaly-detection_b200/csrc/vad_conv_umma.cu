@@ -1857,47 +1857,6 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
       }
       __syncwarp();
     }
-  } else if (warp == 1 || warp == 3) {
-    // ===================================================================== MMA issuers (two warps, alternate tiles)
-    const int mi = warp == 1 ? 0 : 1;
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
-    const uint64_t db = umma_smem_desc(smem_u32(s_w), 512, 4u);
-    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
-    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
-    const uint32_t turn0 = smem_addr_once(&turn_bar[0]);
-    const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 512, 4u);
-    const bool dual = a.dual_mma != 0;
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      if (!dual && mi == 1) break;
-      if (!dual || (it & 1) == mi) {
-        const int as = it % kAS;
-        if (lane == 0) tl_stamp(a, 1, it, 0);
-        mbar_wait_a(acce0 + as * 8, ((it / kAS) & 1) ^ 1u, 3);
-        if (lane == 0) tl_stamp(a, 1, it, 1);
-        mbar_wait_a(full0 + stage * 8, phase, 2);
-        // ping-pong: start issuing only after the other issuer has issued its whole tile, so that this warp's waits
-        // overlap the other's MMAs and the tensor pipe sees one uninterrupted stream (without the token both warps
-        // interleave their MMAs, block on the same queue and then sit in their waits at the same time)
-        if (dual && a.token && it > 0) mbar_wait_a(turn0 + mi * 8, static_cast<uint32_t>(((it - 1) >> 1) & 1), 8);
-        if (lane == 0) tl_stamp(a, 1, it, 2);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-          const uint64_t da = da_base + static_cast<uint64_t>(stage * (kABytes >> 4));
-          umma_bf16(d_tmem, da, db, idesc, 0u);
-          umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
-          umma_commit_a(empty0 + stage * 8);
-          umma_commit_a(accf0 + as * 8);
-          if (dual && a.token) mbar_arrive_a(turn0 + (mi ^ 1) * 8);
-        }
-        __syncwarp();
-        if (lane == 0) tl_stamp(a, 1, it, 3);
-      }
-      if (++stage == kFirstStages) { stage = 0; phase ^= 1u; }
-    }
   } else if (warp >= kFirstConvWarp0) {
     // ===================================================================== converters: fp32 patch -> bf16 im2col rows
     // One warp converts a whole tile (8 rows x 16 columns).  A lane owns one column and four rows, {0,1,4,5} + 2*rg:
@@ -1908,7 +1867,12 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
     const int cw = warp - kFirstConvWarp0;
     const int col = lane & 15, rg = lane >> 4;
     const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
-    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w), 512, 4u);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 512, 4u);
+    static_assert(kConvWarps == kAS, "tile -> converter warp -> accumulator stage -> epilogue group is one chain");
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       if ((it & (kConvWarps - 1)) != cw) continue;
@@ -1952,12 +1916,24 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
           sts128(sa + staged_off(r, 3, 32), make_uint4(pack_bf16x2(v[24], v[25]), pack_bf16x2(v[26], 0.f), 0u, 0u));
         }
       }
-      fence_proxy_async_smem();
+      fence_proxy_async_smem();  // every lane's A rows -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_a(pempty0 + stage * 8);  // patch slot may be refilled
-        mbar_arrive_a(full0 + stage * 8);    // A tile ready for the MMA
+      if (lane == 0) mbar_arrive_a(pempty0 + stage * 8);  // patch slot may be refilled
+      // The converter issues its tile's two MMAs itself (tile -> converter warp -> accumulator stage -> epilogue group
+      // is a fixed 1:1:1:1 chain, it % 4): four issuers instead of two and one hand-off less per tile — the separate
+      // issuer warps' per-tile loop (two barrier waits, issue, two commits) was what capped this kernel.
+      const int as = it % kAS;
+      mbar_wait_a(acce0 + as * 8, static_cast<uint32_t>(((it / kAS) & 1) ^ 1), 3);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint64_t da = da_base + static_cast<uint64_t>(stage * (kABytes >> 4));
+        umma_bf16(d_tmem, da, db, idesc, 0u);
+        umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+        umma_commit_a(empty0 + stage * 8);   // A slot free once the MMAs have read it
+        umma_commit_a(accf0 + as * 8);       // accumulator ready for the epilogue group
       }
+      __syncwarp();
       if (lane == 0) tl_stamp(a, 0, it, 4);
     }
   } else if (warp >= kEpiWarp0) {
