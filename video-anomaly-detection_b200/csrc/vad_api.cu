@@ -165,6 +165,11 @@ static int token_setting() {
   static int v = env_int("VAD_TOKEN", 0);
   return v;
 }
+// VAD_POOL_DIRECT: 1 (default) pooled outputs are stored straight from registers | 0 staged + TMA store
+static int pool_direct_setting() {
+  static int v = env_int("VAD_POOL_DIRECT", 1);
+  return v;
+}
 static int tma_store_setting() {
   static int v = env_int("VAD_TMA_STORE", 1);
   return v;
@@ -841,7 +846,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
                           (cuuint64_t)d->out_frame_stride * 2};
       cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
       a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, 32) == VAD_OK;
-    } else if (aligned && epi == VAD_EPI_POOL && TW >= 2 && TH >= 2) {
+    } else if (aligned && epi == VAD_EPI_POOL && TW >= 2 && TH >= 2 && !pool_direct_setting()) {
       a.out_chunk = (BN % 64 == 0) ? 64 : 32;
       const int Wo = d->W / 2, Ho = d->H / 2;
       cuuint64_t dims[5] = {(cuuint64_t)d->n_total, (cuuint64_t)Wo, (cuuint64_t)Ho, 1, (cuuint64_t)d->B};
@@ -1061,7 +1066,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
     cuuint32_t box[5] = {32, pool ? 8u : 16u, pool ? 4u : 8u, 1, 1};
     const int rc = encode_map5(&a.mapOut, out, dims, st, box, 32);
     if (rc != VAD_OK) return rc;
-    a.tma_store = 1;
+    a.tma_store = (pool && pool_direct_setting()) ? 0 : 1;
   }
   const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
   return launch_conv_first(pool ? VAD_EPI_POOL : VAD_EPI_STORE, a, grid, stream);

@@ -365,8 +365,45 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         ++stg_i;
       }
     } else {
-      // direct stores (fallback for tile shapes the output tensor map cannot express)
+      // direct stores.  POOL: the default path — after the pooling butterfly the 32 lanes of a warp hold 32 different
+      // 16-byte pieces of eight adjacent pooled pixels, i.e. 64-byte (or longer) contiguous runs: fully used sectors
+      // straight from registers, no staging buffer, no group barrier, no proxy fence, no TMA store.  STORE / CONVT: the
+      // fallback for tile shapes the output tensor map cannot express.
       __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+      if constexpr (EPI == VAD_EPI_POOL) {
+        const bool up1 = (ww & 1) != 0, up2 = (hh & 1) != 0;
+        const int part = (up1 ? 2 : 0) + (up2 ? 1 : 0);
+        __nv_bfloat16* dst0 = outp + fb * a.out_fs +
+                              (static_cast<long long>(h >> 1) * (a.W >> 1) + (w >> 1)) * a.out_cp + t.n0 + part * 8;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          load_acc32<BN, KX>(tacc, c * 32, v);
+          if (c * 32 + 32 == BN) release_acc();
+          float g[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lo = __uint_as_float(v[j]), hi = __uint_as_float(v[j + 16]);
+            const float recv = __shfl_xor_sync(0xffffffffu, up1 ? lo : hi, L.mx);
+            g[j] = fmaxf(up1 ? hi : lo, recv);
+          }
+          float m[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float recv = __shfl_xor_sync(0xffffffffu, up2 ? g[j] : g[j + 8], L.my);
+            m[j] = fmaxf(up2 ? g[j + 8] : g[j], recv);
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + t.n0 + c * 32 + part * 8);
+          const float4 b0 = b4[0], b1 = b4[1];
+          if (valid)
+            *reinterpret_cast<uint4*>(dst0 + c * 32) = make_uint4(
+                pack_bf16x2(act_fn(m[0] + b0.x, a.slope), act_fn(m[1] + b0.y, a.slope)),
+                pack_bf16x2(act_fn(m[2] + b0.z, a.slope), act_fn(m[3] + b0.w, a.slope)),
+                pack_bf16x2(act_fn(m[4] + b1.x, a.slope), act_fn(m[5] + b1.y, a.slope)),
+                pack_bf16x2(act_fn(m[6] + b1.z, a.slope), act_fn(m[7] + b1.w, a.slope)));
+        }
+        return;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
