@@ -336,7 +336,7 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": round(byts / (avg_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s"}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01b_dram_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01c_dram_traffic.json")
     if os.path.exists(tpath):  # measured once with ncu --set full at this exact shape (see profiles/)
         traffic = json.load(open(tpath)).get(args.workload, {}).get(top["rep"])
     roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": traffic, "kernel": top_name,
