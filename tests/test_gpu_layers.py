@@ -139,7 +139,11 @@ def test_first_conv(cuda_device, pool, B, H, W):
     _assert_close(out, _nhwc(ref), f"first conv pool={pool}", atol=1e-3)
 
 
-@pytest.mark.parametrize("B,T,H,W", [(2, 3, 8, 8), (3, 2, 6, 10), (1, 5, 24, 40)])
+@pytest.mark.parametrize("B,T,H,W", [(2, 3, 8, 8), (3, 2, 6, 10), (1, 5, 24, 40),
+                                     (1, 1, 8, 8),      # a single step (x half only), odd frame count in a 2-frame tile
+                                     (5, 2, 8, 8),      # 8x8 frames, last tile half empty
+                                     (1, 3, 45, 80),    # the 720p latent: 8x16 tiles, partial last tile row (45 = 32+13)
+                                     (2, 2, 16, 8)])    # narrowest frame the 8x16 tiling accepts
 @pytest.mark.parametrize("persistent", [1, 2, 0])
 def test_convlstm_sequence(cuda_device, B, T, H, W, persistent):
     """ConvLSTM over a short sequence vs the torch formulation of video_autoencoder.py:64-85 (one layer), with the

@@ -150,8 +150,9 @@ static int kx_setting() {
   static int v = env_int("VAD_KX", 1);
   return g_kx_override >= 0 ? g_kx_override : v;
 }
-// VAD_HS: 0 = off | 1 (default) = wide 3x3 layers (Cin >= 128, N multiple of 128) use the patch + streamed-weights kernel
-// | 2 = also Cin = 64
+// VAD_HS: 0 = off | 1 (default) = wide 3x3 layers (N multiple of 128; Cin >= 128, or Cin = 64 without pooling — measured:
+// enc3.0 0.147 -> 0.135 ms, but the pooled 64 -> 128 video layer is faster on the resident-weights kernel) use the
+// patch + streamed-weights kernel | 2 = every Cin = 64 layer too
 static int hs_setting() {
   static int v = env_int("VAD_HS", 1);
   return v;
@@ -728,7 +729,8 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
 
   // ---- patch + streamed-weights kernel for wide 3x3 layers: pairs of 8x16 tiles, N tiles of 128
   bool use_hs = hs_setting() != 0 && d->ntaps == 9 && d->c1 == 0 && d->c0 % 64 == 0 &&
-                d->c0 >= (hs_setting() >= 2 ? 64 : 128) && d->n_total % 128 == 0 && (d->T0 <= 1) && d->H >= 8 &&
+                (d->c0 >= 128 || hs_setting() >= 2 || epi == VAD_EPI_STORE) && d->n_total % 128 == 0 && (d->T0 <= 1) &&
+                d->H >= 8 &&
                 d->W % 16 == 0 && (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL) && hs_patch_stages(epi) >= 2;
   if (use_hs) {
     BN = 128;
