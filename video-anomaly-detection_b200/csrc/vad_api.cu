@@ -784,9 +784,8 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   } else if (use_kx) {
     rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, CK, 8, 18, 1);
   } else if (use_halo) {
-    TileGeom box = g;  // box {CK, PW, PH, 1, 1}: PW/PH need not be powers of two
+    // box {CK, PW, PH, 1, 1}: PW/PH need not be powers of two
     rc = encode_act_map_box(&a.mapA0, d->src0, d->c0, d->W, d->H, 1, d->B, CK, halo_box_w, halo_box_h, 1);
-    (void)box;
   } else {
     rc = encode_act_map(&a.mapA0, d->src0, d->c0, d->W, d->H, d->T0 > 0 ? d->T0 : 1, d->B, CK, g);
   }

@@ -402,8 +402,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
                 pack_bf16x2(act_fn(m[4] + b1.x, a.slope), act_fn(m[5] + b1.y, a.slope)),
                 pack_bf16x2(act_fn(m[6] + b1.z, a.slope), act_fn(m[7] + b1.w, a.slope)));
         }
-        return;
-      }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -413,13 +412,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if constexpr (EPI == VAD_EPI_POOL) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], L.mx));
-            f[j] = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], L.my));
-          }
-        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = act_fn(f[j] + s_bias[col + j], a.slope);
         uint32_t p[16];
@@ -431,19 +423,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
                                                   (static_cast<long long>(h) * a.W + w) * a.out_cp + col);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dst[j] = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
-          }
-        } else if constexpr (EPI == VAD_EPI_POOL) {
-          if (valid) {
-            const int part = (ww & 1) | ((hh & 1) << 1);
-            uint4* dst = reinterpret_cast<uint4*>(
-                outp + fb * a.out_fs + (static_cast<long long>(h >> 1) * (a.W >> 1) + (w >> 1)) * a.out_cp + col +
-                part * 8);
-            uint4 val;
-            if (part == 0) val = make_uint4(p[0], p[1], p[2], p[3]);
-            else if (part == 1) val = make_uint4(p[4], p[5], p[6], p[7]);
-            else if (part == 2) val = make_uint4(p[8], p[9], p[10], p[11]);
-            else val = make_uint4(p[12], p[13], p[14], p[15]);
-            *dst = val;
           }
         } else {  // VAD_EPI_CONVT: column = quad*cout + co, quad = di*2 + dj
           if (valid) {
@@ -457,6 +436,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
           }
         }
       }
+      }  // (STORE / CONVT direct path)
     }
   } else if constexpr (EPI == VAD_EPI_LSTM) {
     // columns of this tile: [gate g in i,f,g,o][32 hidden channels j0..j0+31]; weights/bias pre-permuted on host
