@@ -296,3 +296,26 @@ def test_streaming_scorer_equals_windowed_forward(cuda_device):
         assert torch.equal(out.minmax, ref.minmax)
         assert torch.equal(out.heat, ref.heat)
         assert torch.equal(out.recon, ref.recon)
+
+
+@pytest.mark.parametrize("stress", [False, True])
+def test_unusual_channel_widths_vs_oracle(cuda_device, stress):
+    """Widths that are multiples of 32 but not of 64 / 128 (N tiles of 32, 32-channel K chunks, the CK=32 ConvLSTM
+    sequence kernel, the 1x1 projection) against the CPU oracle."""
+    tol = SCORE_RTOL_STRESS if stress else SCORE_RTOL_INIT
+    m = make_image_model(cuda_device, latent=96, stress=stress)
+    x = image_input(77, 3, 64, 96)
+    with torch.no_grad():
+        ref = vad_oracle.image_reconstruction_error(vad_oracle.cpu_sd(m.state_dict()), x).numpy()
+    got = m.get_reconstruction_error(x.to(cuda_device)).cpu().numpy()
+    print(f"\nimage latent=96 stress={stress}: score rel {rel_err(got, ref):.3g}")
+    assert rel_err(got, ref) <= tol
+    for kw in (dict(latent_dim=96, lstm_hidden_dim=96, lstm_num_layers=2),
+               dict(latent_dim=64, lstm_hidden_dim=160, lstm_num_layers=1)):
+        mv = make_video_model(cuda_device, stress=stress, **kw)
+        xv = video_input(78, 2, 5, 64, 48)
+        with torch.no_grad():
+            refv = vad_oracle.video_reconstruction_error(vad_oracle.cpu_sd(mv.state_dict()), xv, per_frame=True).numpy()
+        gotv = mv.get_reconstruction_error(xv.to(cuda_device), per_frame=True).cpu().numpy()
+        print(f"video {kw} stress={stress}: frame-score rel {rel_err(gotv, refv):.3g}")
+        assert rel_err(gotv, refv) <= tol

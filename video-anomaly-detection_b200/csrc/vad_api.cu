@@ -695,7 +695,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
       return VAD_ERR_ARG;
   }
 
-  if (d->n_total > 512) return VAD_ERR_SHAPE;  // bias slab in shared memory
+  if (d->n_total > 1024) return VAD_ERR_SHAPE;  // bias slab in shared memory (ConvLSTM hidden <= 256, ConvT Cout <= 256)
 
   ensure_trap_slot();
   ConvArgs& a = L.a;

@@ -27,7 +27,8 @@ constexpr int kEpiWarp0 = 4;  // warps 0..3: TMA producer, MMA issuer, TMEM allo
 constexpr int kTileM = 128;
 constexpr int kMaxAccStages = 8;
 constexpr int kStagingBuf = 16384;  // one staged output chunk: 128 rows x 128 B
-constexpr int kMaxBias = 512;
+constexpr int kMaxBias = 512;         // bias slab of the kernels whose whole N fits one or a few tiles
+constexpr int kMaxBiasStream = 1024;  // streaming kernel (ConvT with 4*Cout columns, ConvLSTM gates with 4*hidden columns)
 constexpr int kSmemBudget = 227 * 1024 - 4096;  // dynamic smem we allow ourselves (static smem + slack kept free)
 
 __host__ __device__ constexpr bool epi_uses_staging(int epi) {
@@ -94,7 +95,7 @@ struct Cfg {
   static constexpr int kBBytes = BN * kRowBytes;      // multiple of 1024 for BN >= 16
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = staging_bytes(BN, EPI);
-  static constexpr int kStagesRaw = (kSmemBudget - 1024 - kStagingBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - 1024 - 2048 - kStagingBytes) / kStageBytes;  // (-2048: bias slab)
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024;  // +1024 alignment slack
   static constexpr uint32_t kLayout = (CK == 64) ? 2u : 4u;                        // SWIZZLE_128B : SWIZZLE_64B
@@ -646,7 +647,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvArgs& a, uint32_t tmem_b
 
 template <int BN>
 __device__ __forceinline__ void load_bias_smem(const ConvArgs& a, float* s_bias, int n_total) {
-  for (int i = threadIdx.x; i < n_total && i < kMaxBias; i += blockDim.x) s_bias[i] = a.bias[i];
+  for (int i = threadIdx.x; i < n_total && i < kMaxBiasStream; i += blockDim.x) s_bias[i] = a.bias[i];
 }
 
 // ---------------------------------------------------------------------------------------------------- streaming
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
   __shared__ uint64_t turn_bar[2];  // MMA issuer ping-pong token
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_smem[kMaxAccStages][4][3];
-  __shared__ __align__(16) float s_bias[kMaxBias];
+  __shared__ __align__(16) float s_bias[kMaxBiasStream];
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
