@@ -1744,17 +1744,14 @@ __global__ void __launch_bounds__(384, 1) convlstm_patch_kernel(const __grid_con
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
-      if (leader) {
+      if (leader) {  // publishing h_t is on the critical path of every neighbour: do it before the group barrier
         tma_store_5d(&a.mapOut, stg, j0, tc.w0, tc.h0, t, tc.b0);
         bulk_commit_group();
-        bulk_wait_group_read<0>();
-      }
-      named_bar_sync(1, 256);
-      if (leader) {
-        bulk_wait_group<0>();
+        bulk_wait_group<0>();  // h_t of this tile is in global memory ...
         __threadfence();
-        red_release_gpu_add(step_counter, 1u);
+        red_release_gpu_add(step_counter, 1u);  // ... and published
       }
+      named_bar_sync(1, 256);  // nobody overwrites the staging buffer before the store has read it
     }
     if (valid && a.c_state != nullptr) {
       float* cptr = a.c_state + ((static_cast<long long>(fb) * a.H + h) * a.W + w) * a.cout + j0 + half * 16;
