@@ -1,8 +1,10 @@
 """CPU oracle for the anomaly-scoring hot path.  TEST INFRASTRUCTURE ONLY.
 
 Nothing on the product path may import this module: only ``tests/``,
-``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
-``bench.py`` use it, and there only as the checker / the CPU arm being timed.
+``__graft_entry__.smoke()`` and the baseline legs of ``bench.py`` (``cpu_baseline``,
+``--impl reference``, and the optional ``--gpu-library-baseline``, which times these same
+torch ops in eager mode on the GPU as the library bar) use it, and there only as the
+checker / the reference arm being timed — never as the thing shipped or measured as ours.
 
 What it restates
 ----------------
