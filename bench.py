@@ -252,6 +252,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the scoring path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
+    if world > 1:  # one process per GPU: stage this rank's uploads on the GPU's own socket
+        from runtime.sharding import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -391,7 +395,8 @@ def main():
             "model_tflops": round(frames * gflop_per_frame * 1e9 / (elapsed_ms * 1e-3) / 1e12 / world, 2),
             "roofline": roof, "clocks": clocks,
             "e2e": {"value": round(frames / e2e_s, 1), "unit": "frames/s", "h2d_bytes_per_step": x.numel() * 4,
-                    "d2h_bytes_per_step": B * T * 4, "note": "pinned host -> device copies double-buffered on a side stream"},
+                    "d2h_bytes_per_step": B * T * 4, "note": "pinned host -> device copies double-buffered on a side stream"
+                    + (f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else "")},
             "gpu_launches": int(launches)}
     # extra: the same end-to-end loop fed with the decoder's uint8 HWC frames, normalised on the device
     # (a quarter of the PCIe bytes of the fp32 tensors the reference callers upload)

@@ -1,2 +1,2 @@
 """Host-side runtime helpers around the scoring path (sharding of clips / images over ranks)."""
-from .sharding import ShardPlan, gather_scores, shard_range  # noqa: F401
+from .sharding import ShardPlan, bind_to_gpu_numa_node, gather_scores, shard_range  # noqa: F401

@@ -62,3 +62,30 @@ def gather_scores(local: torch.Tensor, plan: ShardPlan, rank: int, dst: int = 0,
     if rank != dst:
         return None
     return torch.cat([b[:c] for b, c in zip(bufs, plan.counts())], dim=0)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (and so its future pinned-memory allocations and H2D staging) to the CPUs of the NUMA node the
+    GPU hangs off.  One process per GPU uploads its own shard; without the binding half of the ranks of an 8-GPU box
+    stage their uploads through the other socket.  Best effort: returns the node, or None when the topology cannot be
+    read (then nothing is changed)."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
