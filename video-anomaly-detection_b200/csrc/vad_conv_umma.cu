@@ -4,15 +4,23 @@
 //                                        over [B][T][H][W][C] with out-of-bounds zero fill = conv padding)
 //                                     x  B[BN, CK] (bf16, smem via TMA, weights K-major)
 //
-// Two kernels share one epilogue:
-//   conv_umma_kernel  — "streaming": one (A tile, B tile) pair per tap and channel chunk through an mbarrier ring.
-//                       Used for wide layers (tensor-bound), 1-tap GEMMs (ConvT / 1x1) and the ConvLSTM gates.
-//   conv_halo_kernel  — 3x3 conv with Cin in {32, 64} and small N: the nine weight slabs stay resident in smem for
-//                       the whole (persistent) CTA and each tile loads ONE input patch with a 1-pixel halo that all
-//                       nine taps read through shifted shared-memory descriptors — 1.4x instead of 9x operand traffic.
-// Both are persistent and warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/activation/pool/pixel-shuffle/LSTM/score -> swizzled smem
-// -> TMA store).  Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+// Seven kernels share one set of epilogues (section markers below, in file order):
+//   epilogue              — STORE / POOL / CONVT / LSTM / TANH_SCORE / CONVT_TANH_SCORE on one finished accumulator
+//                           tile; EpiLane (per-lane constants), TileIter (division-free tile walking), epilogue_loop.
+//   conv_umma_kernel      — "streaming": one (A tile, B tile) pair per tap and channel chunk through an mbarrier ring.
+//                           1-tap GEMMs (ConvT / 1x1), ConvLSTM steps launched one by one, shapes nothing else takes.
+//   conv_halo_kernel      — 3x3 conv, Cin in {32, 64}: nine weight slabs resident in smem, ONE input patch (1-pixel
+//                           halo) per tile read by all nine taps through shifted shared-memory descriptors.
+//   conv_kx_kernel        — the same with the three horizontal taps folded into N (the 3-channel score layer).
+//   conv_hs_kernel        — wide 3x3 layers: patches for pairs of tiles (M = 256) + streamed weight tiles.
+//   convlstm_seq_kernel   — all T steps of a ConvLSTM layer in one launch (cell state in registers), streamed A tiles.
+//   convlstm_patch_kernel — the same with A patches, a separate weight ring / producer and an 8-warp gate epilogue.
+//   conv_first_kernel     — 3 -> 32 first conv from the fp32 NCHW input: TMA patch -> converter warps (im2col, bf16,
+//                           they also issue the MMAs) -> epilogue.
+// All are persistent and warp-specialised (TMA producer(s), tcgen05.mma issuer(s), TMEM allocator, 1-6 epilogue groups
+// of four warps: TMEM -> registers -> bias/activation/pool/pixel-shuffle/gates/score -> registers or swizzled smem ->
+// global / TMA store); 2-4 accumulator stages in TMEM let epilogues overlap the next tiles' MMAs.  Host-side launchers
+// and the (kernel, tile shape) dispatch tables are at the end of the file; layer -> kernel selection is in vad_api.cu.
 //
 // Replaces (reference file:line): nn.Conv2d 3x3 models/autoencoder.py:39-76,107-137; nn.ConvTranspose2d k2 s2
 // models/autoencoder.py:104-134 and models/video_autoencoder.py:244-259; ConvLSTMCell.forward
