@@ -1528,7 +1528,8 @@ __global__ void __launch_bounds__(256, 1) convlstm_seq_kernel(const __grid_const
 // by a second producer warp that never waits for the recurrence (weights do not depend on it).
 //   geometry 1 (8x8 frames, two frames per tile): patch [y 10][frame 2][x 10], rows ((y*2+f)*8 + x), map dims
 //               {C, W, B, H, T};   geometry 2 (tile 8 wide x 16 tall inside one frame): patch [y 18][x 10].
-constexpr int kLpBRing = 8;
+constexpr int kLpBRing = 8;               // (10 slots + 2 patch slots measured the same: the step is bound by the serial
+                                          //  chain h MMAs -> gates -> store -> publish -> acquire -> patch load, not by the stream)
 constexpr int kLpPatchPitch = 26 * 1024;  // >= 200 rows x 128 B
 constexpr int kLpPatches = 3;
 
