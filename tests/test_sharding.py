@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from runtime.sharding import ShardPlan, gather_scores, shard_range
+from runtime.sharding import ShardPlan, gather_scores, score_clips_sharded, shard_range
 
 
 def test_shard_range_covers_everything_once():
@@ -60,3 +60,37 @@ def test_gather_scores_matches_single_process(tmp_path, world, n_items):
 def test_single_rank_is_identity():
     x = torch.arange(6.0).view(3, 2)
     assert gather_scores(x, ShardPlan(3, 1), 0) is x
+
+
+def _make_clip(clip_id, t=3):
+    g = torch.Generator().manual_seed(1234 + clip_id)  # seed = 1234 + clip_id, independent of the sharding
+    return torch.rand(t, 3, 4, 4, generator=g)
+
+
+def _score_clip(x):
+    return (x * x).mean(dim=(1, 2, 3))
+
+
+def _job_worker(rank, world, n_clips, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = score_clips_sharded(n_clips, _make_clip, _score_clip, rank, world)
+        if rank == 0:
+            torch.save(full, out_path)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_clips", [(2, 9), (3, 2)])
+def test_score_clips_sharded_is_sharding_invariant(tmp_path, world, n_clips):
+    """The config-5 job (per-clip seeds, contiguous shards, one gather) gives bit-identical [n_clips, T] scores for any
+    world size — including a rank with an empty shard."""
+    out = str(tmp_path / "job.pt")
+    port = 31500 + (os.getpid() + world * 11 + n_clips) % 2000
+    mp.spawn(_job_worker, args=(world, n_clips, port, out), nprocs=world, join=True)
+    got = torch.load(out)
+    ref = score_clips_sharded(n_clips, _make_clip, _score_clip, 0, 1)
+    assert got.shape == (n_clips, 3) and torch.equal(got, ref)

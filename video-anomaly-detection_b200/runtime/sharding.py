@@ -64,6 +64,25 @@ def gather_scores(local: torch.Tensor, plan: ShardPlan, rank: int, dst: int = 0,
     return torch.cat([b[:c] for b, c in zip(bufs, plan.counts())], dim=0)
 
 
+def score_clips_sharded(n_clips: int, make_clip, score_clip, rank: int, world: int, dst: int = 0, group=None
+                        ) -> Optional[torch.Tensor]:
+    """The whole config-5 job: rank r scores clips [lo, hi) of `n_clips`, one after another, and the per-frame scores
+    are gathered once at the end.
+
+    `make_clip(clip_id)` returns the clip (for synthetic runs: generated on the rank's device from a seed derived from
+    `clip_id`, so any sharding sees identical data — 10 k 720p clips are 7 TB of fp32 and are never materialised at
+    once); `score_clip(x)` returns its per-frame scores `[T]` (e.g. `model.get_reconstruction_error(x[None],
+    per_frame=True)[0]`).  Returns `[n_clips, T]` on rank `dst` (None elsewhere)."""
+    plan = ShardPlan(n_clips, world)
+    lo, hi = plan.range(rank)
+    rows = [score_clip(make_clip(i)).reshape(1, -1) for i in range(lo, hi)]
+    if rows:
+        local = torch.cat(rows, 0)
+    else:  # an empty shard still takes part in the gather; it needs the row width
+        local = score_clip(make_clip(0)).reshape(1, -1)[:0]
+    return gather_scores(local, plan, rank, dst=dst, group=group)
+
+
 def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
     """Pin this process (and so its future pinned-memory allocations and H2D staging) to the CPUs of the NUMA node the
     GPU hangs off.  One process per GPU uploads its own shard; without the binding half of the ranks of an 8-GPU box
