@@ -171,6 +171,12 @@ static int pool_direct_setting() {
   static int v = env_int("VAD_POOL_DIRECT", 1);
   return v;
 }
+// VAD_PDL_ALL: 1 (default) every conv kernel is launched with programmatic stream serialisation (its prologue overlaps
+// the previous kernel's tail) | 0 plain stream order
+static int pdl_all_setting() {
+  static int v = env_int("VAD_PDL_ALL", 1);
+  return v;
+}
 static int tma_store_setting() {
   static int v = env_int("VAD_TMA_STORE", 1);
   return v;
@@ -873,6 +879,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
 
   a.timeline = g_timeline;
   a.dbg = env_int("VAD_DBG", 0);
+  a.pdl = pdl_all_setting() ? 1 : 0;
   a.dual_mma = (dual_mma_setting() & ((use_halo || use_kx) ? 1 : 4)) != 0;
   a.token = (token_setting() & (use_kx ? 8 : 1)) != 0 || ((use_halo || use_kx) && ((a.halo_stages & 1) || CK == 64));
   L.use_kx = use_kx;
@@ -1039,6 +1046,7 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   a.dbg = env_int("VAD_DBG", 0);
   a.dual_mma = (dual_mma_setting() & 2) != 0;
   a.token = (token_setting() & 2) != 0;
+  a.pdl = pdl_all_setting() ? 1 : 0;
   a.timeline = g_timeline;
   a.out = out;
   a.cout = 32;

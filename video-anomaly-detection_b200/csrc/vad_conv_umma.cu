@@ -873,6 +873,10 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
     tmem_relinquish();
   }
   load_bias_smem<BN>(a, s_bias, BN);
+  if (a.pdl) {  // programmatic dependent launch: everything above touched constants only
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1037,6 +1041,10 @@ __global__ void __launch_bounds__(128 + 128 * kx_groups(BN, EPI), 1) conv_kx_ker
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < BN; i += 128 + 128 * G) s_bias[i] = a.bias[i];
+  if (a.pdl) {  // programmatic dependent launch: everything above touched constants only
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1192,6 +1200,10 @@ __global__ void __launch_bounds__(128 + 256, 1) conv_hs_kernel(const __grid_cons
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < a.n_tiles * BN && i < kMaxBias; i += 384) s_bias[i] = a.bias[i];
+  if (a.pdl) {  // programmatic dependent launch: everything above touched constants only
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1856,6 +1868,10 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   }
   for (int i = threadIdx.x; i < BN; i += kFirstThreads) s_bias[i] = a.bias[i];
   fence_proxy_async_smem();  // s_w is read by the tensor core (async proxy)
+  if (a.pdl) {  // programmatic dependent launch: everything above touched constants only
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1972,6 +1988,30 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   }
 }
 
+// Launch with (a.pdl != 0) or without the programmatic-stream-serialisation attribute.  With it the kernel may start
+// while its predecessor in the stream is still draining; every kernel launched this way runs its prologue (barrier
+// init, TMEM allocation, descriptor prefetch, bias load — constants only) and then `griddepcontrol.wait`s before it
+// touches anything the predecessor wrote.
+template <typename Kernel>
+static int launch_conv_kernel(Kernel kernel, const ConvArgs& a, int grid, int block, int smem, cudaStream_t stream) {
+  count_launch();
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, kernel, a));
+  }
+  kernel<<<grid, block, smem, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <int EPI>
 static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI, kFirstGroupsC);
@@ -1981,9 +2021,7 @@ static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_first_kernel<EPI><<<grid, kFirstThreads, smem, stream>>>(a);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_conv_kernel(conv_first_kernel<EPI>, a, grid, kFirstThreads, smem, stream);
 }
 
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
@@ -2007,23 +2045,7 @@ static int launch_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  if (a.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block_threads(BN, EPI));
-    cfg.dynamicSmemBytes = C::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    count_launch();
-    return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_umma_kernel<CK, BN, EPI>, a));
-  }
-  conv_umma_kernel<CK, BN, EPI><<<grid, block_threads(BN, EPI), C::kSmemBytes, stream>>>(a);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_conv_kernel(conv_umma_kernel<CK, BN, EPI>, a, grid, block_threads(BN, EPI), C::kSmemBytes, stream);
 }
 
 #define VAD_CASE(ck, bn, epi) \
@@ -2068,9 +2090,7 @@ static int launch_halo_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
-  conv_halo_kernel<CK, BN, EPI><<<grid, block_threads(BN), smem, stream>>>(a);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_conv_kernel(conv_halo_kernel<CK, BN, EPI>, a, grid, block_threads(BN), smem, stream);
 }
 
 #define VAD_HALO_CASES(X)              \
@@ -2114,9 +2134,7 @@ static int launch_kx_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
-  conv_kx_kernel<CK, BN, EPI><<<grid, 128 + 128 * kx_groups(BN, EPI), smem, stream>>>(a);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_conv_kernel(conv_kx_kernel<CK, BN, EPI>, a, grid, 128 + 128 * kx_groups(BN, EPI), smem, stream);
 }
 
 #define VAD_KX_CASES(X)                \
@@ -2155,9 +2173,7 @@ static int launch_hs_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
-  conv_hs_kernel<EPI><<<grid, 384, smem, stream>>>(a);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_conv_kernel(conv_hs_kernel<EPI>, a, grid, 384, smem, stream);
 }
 
 // patch ring slots that fit next to the weight ring and the staging buffers
