@@ -146,6 +146,10 @@ def layer_cost(kind, name, B, T, H, W):
         flops = 2.0 * B * h * w * 512 * 9 * (128 + 256 * (T - 1))
         byts = B * h * w * ((128 * 2 * 2 + 128 * 2 + 128 * 4 * 2) * T - 128 * 2 - 128 * 4)
         return flops, byts
+    if name == "decoder.6+9+score":  # fused tail: reads the 64-ch quarter-resolution tensor and x, writes the heat map
+        m = F * (H // 4) * (W // 4)
+        flops = 2.0 * m * (4 * 32 * 64 + 16 * 3 * 32)
+        return flops, m * 64 * 2 + 16 * m * (12 + 4) + F * 12
     cin, cout, div, taps, typ, pooled = img[name]
     h, w = H // div, W // div
     m = F * h * w

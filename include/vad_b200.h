@@ -103,6 +103,16 @@ typedef struct vad_conv_desc {
 } vad_conv_desc;
 
 int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
+/* The last two layers of the video decoder and the error reduction in one kernel (reference
+ * models/video_autoencoder.py:252-259 ConvTranspose2d(64,32,2,2)+BN+ReLU, ConvTranspose2d(32,3,2,2)+Tanh, and
+ * :371-384): a k2s2 transposed convolution has no halo, so input pixel (h,w) alone determines the 4x4 output block
+ * (4h.., 4w..) and the 32-channel intermediate never reaches HBM.  `d` describes the FIRST transposed convolution
+ * (ntaps = 1, c0 = 64, n_total = 128, cout = 32, folded-BN weight / bias, slope) on a [B,H,W,64] bf16 input, plus the
+ * score outputs for the [B,3,4H,4W] model input: x, partials ([vad_convt2_score_tiles(d)][4][4]), optional recon / heat.
+ * weight2: bf16 [16][32], row = (di*2+dj)*3 + co (rows 12..15 zero); bias2: fp32 [16] in the same order.
+ * Other channel widths: VAD_ERR_UNSUPPORTED (callers then run the two layers with vad_conv_layer). */
+int vad_convt2_score(const vad_conv_desc* d, const void* weight2, const float* bias2, vad_stream_t stream);
+int vad_convt2_score_tiles(const vad_conv_desc* d);
 /* One ConvLSTM layer over a whole sequence (reference ConvLSTM.forward time loop, models/video_autoencoder.py:153-167):
  * T launches of the VAD_EPI_LSTM layer with the tensor maps encoded once.  `d` describes a step t >= 1: src0 = input
  * sequence bf16 [B][T][h][w][c0] (T0 = T), src1 = out = hidden sequence bf16 [B][T][h][w][hid] (T1 = T, c1 = hid,

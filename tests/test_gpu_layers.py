@@ -259,6 +259,61 @@ def test_last_convt_tanh_score(cuda_device, B, H, W):
     torch.testing.assert_close(minmax[:, 1], err.amax((1, 2)), rtol=1e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (3, 12, 20), (2, 4, 4), (1, 45, 80), (5, 8, 8)])
+def test_fused_convt_convt_score(cuda_device, B, H, W):
+    """vad_convt2_score (video decoder.6 + decoder.9 + score in one kernel) against torch and against the two layers
+    run one by one: the reconstruction and the heat map must be bit-identical (same bf16 intermediate, same MMAs)."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(31)
+    w1 = torch.randn(64, 32, 2, 2, generator=g) * (2.0 / 64) ** 0.5
+    b1 = torch.randn(32, generator=g) * 0.2
+    w2 = torch.randn(32, 3, 2, 2, generator=g) * (1.0 / 32) ** 0.5
+    b2 = torch.randn(3, generator=g) * 0.1
+    p1 = _dev(prep.pack_convt2x2(w1.double(), b1.double()), dev)
+    p2 = _dev(prep.pack_convt2x2(w2.double(), b2.double(), pad_n_to=16), dev)
+    a = _rand_nhwc(B, H, W, 64, dev, seed=37)
+    Ho, Wo = 4 * H, 4 * W
+    x = (torch.rand(B, 3, Ho, Wo, generator=g) * 2 - 1).to(dev)
+    res = eng._fused_tail(p1, p2, a, B, H, W, x, True, True, Ho, Wo, eng._Buffers())
+    torch.cuda.synchronize()
+    # the two layers one by one
+    mid = torch.empty(B, 2 * H, 2 * W, 32, dtype=torch.bfloat16, device=dev)
+    eng._convt(p1, a, B, H, W, mid, eng.RELU, what="test convt")
+    two = eng._score_layer(p2, mid, B, 2 * H, 2 * W, nat.EPI_CONVT_TANH_SCORE, x, True, True, Ho, Wo, eng._Buffers(),
+                           "test score")
+    torch.cuda.synchronize()
+    assert torch.equal(res.recon, two.recon)
+    assert torch.equal(res.heat, two.heat)
+    assert torch.equal(res.minmax, two.minmax)
+    torch.testing.assert_close(res.score, two.score, rtol=1e-5, atol=1e-8)
+    # torch: bf16-rounded weights, fp32 math, bf16-rounded intermediate
+    m = torch.relu(F.conv_transpose2d(_nchw(a), w1.to(torch.bfloat16).float().to(dev), b1.to(dev), stride=2))
+    m = m.to(torch.bfloat16).float()
+    ref = torch.tanh(F.conv_transpose2d(m, w2.to(torch.bfloat16).float().to(dev), b2.to(dev), stride=2))
+    err = ((x - ref) ** 2).mean(1)
+    _assert_close(res.recon, ref, "recon", rtol=1e-2, atol=2e-2)  # (bf16 rounding flips of the intermediate)
+    assert (res.recon - ref).abs().mean().item() < 1e-3
+    torch.testing.assert_close(res.score, err.mean((1, 2)), rtol=2e-3, atol=1e-6)
+    # outputs only (no recon / heat): same scores
+    res2 = eng._fused_tail(p1, p2, a, B, H, W, x, False, False, Ho, Wo, eng._Buffers())
+    torch.cuda.synchronize()
+    assert res2.recon is None and res2.heat is None
+    assert torch.equal(res2.score, res.score) and torch.equal(res2.minmax, res.minmax)
+
+
+def test_fused_convt_convt_score_rejects_other_widths(cuda_device):
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    p1 = _dev(prep.pack_convt2x2(torch.randn(128, 64, 2, 2, generator=g).double(), torch.zeros(64).double()), dev)
+    p2 = _dev(prep.pack_convt2x2(torch.randn(64, 3, 2, 2, generator=g).double(), torch.zeros(3).double(), pad_n_to=16), dev)
+    a = _rand_nhwc(1, 8, 8, 128, dev, seed=1)
+    x = torch.zeros(1, 3, 32, 32, device=dev)
+    with pytest.raises(RuntimeError):
+        eng._fused_tail(p1, p2, a, 1, 8, 8, x, False, False, 32, 32, eng._Buffers())
+
+
 @pytest.mark.parametrize("N,H,W", [(5, 64, 64), (2, 256, 256), (3, 16, 48)])
 def test_standalone_score_and_heatmap_u8(cuda_device, N, H, W):
     eng, nat, prep = _mods()

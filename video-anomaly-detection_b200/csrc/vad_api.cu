@@ -910,6 +910,60 @@ int vad_conv_layer_tiles(const vad_conv_desc* d) {
   return L.a.total_tiles / L.a.n_tiles;
 }
 
+// ConvT(64->32)+ReLU -> ConvT(32->3)+tanh -> score in one kernel (convt2_score_kernel).  `d` describes the FIRST
+// transposed convolution plus the score outputs; weight2 / bias2 are the second one's [16][32] / [16].
+static int build_convt2_score(const vad_conv_desc* d, const void* weight2, const float* bias2, ConvArgs& a, int& grid) {
+  if (!d || !d->src0 || !d->weight || !d->bias || !weight2 || !bias2 || !d->x || !d->partials) return VAD_ERR_ARG;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0) return VAD_ERR_ARG;
+  if (d->ntaps != 1 || d->c1 != 0) return VAD_ERR_ARG;
+  if (d->c0 != 64 || d->n_total != 128 || d->cout != 32) return VAD_ERR_UNSUPPORTED;
+  if (d->w_ctap != 0 && d->w_ctap != 64) return VAD_ERR_ARG;
+  ensure_trap_slot();
+  std::memset(&a, 0, sizeof(a));
+  const TileGeom g = pick_tile_geometry(d->B, d->H, d->W, true);
+  int rc = encode_act_map(&a.mapA0, d->src0, 64, d->W, d->H, d->T0 > 0 ? d->T0 : 1, d->B, 64, g);
+  if (rc != VAD_OK) return rc;
+  rc = encode_weight_map(&a.mapB, d->weight, 64, 128, 64, 128);
+  if (rc != VAD_OK) return rc;
+  rc = encode_weight_map(&a.mapA1, weight2, 32, 16, 32, 16);  // (mapA1 carries the second layer's weights here)
+  if (rc != VAD_OK) return rc;
+  a.chunks0 = 1;
+  a.ntaps = 1;
+  a.w_ctap = 64;
+  a.pair = 1;
+  a.w_step = a.tw_valid = 1 << g.lgTW;
+  a.tA0 = d->t0;
+  a.B = d->B; a.H = d->H; a.W = d->W;
+  a.lgTW = g.lgTW; a.lgTH = g.lgTH; a.lgTN = g.lgTN;
+  a.tiles_w = g.tiles_w; a.tiles_h = g.tiles_h; a.tiles_b = g.tiles_b;
+  a.n_tiles = 1;
+  a.total_tiles = g.m_tiles();
+  a.bias = d->bias;
+  a.bias2 = bias2;
+  a.slope = d->slope;
+  a.cout = 32;
+  a.x = d->x; a.recon = d->recon; a.heat = d->heat; a.partials = d->partials;
+  a.dbg = env_int("VAD_DBG", 0);
+  a.pdl = pdl_all_setting() ? 1 : 0;
+  grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return VAD_OK;
+}
+
+int vad_convt2_score(const vad_conv_desc* d, const void* weight2, const float* bias2, vad_stream_t stream_) {
+  ConvArgs a;
+  int grid = 0;
+  const int rc = build_convt2_score(d, weight2, bias2, a, grid);
+  if (rc != VAD_OK) return rc;
+  return launch_convt2_score(a, grid, static_cast<cudaStream_t>(stream_));
+}
+
+int vad_convt2_score_tiles(const vad_conv_desc* d) {
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0) return VAD_ERR_ARG;
+  if (d->ntaps != 1 || d->c1 != 0) return VAD_ERR_ARG;
+  if (d->c0 != 64 || d->n_total != 128 || d->cout != 32) return VAD_ERR_UNSUPPORTED;
+  return pick_tile_geometry(d->B, d->H, d->W, true).m_tiles();
+}
+
 int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   // d describes a generic step t >= 1: src0 = layer input sequence [B][T][h][w][c0], src1 = out = hidden sequence
   // [B][T][h][w][hid] (step t reads h_{t-1} from it and writes h_t into it), c_state fp32 [B][h][w][hid].

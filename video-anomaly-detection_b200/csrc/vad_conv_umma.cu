@@ -1988,6 +1988,287 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------- ConvT -> ConvT + tanh + score, fused
+// The last two layers of the video decoder (reference models/video_autoencoder.py:252-259: ConvTranspose2d(64,32,2,2) +
+// BN + ReLU, ConvTranspose2d(32,3,2,2) + Tanh) and the error reduction (:371-384) in ONE kernel.  A k2s2 transposed
+// convolution has no halo: input pixel (h,w) alone determines the 4x4 block of output pixels (4h..4h+3, 4w..4w+3), so the
+// 32-channel full-width intermediate (the largest tensor of the video model: 29.5 MB per 720p frame, written and read
+// back by the layer-by-layer path) never has to exist in HBM.  Per tile of 128 input pixels:
+//   stage 1  D1[128 px][4 taps x 32 ch] = A[128 x 64] · W1^T                     (4 MMAs, N = 128; A by TMA, W1 resident)
+//   ep 1     TMEM -> registers -> +bias, ReLU, bf16 -> smem, one K-major SWIZZLE_64B [128 px][32 ch] operand per tap
+//            (the same swizzled layout the staged TMA stores use — finding 1 of DESIGN.md §4: UMMA reads what TMA writes)
+//   stage 2  D2[tap1][128 px][4 taps x 3 ch -> 16] = A2[tap1][128 x 32] · W2^T   (4 x 2 MMAs, N = 16; into D1's columns)
+//   ep 2     TMEM -> registers -> tanh, (x - recon)^2 against the 4x4 block of the fp32 input (float4 per row and
+//            channel, issued before stage 1 is even waited for), heat map float4 stores, per-tile sum / min / max.
+// Roles: warp 0 TMA producer, warp 1 stage-1 issuer, warp 3 stage-2 issuer, warp 2 TMEM allocator, then kC2Groups
+// epilogue groups of four warps; group g owns TMEM columns [128g, 128g+128), its own A2 buffers, and this CTA's tiles
+// g, g+G, ...  Algorithmic HBM bytes per input pixel: 128 (A) + 192 (x) + 64 (heat) = 384 instead of 1408.
+constexpr int kC2Groups = 3;
+constexpr int kC2Stages = 6;
+constexpr int kC2Threads = 128 + 128 * kC2Groups;
+constexpr int kC2W1Bytes = 128 * 128;     // [4 taps x 32 ch][64 k] bf16, SWIZZLE_128B
+constexpr int kC2W2Bytes = 1024;          // [4 taps x 3 ch -> 16 rows][32 k] bf16, SWIZZLE_64B
+constexpr int kC2ABytes = kTileM * 128;   // one input tile: 128 pixels x 64 channels
+constexpr int kC2TapBytes = kTileM * 64;  // one stage-2 operand: 128 pixels x 32 channels
+constexpr int kC2SmemBytes = 1024 + kC2W1Bytes + kC2W2Bytes + kC2Stages * kC2ABytes + kC2Groups * 4 * kC2TapBytes;
+static_assert(kC2SmemBytes <= kSmemBudget, "convt2_score_kernel shared memory");
+
+__global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int G = kC2Groups;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_bar;
+  __shared__ uint64_t full_bar[kC2Stages];
+  __shared__ uint64_t empty_bar[kC2Stages];
+  __shared__ uint64_t d1_full_bar[G];   // stage-1 accumulator complete                  (MMA commit)
+  __shared__ uint64_t a2_ready_bar[G];  // ep 1 done: A2 written, D1 columns read          (4 warps)
+  __shared__ uint64_t d2_full_bar[G];   // stage-2 accumulators complete                   (MMA commit)
+  __shared__ uint64_t acc_empty_bar[G];  // ep 2 has read D2: the group's columns are free  (4 warps)
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[128 + 16];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w1 = smem;
+  uint8_t* s_w2 = s_w1 + kC2W1Bytes;
+  uint8_t* s_a = s_w2 + kC2W2Bytes;
+  uint8_t* s_a2 = s_a + kC2Stages * kC2ABytes;
+  const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);  // <= 128
+  const uint32_t tx_bytes = static_cast<uint32_t>(rows_valid * 128);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapA1);
+    tma_prefetch_desc(&a.mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < kC2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < G; ++i) {
+      mbar_init(&d1_full_bar[i], 1);
+      mbar_init(&a2_ready_bar[i], 4);
+      mbar_init(&d2_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 128 + 16; i += kC2Threads) s_bias[i] = i < 128 ? a.bias[i] : a.bias2[i - 128];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 0 && elect_one()) {  // both weight matrices, once (constants: may be fetched before the PDL wait)
+    mbar_arrive_expect_tx(&w_bar, kC2W1Bytes + kC2W2Bytes);
+    tma_load_2d(s_w1, &a.mapB, &w_bar, 0, 0);
+    tma_load_2d(s_w2, &a.mapA1, &w_bar, 0, 0);
+  }
+  if (a.pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer: one input tile per tile
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t sa0 = smem_addr_once(s_a);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      const TileCoord t = ti.coord(a, 128);
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(full0 + stage * 8, tx_bytes);
+        tma_load_5d_a(sa0 + stage * kC2ABytes, &a.mapA0, full0 + stage * 8, 0, t.w0, t.h0, a.tA0, t.b0);
+      }
+      __syncwarp();
+      if (++stage == kC2Stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== stage-1 MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 128);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t d1f0 = smem_addr_once(&d1_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 1024, 2u);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w1), 1024, 2u);
+    int stage = 0, g = 0, j = 0;
+    uint32_t phase = 0;
+    mbar_wait(&w_bar, 0, 5);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(acce0 + g * 8, static_cast<uint32_t>(j & 1) ^ 1u, 3);
+      mbar_wait_a(full0 + stage * 8, phase, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = da_base + static_cast<uint64_t>(stage * (kC2ABytes >> 4));
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, kk > 0 ? 1u : 0u);
+        umma_commit_a(empty0 + stage * 8);
+        umma_commit_a(d1f0 + g * 8);
+      }
+      __syncwarp();
+      if (++stage == kC2Stages) { stage = 0; phase ^= 1u; }
+      if (++g == G) { g = 0; ++j; }
+    }
+  } else if (warp == 3) {
+    // ===================================================================== stage-2 MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 16);
+    const uint32_t a2r0 = smem_addr_once(&a2_ready_bar[0]), d2f0 = smem_addr_once(&d2_full_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a2), 512, 4u);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w2), 512, 4u);
+    int g = 0, j = 0;
+    mbar_wait(&w_bar, 0, 5);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(a2r0 + g * 8, static_cast<uint32_t>(j & 1), 6);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+          const uint64_t da = da_base + static_cast<uint64_t>(((g * 4 + tap) * kC2TapBytes) >> 4);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128 + tap * 16);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, kk > 0 ? 1u : 0u);
+        }
+        umma_commit_a(d2f0 + g * 8);
+      }
+      __syncwarp();
+      if (++g == G) { g = 0; ++j; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue groups
+    const int g = (warp - kEpiWarp0) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter == warp_id % 4
+    const int r = q * 32 + lane;
+    const EpiLane L = make_epi_lane(a, q, lane);
+    const uint32_t d1f = smem_addr_once(&d1_full_bar[g]), a2r = smem_addr_once(&a2_ready_bar[g]);
+    const uint32_t d2f = smem_addr_once(&d2_full_bar[g]), acce = smem_addr_once(&acc_empty_bar[g]);
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 128);
+    uint8_t* my_a2 = s_a2 + g * 4 * kC2TapBytes;
+    const int Wo = 4 * a.W;
+    const long long plane = 16LL * a.H * a.W;
+    const float* b2 = s_bias + 128;
+    uint32_t ph = 0;
+    for (TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x); ti.tile < a.total_tiles; ti.next(a), ph ^= 1u) {
+      const TileCoord t = ti.coord(a, 128);
+      const int fb = t.b0 + L.bb, h = t.h0 + L.hh, w = t.w0 + L.ww;
+      const bool valid = L.row_ok && (fb < a.B) && (h < a.H) && (w < a.W);
+      const long long pix0 = static_cast<long long>(4 * h) * Wo + 4 * w;  // first pixel of this lane's 4x4 output block
+      const long long xoff = static_cast<long long>(fb) * 3 * plane + pix0;
+      // the 4x4x3 block of the model input this lane scores against: in flight while both GEMM stages run
+      float4 xr[4][3];
+#pragma unroll
+      for (int ro = 0; ro < 4; ++ro)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          xr[ro][ch] = valid ? __ldg(reinterpret_cast<const float4*>(a.x + xoff + ch * plane + ro * Wo))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+
+      // ---- ep 1: first ConvT's bias + ReLU, bf16, into the stage-2 operands (accumulator row r -> operand row r)
+      mbar_wait_a(d1f, ph, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tap = 0; tap < 4; ++tap) {
+        uint32_t v[32];
+        tmem_ld_x32(tacc + tap * 32, v);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + tap * 32);
+        uint32_t p[16];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 bv = b4[jj];
+          p[2 * jj] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj]) + bv.x, a.slope),
+                                  act_fn(__uint_as_float(v[4 * jj + 1]) + bv.y, a.slope));
+          p[2 * jj + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj + 2]) + bv.z, a.slope),
+                                      act_fn(__uint_as_float(v[4 * jj + 3]) + bv.w, a.slope));
+        }
+        uint8_t* buf = my_a2 + tap * kC2TapBytes;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          sts128(buf + staged_off(r, jj, 32), make_uint4(p[4 * jj], p[4 * jj + 1], p[4 * jj + 2], p[4 * jj + 3]));
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a2r);
+
+      // ---- ep 2: second ConvT's bias + tanh, squared error against x, heat map, per-tile partials
+      mbar_wait_a(d2f, ph, 7);
+      tc_fence_after();
+      float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
+#pragma unroll
+      for (int d1i = 0; d1i < 2; ++d1i) {
+        uint32_t v0[16], v1[16];  // first-layer taps (d1i, 0) and (d1i, 1): output columns 0-1 and 2-3 of rows 2*d1i, +1
+        tmem_ld_x16(tacc + (d1i * 2 + 0) * 16, v0);
+        tmem_ld_x16(tacc + (d1i * 2 + 1) * 16, v1);
+        tmem_ld_wait();
+        if (d1i == 1) {  // the group's TMEM columns are free for the next tile's stage 1
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce);
+        }
+#pragma unroll
+        for (int d2i = 0; d2i < 2; ++d2i) {
+          const int ro = d1i * 2 + d2i;
+          float sq[4] = {0.f, 0.f, 0.f, 0.f};
+          float rec[3][4];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const float xv[4] = {xr[ro][ch].x, xr[ro][ch].y, xr[ro][ch].z, xr[ro][ch].w};
+#pragma unroll
+            for (int cx = 0; cx < 4; ++cx) {
+              const int idx = (d2i * 2 + (cx & 1)) * 3 + ch;
+              const float acc = __uint_as_float((cx >> 1) ? v1[idx] : v0[idx]);
+              rec[ch][cx] = tanh_fn(acc + b2[idx]);
+              const float d = xv[cx] - rec[ch][cx];
+              sq[cx] += d * d;
+            }
+          }
+          if (valid) {
+            const long long rowoff = pix0 + static_cast<long long>(ro) * Wo;
+            if (a.recon) {
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch)
+                *reinterpret_cast<float4*>(a.recon + static_cast<long long>(fb) * 3 * plane + ch * plane + rowoff) =
+                    make_float4(rec[ch][0], rec[ch][1], rec[ch][2], rec[ch][3]);
+            }
+            if (a.heat)
+              *reinterpret_cast<float4*>(a.heat + static_cast<long long>(fb) * plane + rowoff) =
+                  make_float4(sq[0] * (1.f / 3.f), sq[1] * (1.f / 3.f), sq[2] * (1.f / 3.f), sq[3] * (1.f / 3.f));
+            ssum += (sq[0] + sq[1]) + (sq[2] + sq[3]);
+            smin = fminf(smin, fminf(fminf(sq[0], sq[1]), fminf(sq[2], sq[3])));
+            smax = fmaxf(smax, fmaxf(fmaxf(sq[0], sq[1]), fmaxf(sq[2], sq[3])));
+          }
+        }
+      }
+      // fixed-order reduction (deterministic), as in the layer-by-layer score epilogue
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+      }
+      if (lane == 0)
+        *reinterpret_cast<float4*>(a.partials + (static_cast<long long>(t.m_tile) * 4 + q) * 4) =
+            make_float4(ssum, smin * (1.f / 3.f), smax * (1.f / 3.f), 0.f);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Launch with (a.pdl != 0) or without the programmatic-stream-serialisation attribute.  With it the kernel may start
 // while its predecessor in the stream is still draining; every kernel launched this way runs its prologue (barrier
 // init, TMEM allocation, descriptor prefetch, bias load — constants only) and then `griddepcontrol.wait`s before it
@@ -2022,6 +2303,16 @@ static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
     configured = true;
   }
   return launch_conv_kernel(conv_first_kernel<EPI>, a, grid, kFirstThreads, smem, stream);
+}
+
+int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convt2_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  return launch_conv_kernel(convt2_score_kernel, a, grid, kC2Threads, kC2SmemBytes, stream);
 }
 
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {

@@ -120,7 +120,28 @@ def _score_layer(w: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int,
     return ScoreOutputs(score, minmax, heat, recon)
 
 
+def _fused_tail(w6: GemmWeights, w9: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int, x: torch.Tensor,
+                want_recon: bool, want_heat: bool, Ho: int, Wo: int, bufs: "_Buffers") -> "ScoreOutputs":
+    """Video decoder.6 (ConvT 64->32 + BN + ReLU) + decoder.9 (ConvT 32->3 + Tanh) + scoring: `vad_convt2_score`."""
+    dev = x.device
+    recon = torch.empty(frames, 3, Ho, Wo, dtype=torch.float32, device=dev) if want_recon else None
+    heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
+    d = _gemm_desc(w6, src, frames, H, W, nat.EPI_CONVT, RELU, None, x=x, recon=recon, heat=heat, partials=x)
+    tiles = nat.load().vad_convt2_score_tiles(C.byref(d))
+    if tiles <= 0:
+        nat.check(tiles if tiles < 0 else -1, "vad_convt2_score_tiles")
+    partials = bufs.get("partials", (tiles, 4, 4), torch.float32, dev)
+    d.partials = partials.data_ptr()
+    _timed("decoder.6+9+score", lambda: nat.check(
+        nat.load().vad_convt2_score(C.byref(d), w9.w.data_ptr(), w9.bias.data_ptr(), nat.stream_ptr()),
+        "vad_convt2_score"))
+    score, minmax = _finalize(partials, frames, 4 * (tiles // frames), Ho, Wo, bufs, dev)
+    return ScoreOutputs(score, minmax, heat, recon)
+
+
 FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
+# VAD_FUSE_DEC=0: run the video decoder's last two layers one by one (vad_conv_layer) instead of vad_convt2_score
+FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 
 
 def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
@@ -272,10 +293,10 @@ class VideoEngine:
         _conv(wt, seq, F, h, w, out, IDENT, what="proj")
         return out
 
-    def decode_to(self, z: torch.Tensor, F: int, h: int, w: int) -> Tuple[torch.Tensor, int, int]:
-        """bf16 NHWC [F,h,w,latent] -> input of the last ConvT, bf16 NHWC [F,8h,8w,32]."""
+    def decode_to(self, z: torch.Tensor, F: int, h: int, w: int, layers=(0, 3, 6)) -> Tuple[torch.Tensor, int, int]:
+        """bf16 NHWC [F,h,w,latent] -> input of the last ConvT, bf16 NHWC [F,8h,8w,32] (or of an earlier one)."""
         cur = z
-        for i in (0, 3, 6):
+        for i in layers:
             wt: GemmWeights = self.p[f"dec.{i}"]
             up = self.bufs.get(f"d{i}", (F, 2 * h, 2 * w, wt.cout), torch.bfloat16, z.device)
             _convt(wt, cur, F, h, w, up, RELU, what=f"decoder.{i}")
@@ -291,6 +312,18 @@ class VideoEngine:
         z, h, w = self.encode(x4)
         seq = self.convlstm(z.view(B, T, h, w, z.shape[-1]), B, T, h, w)
         zp = self.project(seq.view(F, h, w, seq.shape[-1]), F, h, w)
+        return self.decode_and_score(zp, F, h, w, x4, want_recon, want_heat)
+
+    def decode_and_score(self, zp: torch.Tensor, F: int, h: int, w: int, x4: torch.Tensor, want_recon: bool,
+                         want_heat: bool) -> ScoreOutputs:
+        """Decoder + fused scoring of F frames: zp bf16 NHWC [F,h,w,latent], x4 fp32 [F,3,16h,16w]."""
+        H, W = x4.shape[-2], x4.shape[-1]
+        w6: GemmWeights = self.p["dec.6"]
+        w9: GemmWeights = self.p["dec.9"]
+        if FUSE_DEC_TAIL and (w6.ctap, w6.n_total, w6.cout, w9.ctap, w9.n_total) == (64, 128, 32, 32, 16):
+            # decoder.6 + decoder.9 + score in one kernel: the 32-channel half-resolution tensor never reaches HBM
+            d, hd, wd = self.decode_to(zp, F, h, w, layers=(0, 3))
+            return _fused_tail(w6, w9, d, F, hd, wd, x4, want_recon, want_heat, H, W, self.bufs)
         d, hd, wd = self.decode_to(zp, F, h, w)
-        return _score_layer(self.p["dec.9"], d, F, hd, wd, nat.EPI_CONVT_TANH_SCORE, x4, want_recon, want_heat, H, W,
+        return _score_layer(w9, d, F, hd, wd, nat.EPI_CONVT_TANH_SCORE, x4, want_recon, want_heat, H, W,
                             self.bufs, "decoder.9+score")

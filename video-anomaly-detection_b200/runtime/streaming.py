@@ -64,6 +64,4 @@ class StreamingVideoScorer:
         H, W = x4.shape[-2:]
         seq = engine.convlstm(lat.view(1, T, h, w, lat.shape[-1]), 1, T, h, w)
         zp = engine.project(seq.view(T, h, w, seq.shape[-1]), T, h, w)
-        d, hd, wd = engine.decode_to(zp, T, h, w)
-        return eng._score_layer(engine.p["dec.9"], d, T, hd, wd, nat.EPI_CONVT_TANH_SCORE, x4, self.want_recon,
-                                self.want_heat, H, W, engine.bufs, "decoder.9+score")
+        return engine.decode_and_score(zp, T, h, w, x4, self.want_recon, self.want_heat)
