@@ -150,6 +150,10 @@ def layer_cost(kind, name, B, T, H, W):
         m = F * (H // 4) * (W // 4)
         flops = 2.0 * m * (4 * 32 * 64 + 16 * 3 * 32)
         return flops, m * 64 * 2 + 16 * m * (12 + 4) + F * 12
+    if name == "dec4.0+4.3+score":  # fused tail: reads the 32-ch half-resolution tensor and x, writes the heat map
+        m = F * (H // 2) * (W // 2)
+        flops = 2.0 * m * (4 * 32 * 32 + 4 * 3 * 9 * 32)
+        return flops, m * 32 * 2 + 4 * m * (12 + 4) + F * 12
     cin, cout, div, taps, typ, pooled = img[name]
     h, w = H // div, W // div
     m = F * h * w

@@ -113,6 +113,15 @@ int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
  * Other channel widths: VAD_ERR_UNSUPPORTED (callers then run the two layers with vad_conv_layer). */
 int vad_convt2_score(const vad_conv_desc* d, const void* weight2, const float* bias2, vad_stream_t stream);
 int vad_convt2_score_tiles(const vad_conv_desc* d);
+/* The last block of the image decoder and the error reduction in one kernel (reference models/autoencoder.py:131-138
+ * ConvTranspose2d(32,32,2,2)+BN+ReLU, Conv2d(32,3,3,padding=1)+Tanh, and :214-221): the transposed convolution is
+ * recomputed per tile with a one-pixel halo and its 32-channel full-resolution output stays in shared memory.
+ * `d` describes the transposed convolution (ntaps = 1, c0 = 32, n_total = 128, cout = 32) on a [B,H,W,32] bf16 input
+ * plus the score outputs for the [B,3,2H,2W] model input: x, partials ([vad_convt_conv_score_tiles(d)][4][4]),
+ * optional recon / heat.  weight2_kx: the 3x3 conv's kx-folded layout (see vad_conv_desc.weight_kx) bf16 [16][96];
+ * bias2: fp32 [16] (3 real entries).  Other channel widths: VAD_ERR_UNSUPPORTED. */
+int vad_convt_conv_score(const vad_conv_desc* d, const void* weight2_kx, const float* bias2, vad_stream_t stream);
+int vad_convt_conv_score_tiles(const vad_conv_desc* d);
 /* One ConvLSTM layer over a whole sequence (reference ConvLSTM.forward time loop, models/video_autoencoder.py:153-167):
  * T launches of the VAD_EPI_LSTM layer with the tensor maps encoded once.  `d` describes a step t >= 1: src0 = input
  * sequence bf16 [B][T][h][w][c0] (T0 = T), src1 = out = hidden sequence bf16 [B][T][h][w][hid] (T1 = T, c1 = hid,

@@ -302,6 +302,50 @@ def test_fused_convt_convt_score(cuda_device, B, H, W):
     assert torch.equal(res2.score, res.score) and torch.equal(res2.minmax, res.minmax)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (3, 24, 40), (1, 8, 8), (2, 128, 128), (1, 7, 15), (2, 21, 45)])
+def test_fused_convt_conv_score(cuda_device, B, H, W):
+    """vad_convt_conv_score (image dec4.0 + dec4.3 + score in one kernel, transposed conv recomputed per tile with a
+    halo) against the two layers run one by one: reconstruction and heat map bit-identical (same bf16 intermediate, same
+    MMA sequence per output pixel), and against torch."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(41)
+    w1 = torch.randn(32, 32, 2, 2, generator=g) * (2.0 / 32) ** 0.5
+    b1 = torch.randn(32, generator=g) * 0.2
+    w2 = torch.randn(3, 32, 3, 3, generator=g) * (1.0 / 288) ** 0.5
+    b2 = torch.randn(3, generator=g) * 0.1
+    p1 = _dev(prep.pack_convt2x2(w1.double(), b1.double()), dev)
+    p2 = _dev(prep.pack_conv3x3(w2.double(), b2.double(), pad_n_to=16), dev)
+    a = _rand_nhwc(B, H, W, 32, dev, seed=43)
+    Ho, Wo = 2 * H, 2 * W
+    x = (torch.rand(B, 3, Ho, Wo, generator=g) * 2 - 1).to(dev)
+    res = eng._fused_image_tail(p1, p2, a, B, H, W, x, True, True, eng._Buffers())
+    torch.cuda.synchronize()
+    m = torch.relu(F.conv_transpose2d(_nchw(a), w1.to(torch.bfloat16).float().to(dev), b1.to(dev), stride=2))
+    m = m.to(torch.bfloat16).float()
+    ref = torch.tanh(F.conv2d(m, w2.to(torch.bfloat16).float().to(dev), b2.to(dev), padding=1))
+    err = ((x - ref) ** 2).mean(1)
+    _assert_close(res.recon, ref, "recon", rtol=1e-2, atol=2e-2)  # (bf16 rounding flips of the intermediate)
+    assert (res.recon - ref).abs().mean().item() < 1e-3
+    torch.testing.assert_close(res.score, err.mean((1, 2)), rtol=2e-3, atol=1e-6)
+    torch.testing.assert_close(res.heat.mean((1, 2)), res.score, rtol=1e-5, atol=0)
+    assert torch.equal(res.minmax[:, 0], res.heat.amin((1, 2))) and torch.equal(res.minmax[:, 1], res.heat.amax((1, 2)))
+    if H >= 16 and W >= 16 and H % 8 == 0 and W % 8 == 0:  # shapes the layer-by-layer kernels take
+        mid = torch.empty(B, Ho, Wo, 32, dtype=torch.bfloat16, device=dev)
+        eng._convt(p1, a, B, H, W, mid, eng.RELU, what="test convt")
+        two = eng._score_layer(p2, mid, B, Ho, Wo, nat.EPI_TANH_SCORE, x, True, True, Ho, Wo, eng._Buffers(),
+                               "test score")
+        torch.cuda.synchronize()
+        assert torch.equal(res.recon, two.recon)
+        assert torch.equal(res.heat, two.heat)
+        assert torch.equal(res.minmax, two.minmax)
+        torch.testing.assert_close(res.score, two.score, rtol=1e-5, atol=1e-8)
+    res2 = eng._fused_image_tail(p1, p2, a, B, H, W, x, False, False, eng._Buffers())
+    torch.cuda.synchronize()
+    assert res2.recon is None and res2.heat is None
+    assert torch.equal(res2.score, res.score) and torch.equal(res2.minmax, res.minmax)
+
+
 def test_fused_convt_convt_score_rejects_other_widths(cuda_device):
     eng, nat, prep = _mods()
     dev = cuda_device

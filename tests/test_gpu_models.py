@@ -222,6 +222,28 @@ def test_video_fused_decoder_tail_equals_layerwise(cuda_device, shape):
     torch.testing.assert_close(a_score, b.score, rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("shape", [(3, 64, 64), (2, 256, 256), (2, 48, 80)])
+def test_image_fused_decoder_tail_equals_layerwise(cuda_device, shape):
+    """The fused dec4.0 + dec4.3 + score kernel (default) and the layer-by-layer schedule (VAD_FUSE_DEC=0) produce the
+    same reconstruction and heat map bit for bit; scores differ only by the summation order."""
+    from models import _engine as eng
+    m = make_image_model(cuda_device, stress=True)
+    g = torch.Generator().manual_seed(77)
+    x = (torch.rand(shape[0], 3, shape[1], shape[2], generator=g) * 2 - 1).to(cuda_device)
+    assert eng.FUSE_DEC_TAIL
+    a = m.score_all(x, want_recon=True, want_heat=True)
+    a_score, a_heat, a_recon, a_mm = a.score.clone(), a.heat.clone(), a.recon.clone(), a.minmax.clone()
+    eng.FUSE_DEC_TAIL = False
+    try:
+        b = m.score_all(x, want_recon=True, want_heat=True)
+    finally:
+        eng.FUSE_DEC_TAIL = True
+    assert torch.equal(a_recon, b.recon)
+    assert torch.equal(a_heat, b.heat)
+    assert torch.equal(a_mm, b.minmax)
+    torch.testing.assert_close(a_score, b.score, rtol=1e-5, atol=0)
+
+
 def test_full_size_properties_cfg2(cuda_device):
     """BASELINE cfg2 (batch 256 of 256x256): determinism, batch-partition invariance, map/score consistency."""
     m = make_image_model(cuda_device, stress=True)

@@ -964,6 +964,67 @@ int vad_convt2_score_tiles(const vad_conv_desc* d) {
   return pick_tile_geometry(d->B, d->H, d->W, true).m_tiles();
 }
 
+// ConvT(32->32)+ReLU -> Conv3x3(32->3)+tanh -> score in one kernel (convt_conv_score_kernel).  `d` describes the
+// transposed convolution plus the score outputs; weight2_kx / bias2 are the 3x3 conv's kx-folded [16][96] / [16].
+static bool convt_conv_score_shape_ok(const vad_conv_desc* d) {
+  return d->c0 == 32 && d->n_total == 128 && d->cout == 32;
+}
+static void convt_conv_score_tiles(const vad_conv_desc* d, int& tiles_w, int& tiles_h) {
+  tiles_h = (2 * d->H + 1 + 13) / 14;  // tile th scores output rows [14*th - 1, 14*th + 13)
+  tiles_w = (2 * d->W + 1 + 29) / 30;  // tile tw scores output columns [30*tw - 1, 30*tw + 29)
+}
+static int build_convt_conv_score(const vad_conv_desc* d, const void* weight2_kx, const float* bias2, ConvArgs& a,
+                                  int& grid) {
+  if (!d || !d->src0 || !d->weight || !d->bias || !weight2_kx || !bias2 || !d->x || !d->partials) return VAD_ERR_ARG;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0) return VAD_ERR_ARG;
+  if (d->ntaps != 1 || d->c1 != 0 || d->T0 > 1) return VAD_ERR_ARG;
+  if (!convt_conv_score_shape_ok(d)) return VAD_ERR_UNSUPPORTED;
+  if (d->w_ctap != 0 && d->w_ctap != 32) return VAD_ERR_ARG;
+  ensure_trap_slot();
+  std::memset(&a, 0, sizeof(a));
+  int rc = encode_act_map_box(&a.mapA0, d->src0, 32, d->W, d->H, 1, d->B, 32, 16, 8, 1);
+  if (rc != VAD_OK) return rc;
+  rc = encode_weight_map(&a.mapB, d->weight, 32, 128, 32, 128);
+  if (rc != VAD_OK) return rc;
+  rc = encode_weight_map(&a.mapA1, weight2_kx, 96, 16, 32, 16);  // (mapA1 carries the 3x3 conv's weights here)
+  if (rc != VAD_OK) return rc;
+  a.chunks0 = 1;
+  a.ntaps = 1;
+  a.w_ctap = 32;
+  a.pair = 1;
+  a.B = d->B; a.H = d->H; a.W = d->W;
+  convt_conv_score_tiles(d, a.tiles_w, a.tiles_h);
+  a.tiles_b = d->B;
+  a.n_tiles = 1;
+  a.total_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
+  a.bias = d->bias;
+  a.bias2 = bias2;
+  a.slope = d->slope;
+  a.cout = 32;
+  a.x = d->x; a.recon = d->recon; a.heat = d->heat; a.partials = d->partials;
+  a.dbg = env_int("VAD_DBG", 0);
+  a.pdl = pdl_all_setting() ? 1 : 0;
+  grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return VAD_OK;
+}
+
+int vad_convt_conv_score(const vad_conv_desc* d, const void* weight2_kx, const float* bias2, vad_stream_t stream_) {
+  ConvArgs a;
+  int grid = 0;
+  const int rc = build_convt_conv_score(d, weight2_kx, bias2, a, grid);
+  if (rc != VAD_OK) return rc;
+  return launch_convt_conv_score(a, grid, static_cast<cudaStream_t>(stream_));
+}
+
+int vad_convt_conv_score_tiles(const vad_conv_desc* d) {
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0) return VAD_ERR_ARG;
+  if (d->ntaps != 1 || d->c1 != 0) return VAD_ERR_ARG;
+  if (!convt_conv_score_shape_ok(d)) return VAD_ERR_UNSUPPORTED;
+  int tw, th;
+  convt_conv_score_tiles(d, tw, th);
+  return tw * th * d->B;
+}
+
 int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   // d describes a generic step t >= 1: src0 = layer input sequence [B][T][h][w][c0], src1 = out = hidden sequence
   // [B][T][h][w][hid] (step t reads h_{t-1} from it and writes h_t into it), c_state fp32 [B][h][w][hid].

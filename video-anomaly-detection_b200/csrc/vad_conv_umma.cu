@@ -2152,6 +2152,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
     const uint32_t d2f = smem_addr_once(&d2_full_bar[g]), acce = smem_addr_once(&acc_empty_bar[g]);
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 128);
     uint8_t* my_a2 = s_a2 + g * 4 * kC2TapBytes;
+    const bool relu = a.slope == 0.f;  // (the model's case: ReLU folded into the bf16 conversion)
     const int Wo = 4 * a.W;
     const long long plane = 16LL * a.H * a.W;
     const float* b2 = s_bias + 128;
@@ -2181,13 +2182,22 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
         tmem_ld_wait();
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + tap * 32);
         uint32_t p[16];
+        if (relu) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float4 bv = b4[jj];
-          p[2 * jj] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj]) + bv.x, a.slope),
-                                  act_fn(__uint_as_float(v[4 * jj + 1]) + bv.y, a.slope));
-          p[2 * jj + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj + 2]) + bv.z, a.slope),
-                                      act_fn(__uint_as_float(v[4 * jj + 3]) + bv.w, a.slope));
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 bv = b4[jj];
+            p[2 * jj] = pack_bf16x2_relu(__uint_as_float(v[4 * jj]) + bv.x, __uint_as_float(v[4 * jj + 1]) + bv.y);
+            p[2 * jj + 1] = pack_bf16x2_relu(__uint_as_float(v[4 * jj + 2]) + bv.z, __uint_as_float(v[4 * jj + 3]) + bv.w);
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 bv = b4[jj];
+            p[2 * jj] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj]) + bv.x, a.slope),
+                                    act_fn(__uint_as_float(v[4 * jj + 1]) + bv.y, a.slope));
+            p[2 * jj + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj + 2]) + bv.z, a.slope),
+                                        act_fn(__uint_as_float(v[4 * jj + 3]) + bv.w, a.slope));
+          }
         }
         uint8_t* buf = my_a2 + tap * kC2TapBytes;
 #pragma unroll
@@ -2269,6 +2279,306 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------------- ConvT -> conv3x3 + tanh + score, fused
+// The last block of the image decoder (reference models/autoencoder.py:131-138: ConvTranspose2d(32,32,2,2) + BN + ReLU,
+// Conv2d(32,3,3,padding=1) + Tanh) and the error reduction (:214-221) in ONE kernel: the 32-channel full-resolution
+// intermediate (1.07 GB at batch 256, written by dec4.0 and read back by dec4.3) stays in shared memory.
+// Per tile: an 8 x 16 block of input pixels (TMA, origin (7*th - 1, 15*tw - 1), zero fill outside) ->
+//   stage 1  D1[128 px][4 taps x 32 ch] = A[128 x 32] · W1^T                      (2 MMAs, N = 128)
+//   ep 1     bias + ReLU, bf16 -> a 16 x 32 pixel PATCH of the intermediate in smem (pixel p = y*32 + x at p*64 B with
+//            the SWIZZLE_64B pattern on absolute address bits; pixels outside the image are written as zeros = the
+//            3x3 conv's padding)
+//   stage 2  five 16 x 8 sub-tiles at patch columns 6s: D2[s][q][kx*3 + co] = sum_ky A(patch + (ky*32 + 6s) px,
+//            row pitch 32 px) · W2[ky]^T — the kx-folded form of conv_kx_kernel (3 x 2 MMAs each, N = 16), into D1's columns
+//   ep 2     out[y][x] = D2[x-1][kx=0] + D2[x][1] + D2[x+1][2] (two lane shuffles), tanh, (x - recon)^2, heat, partials.
+// Valid outputs of a tile: patch rows 1..14 x columns 1..30 = output rows [14*th - 1, 14*th + 13), columns
+// [30*tw - 1, 30*tw + 29) — tiles overlap by one input pixel, 75-80 % of stage 1 and 66 % of stage 2 is useful work,
+// which is cheap next to the 2.1 GB of HBM traffic saved per batch.
+constexpr int kI2Groups = 4;
+constexpr int kI2Stages = 8;
+constexpr int kI2Threads = 128 + 128 * kI2Groups;
+constexpr int kI2W1Bytes = 128 * 64;          // [4 taps x 32 ch][32 k] bf16, SWIZZLE_64B
+constexpr int kI2W2Bytes = 3 * 1024;          // three [16][32] slabs (ky), SWIZZLE_64B
+constexpr int kI2ABytes = kTileM * 64;        // one input tile: 8 x 16 pixels x 32 channels
+constexpr int kI2PatchBytes = 18 * 32 * 64;   // 16 patch rows + 2 rows only ever read into discarded accumulator rows
+constexpr int kI2SmemBytes = 1024 + kI2W1Bytes + kI2W2Bytes + kI2Stages * kI2ABytes + kI2Groups * kI2PatchBytes;
+static_assert(kI2SmemBytes <= kSmemBudget, "convt_conv_score_kernel shared memory");
+static_assert((kI2W1Bytes + kI2W2Bytes) % 1024 == 0 && kI2PatchBytes % 1024 == 0, "1024-byte aligned operands");
+
+__global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int G = kI2Groups;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_bar;
+  __shared__ uint64_t full_bar[kI2Stages];
+  __shared__ uint64_t empty_bar[kI2Stages];
+  __shared__ uint64_t d1_full_bar[G];
+  __shared__ uint64_t a2_ready_bar[G];
+  __shared__ uint64_t d2_full_bar[G];
+  __shared__ uint64_t acc_empty_bar[G];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[128 + 16];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w1 = smem;
+  uint8_t* s_w2 = s_w1 + kI2W1Bytes;
+  uint8_t* s_a = s_w2 + kI2W2Bytes;
+  uint8_t* s_p = s_a + kI2Stages * kI2ABytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapA1);
+    tma_prefetch_desc(&a.mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < kI2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < G; ++i) {
+      mbar_init(&d1_full_bar[i], 1);
+      mbar_init(&a2_ready_bar[i], 4);
+      mbar_init(&d2_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 128 + 16; i += kI2Threads) s_bias[i] = i < 128 ? a.bias[i] : a.bias2[i - 128];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 0 && elect_one()) {  // weights, once (constants: may be fetched before the PDL wait)
+    mbar_arrive_expect_tx(&w_bar, kI2W1Bytes + kI2W2Bytes);
+    tma_load_2d(s_w1, &a.mapB, &w_bar, 0, 0);
+    for (int ky = 0; ky < 3; ++ky) tma_load_2d(s_w2 + ky * 1024, &a.mapA1, &w_bar, ky * 32, 0);
+  }
+  if (a.pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer: one 8 x 16 input block per tile
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t sa0 = smem_addr_once(s_a);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(full0 + stage * 8, kI2ABytes);
+        tma_load_5d_a(sa0 + stage * kI2ABytes, &a.mapA0, full0 + stage * 8, 0, 15 * ti.tw - 1, 7 * ti.th - 1, 0, ti.tb);
+      }
+      __syncwarp();
+      if (++stage == kI2Stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== stage-1 MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 128);
+    const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t d1f0 = smem_addr_once(&d1_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 512, 4u);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w1), 512, 4u);
+    int stage = 0, g = 0, j = 0;
+    uint32_t phase = 0;
+    mbar_wait(&w_bar, 0, 5);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(acce0 + g * 8, static_cast<uint32_t>(j & 1) ^ 1u, 3);
+      mbar_wait_a(full0 + stage * 8, phase, 2);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = da_base + static_cast<uint64_t>(stage * (kI2ABytes >> 4));
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, kk > 0 ? 1u : 0u);
+        umma_commit_a(empty0 + stage * 8);
+        umma_commit_a(d1f0 + g * 8);
+      }
+      __syncwarp();
+      if (++stage == kI2Stages) { stage = 0; phase ^= 1u; }
+      if (++g == G) { g = 0; ++j; }
+    }
+  } else if (warp == 3) {
+    // ===================================================================== stage-2 MMA issuer (kx-folded 3x3 conv)
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 16);
+    const uint32_t a2r0 = smem_addr_once(&a2_ready_bar[0]), d2f0 = smem_addr_once(&d2_full_bar[0]);
+    const uint64_t da_hi = umma_smem_desc(0, 32 * 64, 4u);  // 8-row groups = patch rows, 32 pixels (2048 B) apart
+    const uint64_t db0 = umma_smem_desc(smem_u32(s_w2), 512, 4u);
+    const uint32_t sp16 = (smem_u32(s_p) & 0x3FFFF) >> 4;
+    int g = 0, j = 0;
+    mbar_wait(&w_bar, 0, 5);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(a2r0 + g * 8, static_cast<uint32_t>(j & 1), 6);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p16 = sp16 + static_cast<uint32_t>(g * (kI2PatchBytes >> 4));
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128 + s * 16);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint64_t da = da_hi | static_cast<uint64_t>(p16 + (((ky * 32 + 6 * s) * 64) >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>((ky * 1024) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              if ((a.dbg & 16) && (ky > 0 || kk > 0)) continue;  // ablation: one MMA per sub-tile
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (ky > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit_a(d2f0 + g * 8);
+      }
+      __syncwarp();
+      if (++g == G) { g = 0; ++j; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue groups
+    const int g = (warp - kEpiWarp0) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter == warp_id % 4
+    const int r = q * 32 + lane;
+    const uint32_t d1f = smem_addr_once(&d1_full_bar[g]), a2r = smem_addr_once(&a2_ready_bar[g]);
+    const uint32_t d2f = smem_addr_once(&d2_full_bar[g]), acce = smem_addr_once(&acc_empty_bar[g]);
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 128);
+    uint8_t* patch = s_p + g * kI2PatchBytes;
+    const int Ho = 2 * a.H, Wo = 2 * a.W;
+    const long long plane = static_cast<long long>(Ho) * Wo;
+    const float* b2 = s_bias + 128;
+    const bool relu = a.slope == 0.f;     // (the model's case: ReLU folded into the bf16 conversion)
+    const int iy = r >> 4, ix = r & 15;   // ep 1: this accumulator row's input pixel inside the 8 x 16 block
+    const int srow = r >> 3, scol = r & 7;  // ep 2: this accumulator row's pixel inside a 16 x 8 sub-tile
+    uint32_t ph = 0;
+    for (TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x); ti.tile < a.total_tiles; ti.next(a), ph ^= 1u) {
+      const int oy0 = 14 * ti.th - 2, ox0 = 30 * ti.tw - 2;  // output coordinates of patch pixel (0, 0)
+      const int fb = ti.tb;
+      const int m_tile = (ti.tb * a.tiles_h + ti.th) * a.tiles_w + ti.tw;
+      // the model-input pixels this lane scores in the five sub-tiles (in flight while both GEMM stages run)
+      const int oy = oy0 + 1 + srow;
+      const bool row_ok = scol < 6 && srow < 14 && oy >= 0 && oy < Ho;
+      const long long xrow = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(oy) * Wo;
+      float xs[5][3];
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const int ox = ox0 + 1 + 6 * s + scol;
+        const bool ok = row_ok && ox >= 0 && ox < Wo;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) xs[s][ch] = (ok && !(a.dbg & 128)) ? __ldg(a.x + xrow + ch * plane + ox) : 0.f;
+      }
+
+      // ---- ep 1: transposed conv's bias + ReLU -> bf16 patch (zeros outside the image: the 3x3 conv's padding).
+      // Eight 16-column pieces (half a tap each), the next piece's TMEM load in flight while this one is packed.
+      mbar_wait_a(d1f, ph, 4);
+      tc_fence_after();
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld_x16(tacc, va);
+#pragma unroll
+        for (int hp = 0; hp < 8; ++hp) {
+          uint32_t (&v)[16] = (hp & 1) ? vb : va;
+          uint32_t (&vn)[16] = (hp & 1) ? va : vb;
+          tmem_ld_wait();
+          if (hp < 7) tmem_ld_x16(tacc + (hp + 1) * 16, vn);
+          const int tap = hp >> 1;
+          const int py = 2 * iy + (tap >> 1), px = 2 * ix + (tap & 1);
+          const int gy = oy0 + py, gx = ox0 + px;
+          const bool inside = gy >= 0 && gy < Ho && gx >= 0 && gx < Wo;
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + hp * 16);
+          uint32_t p[8];
+          if (relu) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float4 bv = b4[jj];
+              p[2 * jj] = pack_bf16x2_relu(__uint_as_float(v[4 * jj]) + bv.x, __uint_as_float(v[4 * jj + 1]) + bv.y);
+              p[2 * jj + 1] = pack_bf16x2_relu(__uint_as_float(v[4 * jj + 2]) + bv.z, __uint_as_float(v[4 * jj + 3]) + bv.w);
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float4 bv = b4[jj];
+              p[2 * jj] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj]) + bv.x, a.slope),
+                                      act_fn(__uint_as_float(v[4 * jj + 1]) + bv.y, a.slope));
+              p[2 * jj + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj + 2]) + bv.z, a.slope),
+                                          act_fn(__uint_as_float(v[4 * jj + 3]) + bv.w, a.slope));
+            }
+          }
+          const int pp = py * 32 + px;
+          if (a.dbg & 32) continue;  // ablation: no patch writes
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+            sts128(patch + staged_off(pp, (hp & 1) * 2 + jj, 32),
+                   inside ? make_uint4(p[4 * jj], p[4 * jj + 1], p[4 * jj + 2], p[4 * jj + 3]) : make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a2r);
+
+      // ---- ep 2: fold the horizontal taps, bias + tanh, squared error against x, heat map, per-tile partials
+      mbar_wait_a(d2f, ph, 7);
+      tc_fence_after();
+      float ssum = 0.f, smin = INFINITY, smax = -INFINITY;
+      uint32_t wa[16], wb[16];
+      tmem_ld_x16(tacc, wa);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        uint32_t (&v)[16] = (s & 1) ? wb : wa;
+        uint32_t (&vn)[16] = (s & 1) ? wa : wb;
+        tmem_ld_wait();
+        if (s < 4) tmem_ld_x16(tacc + (s + 1) * 16, vn);  // next sub-tile's accumulator in flight during this one's math
+        if (s == 4) {  // the group's TMEM columns are free for the next tile's stage 1
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce);
+        }
+        const int ox = ox0 + 1 + 6 * s + scol;
+        const bool ok = row_ok && ox >= 0 && ox < Wo && !(a.dbg & 64);  // (ablation bit 64: no stores / reduction)
+        if (a.dbg & 256) continue;  // ablation: no ep 2 math
+        float sq = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[3 + ch]), 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[6 + ch]), 2);
+          const float rec = tanh_fn(((__uint_as_float(v[ch]) + s1) + s2) + b2[ch]);
+          const float d = xs[s][ch] - rec;
+          sq += d * d;
+          if (ok && a.recon) a.recon[xrow + ch * plane + ox] = rec;
+        }
+        if (ok) {
+          if (a.heat) a.heat[static_cast<long long>(fb) * plane + static_cast<long long>(oy) * Wo + ox] = sq * (1.f / 3.f);
+          ssum += sq;
+          smin = fminf(smin, sq);
+          smax = fmaxf(smax, sq);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+      }
+      if (lane == 0)
+        *reinterpret_cast<float4*>(a.partials + (static_cast<long long>(m_tile) * 4 + q) * 4) =
+            make_float4(ssum, smin * (1.f / 3.f), smax * (1.f / 3.f), 0.f);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Launch with (a.pdl != 0) or without the programmatic-stream-serialisation attribute.  With it the kernel may start
 // while its predecessor in the stream is still draining; every kernel launched this way runs its prologue (barrier
 // init, TMEM allocation, descriptor prefetch, bias load — constants only) and then `griddepcontrol.wait`s before it
@@ -2313,6 +2623,16 @@ int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream) {
     configured = true;
   }
   return launch_conv_kernel(convt2_score_kernel, a, grid, kC2Threads, kC2SmemBytes, stream);
+}
+
+int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convt_conv_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kI2SmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  return launch_conv_kernel(convt_conv_score_kernel, a, grid, kI2Threads, kI2SmemBytes, stream);
 }
 
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {

@@ -80,6 +80,7 @@ int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t
 int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t stream);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream);
+int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream);
 // dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)
 int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);
 int set_trap_slot(unsigned long long* device_ptr);

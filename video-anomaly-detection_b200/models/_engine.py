@@ -139,8 +139,30 @@ def _fused_tail(w6: GemmWeights, w9: GemmWeights, src: torch.Tensor, frames: int
     return ScoreOutputs(score, minmax, heat, recon)
 
 
+def _fused_image_tail(wt: GemmWeights, wc: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int,
+                      x: torch.Tensor, want_recon: bool, want_heat: bool, bufs: "_Buffers") -> "ScoreOutputs":
+    """Image dec4.0 (ConvT 32->32 + BN + ReLU) + dec4.3 (Conv3x3 32->3 + Tanh) + scoring: `vad_convt_conv_score`.
+    src bf16 NHWC [frames,H,W,32]; x fp32 [frames,3,2H,2W]."""
+    dev = x.device
+    Ho, Wo = 2 * H, 2 * W
+    recon = torch.empty(frames, 3, Ho, Wo, dtype=torch.float32, device=dev) if want_recon else None
+    heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
+    d = _gemm_desc(wt, src, frames, H, W, nat.EPI_CONVT, RELU, None, x=x, recon=recon, heat=heat, partials=x)
+    tiles = nat.load().vad_convt_conv_score_tiles(C.byref(d))
+    if tiles <= 0:
+        nat.check(tiles if tiles < 0 else -1, "vad_convt_conv_score_tiles")
+    partials = bufs.get("partials", (tiles, 4, 4), torch.float32, dev)
+    d.partials = partials.data_ptr()
+    _timed("dec4.0+4.3+score", lambda: nat.check(
+        nat.load().vad_convt_conv_score(C.byref(d), wc.w_kx.data_ptr(), wc.bias.data_ptr(), nat.stream_ptr()),
+        "vad_convt_conv_score"))
+    score, minmax = _finalize(partials, frames, 4 * (tiles // frames), Ho, Wo, bufs, dev)
+    return ScoreOutputs(score, minmax, heat, recon)
+
+
 FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
-# VAD_FUSE_DEC=0: run the video decoder's last two layers one by one (vad_conv_layer) instead of vad_convt2_score
+# VAD_FUSE_DEC=0: run the decoders' last two layers one by one (vad_conv_layer) instead of the fused tail kernels
+# (video: vad_convt2_score, image: vad_convt_conv_score)
 FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 
 
@@ -224,7 +246,14 @@ class ImageEngine:
         z, h, w = self.encode(x)
         g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
         cur = z
+        w40: GemmWeights = p["dec4.0"]
+        w43: GemmWeights = p["dec4.3"]
+        fuse_tail = FUSE_DEC_TAIL and w43.w_kx is not None and \
+            (w40.ctap, w40.n_total, w40.cout, w43.ctap, w43.n_total) == (32, 128, 32, 32, 16)
         for blk in ("dec1", "dec2", "dec3", "dec4"):
+            if blk == "dec4" and fuse_tail:
+                # dec4.0 + dec4.3 + score in one kernel: the 32-channel full-resolution tensor never reaches HBM
+                return _fused_image_tail(w40, w43, cur, B, h, w, x, want_recon, want_heat, self.bufs)
             wt: GemmWeights = p[f"{blk}.0"]
             up = g(f"{blk}a", (B, 2 * h, 2 * w, wt.cout))
             _convt(wt, cur, B, h, w, up, RELU, what=f"{blk}.0")
