@@ -127,6 +127,12 @@ int vad_convt_conv_score_tiles(const vad_conv_desc* d);
  * sequence bf16 [B][T][h][w][c0] (T0 = T), src1 = out = hidden sequence bf16 [B][T][h][w][hid] (T1 = T, c1 = hid,
  * out_frame_stride = T*h*w*hid), c_state fp32 [B][h][w][hid]; zero initial state. */
 int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream);
+/* Both layers of a two-layer ConvLSTM in ONE persistent launch, as a wavefront (layer 2's step t only needs layer 1's
+ * h_t): each CTA alternates between layer 1's step t+1 and layer 2's step t, so one layer's recurrence chain runs under
+ * the other's MMAs.  d1 / d2 as for vad_convlstm_sequence with d2->src0 == d1->out; results are bit-identical to two
+ * vad_convlstm_sequence calls.  VAD_ERR_UNSUPPORTED when the shapes do not fit the persistent patch kernel (the tiles
+ * of a layer must all be resident at once) or VAD_LSTM2=0: callers then run the layers one after the other. */
+int vad_convlstm2_sequence(const vad_conv_desc* d1, const vad_conv_desc* d2, int T, vad_stream_t stream);
 /* number of M tiles (= rows of `partials` for a *_SCORE layer) vad_conv_layer will use for this description;
  * negative = the error vad_conv_layer would return.  Launches nothing. */
 int vad_conv_layer_tiles(const vad_conv_desc* d);

@@ -206,6 +206,43 @@ def test_convlstm_paths_agree(cuda_device):
     _assert_close(outs[1][0], outs[0][0].float(), "patch kernel h vs per-step h", atol=1e-2)
     _assert_close(outs[1][1], outs[0][1], "patch kernel c vs per-step c", rtol=1e-3, atol=1e-3)
 
+
+@pytest.mark.parametrize("B,T,H,W", [(4, 6, 8, 8), (1, 1, 8, 8), (5, 2, 8, 8), (1, 5, 24, 40), (1, 3, 45, 80), (64, 16, 8, 8)])
+def test_convlstm_two_layer_wavefront(cuda_device, B, T, H, W):
+    """vad_convlstm2_sequence (both layers in one persistent launch, layer 2 one step behind layer 1) against two
+    vad_convlstm_sequence launches: hidden sequences of both layers and both final cell states are bit-identical (same
+    kernel roles, same MMA order per step)."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    cin = hid = 128
+    g = torch.Generator().manual_seed(17)
+    packed = {"lstm_layers": 2}
+    for layer in range(2):
+        w = torch.randn(4 * hid, cin + hid, 3, 3, generator=g) * (2.0 / (9 * (cin + hid))) ** 0.5
+        b = torch.randn(4 * hid, generator=g) * 0.1
+        packed[f"lstm.{layer}"] = _dev(prep.pack_lstm(w.double(), b.double(), hid), dev)
+    seq = _rand_nhwc(B * T, H, W, cin, dev, seed=7).view(B, T, H, W, cin)
+    res = {}
+    launches = {}
+    for fused in (True, False):
+        ve = eng.VideoEngine(packed)
+        eng.FUSE_LSTM_LAYERS = fused
+        n0 = nat.launch_count()
+        try:
+            out = ve.convlstm(seq, B, T, H, W).clone()
+        finally:
+            eng.FUSE_LSTM_LAYERS = True
+        torch.cuda.synchronize()
+        launches[fused] = nat.launch_count() - n0
+        res[fused] = (out, ve.bufs.get("hseq0", (B, T, H, W, hid), torch.bfloat16, dev).clone(),
+                      ve.bufs.get("c0", (B, H, W, hid), torch.float32, dev).clone(),
+                      ve.bufs.get("c1", (B, H, W, hid), torch.float32, dev).clone())
+    assert launches[True] == 1 and launches[False] == 2
+    for a, b, what in zip(res[True], res[False], ("h2 sequence", "h1 sequence", "c1", "c2")):
+        assert torch.equal(a, b), what
+    assert res[True][0].float().abs().mean().item() > 1e-3
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 32, 32), (3, 16, 48), (1, 48, 256)])
 @pytest.mark.parametrize("kx", [True, False])
 def test_last_conv_tanh_score(cuda_device, B, H, W, kx):

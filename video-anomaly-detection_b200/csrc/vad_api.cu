@@ -1025,12 +1025,14 @@ int vad_convt_conv_score_tiles(const vad_conv_desc* d) {
   return tw * th * d->B;
 }
 
-int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
+// Validates one ConvLSTM layer description and fills the kernel argument block; `patch_ok` tells whether the arguments
+// were set up for the persistent patch kernel (every tile has its own resident CTA, tile shapes apply, mode 1).
+static int build_lstm_layer(const vad_conv_desc* d, int T, ConvLaunch& L, bool& patch_ok, int& seq) {
   // d describes a generic step t >= 1: src0 = layer input sequence [B][T][h][w][c0], src1 = out = hidden sequence
   // [B][T][h][w][hid] (step t reads h_{t-1} from it and writes h_t into it), c_state fp32 [B][h][w][hid].
+  patch_ok = false;
   if (!d || T <= 0 || d->epilogue != VAD_EPI_LSTM || !d->src1 || d->src1 != d->out || d->c1 != d->cout) return VAD_ERR_ARG;
   if (d->T0 != T || d->T1 != T) return VAD_ERR_ARG;
-  ConvLaunch L;
   int rc = build_conv(d, L);
   if (rc != VAD_OK) return rc;
   ConvArgs& a = L.a;
@@ -1045,12 +1047,10 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
     cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
     if (encode_map5(&a.mapOut, d->out, dims, st, box, 32) != VAD_OK) a.tma_store = 0;
   }
-  const int chunks1 = a.chunks1;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // One persistent launch for the whole sequence when every tile gets its own resident CTA (cell state in registers,
   // grid-wide step counter); VAD_LSTM_SEQ=0 keeps one launch per step.
   static const int seq_env = env_int("VAD_LSTM_SEQ", 1);
-  const int seq = g_lstm_mode_override >= 0 ? g_lstm_mode_override : seq_env;
+  seq = g_lstm_mode_override >= 0 ? g_lstm_mode_override : seq_env;
   // Patch variant (A operand through one patch per chunk, weights through their own ring): 8x8 frames (two per tile) or
   // tiles of 8 x 16 pixels inside larger frames.  VAD_LSTM_SEQ=2 disables it (streaming sequence kernel instead).
   if (seq == 1 && a.tma_store && L.CK == 64 && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
@@ -1083,18 +1083,50 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
         cuuint32_t box[5] = {32, 8, 1u << g.lgTH, 1, 1u << g.lgTN};
         rc = encode_map5(&a.mapOut, d->out, dims, st, box, 32);
       }
-      if (rc == VAD_OK) {
-        a.lgTW = g.lgTW; a.lgTH = g.lgTH; a.lgTN = g.lgTN;
-        a.tiles_w = g.tiles_w; a.tiles_h = g.tiles_h; a.tiles_b = g.tiles_b;
-        a.total_tiles = g.m_tiles() * a.n_tiles;
-        a.w_step = 8; a.tw_valid = 8; a.pair = 1;
-        a.row_perm = geo1 ? 2 : 0;
-        a.out = d->out;
-        return launch_convlstm_patch(a, T, a.total_tiles, stream);
-      }
-      return rc;
+      if (rc != VAD_OK) return rc;
+      a.lgTW = g.lgTW; a.lgTH = g.lgTH; a.lgTN = g.lgTN;
+      a.tiles_w = g.tiles_w; a.tiles_h = g.tiles_h; a.tiles_b = g.tiles_b;
+      a.total_tiles = g.m_tiles() * a.n_tiles;
+      a.w_step = 8; a.tw_valid = 8; a.pair = 1;
+      a.row_perm = geo1 ? 2 : 0;
+      a.out = d->out;
+      patch_ok = true;
     }
   }
+  return VAD_OK;
+}
+
+// Both layers of a two-layer ConvLSTM in ONE persistent launch, as a wavefront: the CTA alternates between layer 1's
+// step t+1 and layer 2's step t, so one layer's recurrence chain (gates -> store -> publish -> acquire -> patch load)
+// runs under the other's MMAs.  d1 / d2 as for vad_convlstm_sequence, with d2->src0 == d1->out.  VAD_ERR_UNSUPPORTED when
+// the shapes do not fit the persistent patch kernel (callers then run the layers one after the other).
+int vad_convlstm2_sequence(const vad_conv_desc* d1, const vad_conv_desc* d2, int T, vad_stream_t stream_) {
+  if (!d1 || !d2) return VAD_ERR_ARG;
+  if (d2->src0 != d1->out || d2->c0 != d1->cout || d1->B != d2->B || d1->H != d2->H || d1->W != d2->W) return VAD_ERR_ARG;
+  static const int lstm2_env = env_int("VAD_LSTM2", 1);
+  if (!lstm2_env) return VAD_ERR_UNSUPPORTED;
+  ConvLaunch L1, L2;
+  bool ok1 = false, ok2 = false;
+  int seq = 0;
+  int rc = build_lstm_layer(d1, T, L1, ok1, seq);
+  if (rc != VAD_OK) return rc;
+  rc = build_lstm_layer(d2, T, L2, ok2, seq);
+  if (rc != VAD_OK) return rc;
+  if (!ok1 || !ok2 || L1.a.total_tiles != L2.a.total_tiles || L1.a.n_tiles != L2.a.n_tiles) return VAD_ERR_UNSUPPORTED;
+  return launch_convlstm2_patch(L1.a, L2.a, T, L1.a.total_tiles, static_cast<cudaStream_t>(stream_));
+}
+
+int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
+  ConvLaunch L;
+  bool patch_ok = false;
+  int seq = 0;
+  int rc = build_lstm_layer(d, T, L, patch_ok, seq);
+  if (rc != VAD_OK) return rc;
+  ConvArgs& a = L.a;
+  const long long step_elems = static_cast<long long>(d->H) * d->W * d->out_cpitch;
+  const int chunks1 = a.chunks1;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (patch_ok) return launch_convlstm_patch(a, T, a.total_tiles, stream);
   if (seq && a.tma_store && a.total_tiles <= sm_count() && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
     a.out = d->out;
     return launch_convlstm_seq(L.CK, a, T, a.total_tiles, stream);

@@ -1789,6 +1789,286 @@ __global__ void __launch_bounds__(384, 1) convlstm_patch_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------- ConvLSTM, two layers, wavefront
+// Both layers of the video model's ConvLSTM (reference ConvLSTM.forward, models/video_autoencoder.py:153-167: layer-outer,
+// time-inner loops) in one persistent launch.  Layer 2's step t only needs layer 1's h_t, so the two recurrences are
+// independent chains one step apart; the CTA (one pixel tile x one 32-channel tile of BOTH layers) walks the flat item
+// list  L1(0), L1(1), L2(0), L1(2), L2(1), ..., L1(T-1), L2(T-2), L2(T-1)  with the same roles as convlstm_patch_kernel.
+// While one layer's serial chain (gates -> h store -> publish -> neighbours acquire -> patch load) is in flight the
+// tensor pipe works on the other layer's item, which is what the single-layer kernel could not hide (9.3 us per step
+// against 4.7 us of MMAs).  One step counter per layer; layer 2's x patches wait for layer 1's counter.
+__device__ __forceinline__ void lstm2_item(int i, int T, int& layer, int& t) {
+  if (i == 0) { layer = 0; t = 0; }
+  else if (i == 2 * T - 1) { layer = 1; t = T - 1; }
+  else if (i & 1) { layer = 0; t = (i + 1) >> 1; }
+  else { layer = 1; t = (i >> 1) - 1; }
+}
+
+__device__ __forceinline__ void lstm_wait_counter(const unsigned int* counter, unsigned int target, int lane, int tag) {
+  if (lane == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(counter) < target) {
+      if (clock64() - t0 > 2000000000LL) {
+        if (g_vad_trap_slot) {
+          g_vad_trap_slot[0] = static_cast<unsigned long long>(tag);
+          g_vad_trap_slot[1] = blockIdx.x;
+          g_vad_trap_slot[2] = target;
+          g_vad_trap_slot[3] = ld_acquire_gpu(counter);
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  fence_proxy_async_all();  // the TMA loads that follow read what other CTAs published
+}
+
+__global__ void __launch_bounds__(384, 1) convlstm2_patch_kernel(const __grid_constant__ ConvArgs a1,
+                                                                 const __grid_constant__ ConvArgs a2, int T,
+                                                                 unsigned int* __restrict__ counters) {
+  constexpr int BN = 128, CK = 64;
+  constexpr int kRowBytes = 128;
+  constexpr int kBBytes = BN * kRowBytes;  // 16 KB
+  constexpr uint32_t kLayout = 2u;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t p_full[kLpPatches], p_empty[kLpPatches];
+  __shared__ uint64_t b_full[kLpBRing], b_empty[kLpBRing];
+  __shared__ uint64_t acc_full_bar[2];
+  __shared__ uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[2][BN];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_b = smem;
+  uint8_t* s_p = smem + kLpBRing * kBBytes;
+  uint8_t* stg = s_p + kLpPatches * kLpPatchPitch;
+
+  const bool geo1 = a1.row_perm == 2;
+  const uint32_t patch_tx = static_cast<uint32_t>((geo1 ? 200 : 180) * kRowBytes);
+  const int ky_rows = geo1 ? 20 : 10;  // patch rows per image row
+  const TileCoord tc = TileIter(a1, blockIdx.x, gridDim.x).coord(a1, BN);
+  const int n_items = 2 * T;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a1.mapA0); tma_prefetch_desc(&a1.mapA1); tma_prefetch_desc(&a1.mapB); tma_prefetch_desc(&a1.mapOut);
+    tma_prefetch_desc(&a2.mapA0); tma_prefetch_desc(&a2.mapA1); tma_prefetch_desc(&a2.mapB); tma_prefetch_desc(&a2.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kLpPatches; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < kLpBRing; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 8);  // eight epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<256>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * BN; i += 384) s_bias[i >> 7][i & 127] = (i < BN ? a1.bias : a2.bias)[tc.n0 + (i & 127)];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== patch producer (x half, then h half)
+    const uint32_t pf0 = smem_addr_once(&p_full[0]), pe0 = smem_addr_once(&p_empty[0]);
+    const uint32_t sp0 = smem_addr_once(s_p);
+    int ps = 0;
+    uint32_t pphase = 0;
+    for (int i = 0; i < n_items; ++i) {
+      int layer, t;
+      lstm2_item(i, T, layer, t);
+      const ConvArgs& a = layer == 0 ? a1 : a2;
+      for (int src = 0; src < 2; ++src) {
+        if (src == 1 && t == 0) break;
+        // layer 2's input x_t is layer 1's h_t: published once counter 0 has reached (t+1) * grid;
+        // a layer's own h_{t-1}: its counter at t * grid
+        if (src == 0 && layer == 1) lstm_wait_counter(counters, static_cast<unsigned int>(t + 1) * gridDim.x, lane, 13);
+        if (src == 1) lstm_wait_counter(counters + layer, static_cast<unsigned int>(t) * gridDim.x, lane, 12);
+        const int n_chunks = src == 0 ? a.chunks0 : a.chunks1;
+        const void* map = src == 0 ? static_cast<const void*>(&a.mapA0) : static_cast<const void*>(&a.mapA1);
+        const int tt = src == 0 ? t : t - 1;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait_a(pe0 + ps * 8, pphase ^ 1u, 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx_a(pf0 + ps * 8, patch_tx);
+            if (geo1)  // map dims {C, W, B, H, T}
+              tma_load_5d_a(sp0 + ps * kLpPatchPitch, map, pf0 + ps * 8, c * CK, tc.w0 - 1, tc.b0, tc.h0 - 1, tt);
+            else       // map dims {C, W, H, T, B}
+              tma_load_5d_a(sp0 + ps * kLpPatchPitch, map, pf0 + ps * 8, c * CK, tc.w0 - 1, tc.h0 - 1, tt, tc.b0);
+          }
+          __syncwarp();
+          if (++ps == kLpPatches) { ps = 0; pphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================================== weight producer (independent of the steps)
+    const uint32_t bf0 = smem_addr_once(&b_full[0]), be0 = smem_addr_once(&b_empty[0]);
+    const uint32_t sb0 = smem_addr_once(s_b);
+    int bs = 0;
+    uint32_t bphase = 0;
+    for (int i = 0; i < n_items; ++i) {
+      int layer, t;
+      lstm2_item(i, T, layer, t);
+      const ConvArgs& a = layer == 0 ? a1 : a2;
+      for (int src = 0; src < 2; ++src) {
+        if (src == 1 && t == 0) break;
+        const int n_chunks = src == 0 ? a.chunks0 : a.chunks1;
+        const int kbase = src == 0 ? 0 : a.chunks0 * CK;
+        for (int c = 0; c < n_chunks; ++c) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait_a(be0 + bs * 8, bphase ^ 1u, 9);
+            if (elect_one()) {
+              mbar_arrive_expect_tx_a(bf0 + bs * 8, kBBytes);
+              tma_load_2d_a(sb0 + bs * kBBytes, &a.mapB, bf0 + bs * 8, tap * a.w_ctap + kbase + c * CK, tc.n0);
+            }
+            __syncwarp();
+            if (++bs == kLpBRing) { bs = 0; bphase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+    const uint32_t pf0 = smem_addr_once(&p_full[0]), pe0 = smem_addr_once(&p_empty[0]);
+    const uint32_t bf0 = smem_addr_once(&b_full[0]), be0 = smem_addr_once(&b_empty[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_p), 10 * kRowBytes, kLayout);  // 8-row groups 10 patch rows apart
+    const uint64_t db_base = umma_smem_desc(smem_u32(s_b), 8 * kRowBytes, kLayout);
+    int ps = 0, bs = 0;
+    uint32_t pphase = 0, bphase = 0;
+    for (int i = 0; i < n_items; ++i) {
+      int layer, t;
+      lstm2_item(i, T, layer, t);
+      const ConvArgs& a = layer == 0 ? a1 : a2;
+      const int n_patches = a.chunks0 + (t > 0 ? a.chunks1 : 0);
+      const int as = i & 1;
+      mbar_wait_a(acce0 + as * 8, static_cast<uint32_t>(((i >> 1) & 1) ^ 1), 3);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int p = 0; p < n_patches; ++p) {
+        mbar_wait_a(pf0 + ps * 8, pphase, 2);
+        const uint64_t da_p = da_base + static_cast<uint64_t>(ps * (kLpPatchPitch >> 4));
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait_a(bf0 + bs * 8, bphase, 10);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = da_p + static_cast<uint64_t>(((ky * ky_rows + kx) * kRowBytes) >> 4);
+            const uint64_t db = db_base + static_cast<uint64_t>(bs * (kBBytes >> 4));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (p > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_a(be0 + bs * 8);
+            if (tap == 8) umma_commit_a(pe0 + ps * 8);
+            if (tap == 8 && p == n_patches - 1) umma_commit_a(accf0 + as * 8);
+          }
+          __syncwarp();
+          if (++bs == kLpBRing) { bs = 0; bphase ^= 1u; }
+          if (++kx == 3) { kx = 0; ++ky; }
+        }
+        if (++ps == kLpPatches) { ps = 0; pphase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue: gates, c (registers), h
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;  // 0 | 1: which 16 channels
+    const EpiLane L = make_epi_lane(a1, q, lane);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const bool leader = (warp == kEpiWarp0 && lane == 0);
+    const int fb = tc.b0 + L.bb, h = tc.h0 + L.hh, w = tc.w0 + L.ww;
+    const bool valid = L.row_ok && (fb < a1.B) && (h < a1.H) && (w < a1.W);
+    const int j0 = (tc.n0 >> 7) * 32;
+    float c1[16], c2[16];  // cell state of this lane's pixel, 16 channels, both layers
+#pragma unroll
+    for (int e = 0; e < 16; ++e) c1[e] = c2[e] = 0.f;
+    for (int i = 0; i < n_items; ++i) {
+      int layer, t;
+      lstm2_item(i, T, layer, t);
+      const int as = i & 1;
+      mbar_wait_a(accf0 + as * 8, static_cast<uint32_t>((i >> 1) & 1), 4u | (static_cast<uint32_t>(i) << 8));
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int s = half * 2 + s2;  // 8-channel group of the tile
+        uint32_t gi[8], gf[8], gg[8], go[8];
+        tmem_ld_x8(tacc + 0 + s * 8, gi);
+        tmem_ld_x8(tacc + 32 + s * 8, gf);
+        tmem_ld_x8(tacc + 64 + s * 8, gg);
+        tmem_ld_x8(tacc + 96 + s * 8, go);
+        tmem_ld_wait();
+        if (s2 == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce0 + as * 8);
+        }
+        float hn[8];
+        const float* bp = s_bias[layer] + s * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xi = __uint_as_float(gi[e]) + bp[e];
+          const float xf = __uint_as_float(gf[e]) + bp[32 + e];
+          const float xg = __uint_as_float(gg[e]) + bp[64 + e];
+          const float xo = __uint_as_float(go[e]) + bp[96 + e];
+          const float cprev = layer == 0 ? c1[s2 * 8 + e] : c2[s2 * 8 + e];
+          const float cn = sigmoid_fn(xf) * cprev + sigmoid_fn(xi) * tanh_fn(xg);
+          if (layer == 0) c1[s2 * 8 + e] = cn; else c2[s2 * 8 + e] = cn;
+          hn[e] = sigmoid_fn(xo) * tanh_fn(cn);
+        }
+        sts128(stg + staged_off(L.srow, s, 32), make_uint4(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]),
+                                                            pack_bf16x2(hn[4], hn[5]), pack_bf16x2(hn[6], hn[7])));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (leader) {  // publishing h_t is on the critical path of every neighbour: do it before the group barrier
+        tma_store_5d(layer == 0 ? &a1.mapOut : &a2.mapOut, stg, j0, tc.w0, tc.h0, t, tc.b0);
+        bulk_commit_group();
+        bulk_wait_group<0>();  // h_t of this tile is in global memory ...
+        __threadfence();
+        red_release_gpu_add(counters + layer, 1u);  // ... and published
+      }
+      named_bar_sync(1, 256);  // nobody overwrites the staging buffer before the store has read it
+    }
+    if (valid) {
+      const long long pix = (static_cast<long long>(fb) * a1.H + h) * a1.W + w;
+      if (a1.c_state != nullptr) {
+        float* cptr = a1.c_state + pix * a1.cout + j0 + half * 16;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(cptr + e) = make_float4(c1[e], c1[e + 1], c1[e + 2], c1[e + 3]);
+      }
+      if (a2.c_state != nullptr) {
+        float* cptr = a2.c_state + pix * a2.cout + j0 + half * 16;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(cptr + e) = make_float4(c2[e], c2[e + 1], c2[e + 2], c2[e + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- first conv
 // 3 -> 32 channel 3x3 conv straight from the fp32 NCHW model input.  K = 27 (padded to 32).  TMA brings the fp32
 // input patch of a tile (3 channels x 10 rows x 24 columns, zero-filled outside the frame = conv padding) into smem;
@@ -2849,6 +3129,28 @@ int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t strea
   e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
   convlstm_patch_kernel<<<grid, 384, smem, stream>>>(a, T, counter);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+__device__ unsigned int g_lstm2_counters[64];  // pairs {layer 1, layer 2}, a rotating pool as above
+
+int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int grid, cudaStream_t stream) {
+  constexpr int smem = kLpBRing * 128 * 128 + kLpPatches * kLpPatchPitch + 8192 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convlstm2_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  static unsigned int next_slot = 0;
+  unsigned int* base = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm2_counters);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  unsigned int* counters = base + 2 * (next_slot++ & 31u);
+  e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  convlstm2_patch_kernel<<<grid, 384, smem, stream>>>(a1, a2, T, counters);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

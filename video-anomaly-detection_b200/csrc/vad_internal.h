@@ -78,6 +78,7 @@ int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int hs_patch_stages(int EPI);
 int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t stream);
 int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t stream);
+int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int grid, cudaStream_t stream);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream);

@@ -164,6 +164,8 @@ FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
 # VAD_FUSE_DEC=0: run the decoders' last two layers one by one (vad_conv_layer) instead of the fused tail kernels
 # (video: vad_convt2_score, image: vad_convt_conv_score)
 FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
+# VAD_LSTM2=0: one launch per ConvLSTM layer (vad_convlstm_sequence) instead of the two-layer wavefront kernel
+FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
 
 
 def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
@@ -291,27 +293,50 @@ class VideoEngine:
             cur, h, w = nxt, h // 2, w // 2
         return cur, h, w
 
+    def _lstm_desc(self, layer: int, cur: torch.Tensor, B: int, T: int, h: int, w: int):
+        p, dev = self.p, cur.device
+        wt: GemmWeights = p[f"lstm.{layer}"]
+        hid = wt.cout
+        cin = wt.ctap - hid
+        hseq = self.bufs.get(f"hseq{layer}", (B, T, h, w, hid), torch.bfloat16, dev)
+        cst = self.bufs.get(f"c{layer}", (B, h, w, hid), torch.float32, dev)
+        d = nat.ConvDesc()
+        d.src0, d.src1, d.out = cur.data_ptr(), hseq.data_ptr(), hseq.data_ptr()
+        d.c0, d.c1, d.T0, d.T1 = cin, hid, T, T
+        d.B, d.H, d.W, d.ntaps = B, h, w, 9
+        d.weight, d.bias, d.w_ctap = wt.w.data_ptr(), wt.bias.data_ptr(), wt.ctap
+        d.n_total, d.cout, d.epilogue, d.slope = wt.n_total, hid, nat.EPI_LSTM, IDENT
+        d.out_frame_stride, d.out_cpitch = T * h * w * hid, hid
+        d.c_state = cst.data_ptr()
+        return d, hseq
+
     def convlstm(self, seq: torch.Tensor, B: int, T: int, h: int, w: int) -> torch.Tensor:
         """seq bf16 [B,T,h,w,C] -> last layer's hidden sequence bf16 [B,T,h,w,hid] (zero initial state)."""
-        p, dev = self.p, seq.device
+        p = self.p
         cur = seq
-        for layer in range(p["lstm_layers"]):
-            wt: GemmWeights = p[f"lstm.{layer}"]
-            hid = wt.cout
-            cin = wt.ctap - hid
-            hseq = self.bufs.get(f"hseq{layer}", (B, T, h, w, hid), torch.bfloat16, dev)
-            cst = self.bufs.get(f"c{layer}", (B, h, w, hid), torch.float32, dev)
-            d = nat.ConvDesc()
-            d.src0, d.src1, d.out = cur.data_ptr(), hseq.data_ptr(), hseq.data_ptr()
-            d.c0, d.c1, d.T0, d.T1 = cin, hid, T, T
-            d.B, d.H, d.W, d.ntaps = B, h, w, 9
-            d.weight, d.bias, d.w_ctap = wt.w.data_ptr(), wt.bias.data_ptr(), wt.ctap
-            d.n_total, d.cout, d.epilogue, d.slope = wt.n_total, hid, nat.EPI_LSTM, IDENT
-            d.out_frame_stride, d.out_cpitch = T * h * w * hid, hid
-            d.c_state = cst.data_ptr()
+        layer = 0
+        while layer < p["lstm_layers"]:
+            d, hseq = self._lstm_desc(layer, cur, B, T, h, w)
+            if FUSE_LSTM_LAYERS and layer + 1 < p["lstm_layers"]:
+                # two layers as one wavefront launch (layer 2's step t runs next to layer 1's step t+1)
+                d2, hseq2 = self._lstm_desc(layer + 1, hseq, B, T, h, w)
+                rc = [0]
+
+                def both():
+                    rc[0] = nat.load().vad_convlstm2_sequence(C.byref(d), C.byref(d2), T, nat.stream_ptr())
+                    if rc[0] != nat.ERR_UNSUPPORTED:
+                        nat.check(rc[0], f"convlstm.{layer}+{layer + 1}")
+                _timed(f"convlstm.{layer}+{layer + 1}", both)
+                if rc[0] == 0:
+                    cur = hseq2
+                    layer += 2
+                    continue
+                if PROFILE is not None:
+                    PROFILE.pop()  # nothing was launched
             _timed(f"convlstm.{layer}", lambda: nat.check(
                 nat.load().vad_convlstm_sequence(C.byref(d), T, nat.stream_ptr()), f"convlstm.{layer}"))
             cur = hseq
+            layer += 1
         return cur
 
     def project(self, seq: torch.Tensor, F: int, h: int, w: int) -> torch.Tensor:

@@ -13,11 +13,12 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_DIR, "libvad_b200.so")
 
+ERR_UNSUPPORTED = -3
 EPI_STORE, EPI_POOL, EPI_CONVT, EPI_LSTM, EPI_TANH_SCORE, EPI_CONVT_TANH_SCORE = range(6)
 
 # every symbol include/vad_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convt2_score", "vad_convt2_score_tiles", "vad_convt_conv_score", "vad_convt_conv_score_tiles", "vad_convlstm_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
+    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convt2_score", "vad_convt2_score_tiles", "vad_convt_conv_score", "vad_convt_conv_score_tiles", "vad_convlstm_sequence", "vad_convlstm2_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8", "vad_u8_hwc_to_f32_nchw", "vad_f32_nchw_to_u8_hwc",
     "vad_heatmap_jet_rgb", "vad_ssim_scratch_bytes", "vad_ssim_loss",
@@ -71,6 +72,7 @@ def load() -> C.CDLL:
     lib.vad_convt_conv_score.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vad_convt_conv_score_tiles.argtypes = [C.POINTER(ConvDesc)]
     lib.vad_convlstm_sequence.argtypes = [C.POINTER(ConvDesc), C.c_int, C.c_void_p]
+    lib.vad_convlstm2_sequence.argtypes = [C.POINTER(ConvDesc), C.POINTER(ConvDesc), C.c_int, C.c_void_p]
     lib.vad_conv_m_tiles.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.vad_first_conv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]
