@@ -4,7 +4,7 @@
 TAG=${1:-r01d}
 mkdir -p gpurun_out
 for W in cfg2 cfg3; do
-  N=$([ $W = cfg2 ] && echo 16 || echo 10)   # launches of this library per step (incl. score_finalize)
+  N=$([ $W = cfg2 ] && echo 16 || echo 9)   # launches of this library per step (incl. score_finalize)
   timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --workload $W > gpurun_out/plain_${TAG}_$W.log 2>&1 || { echo "plain $W failed"; tail -5 gpurun_out/plain_${TAG}_$W.log; continue; }
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}_$W.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --workload $W > gpurun_out/ncu_${TAG}_a_$W.log 2>&1
