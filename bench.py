@@ -267,7 +267,13 @@ def main():
         from runtime.sharding import bind_to_gpu_numa_node
         numa_node = bind_to_gpu_numa_node(local_rank)
     dist = None
+    stdout_fd = None
     if world > 1:
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout must carry the JSON
+        # line and nothing else, so file descriptor 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -469,8 +475,13 @@ def main():
         line["gpu_library_baseline"] = gpu_library_baseline(kind, B, T, H, W, dev, x)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(kind, T, H, W)
-    print(json.dumps(line))
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        os.close(stdout_fd)
+    print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)  # (anything NCCL says while shutting down goes to stderr too)
         dist.destroy_process_group()
 
 
