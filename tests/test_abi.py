@@ -64,6 +64,33 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.vad_score(None, None, 1, 16, 16, None, None, None, None, None) == -1
 
 
+def test_fused_tail_entry_points_validate_on_the_host(lib):
+    """The fused decoder-tail / two-layer ConvLSTM entry points reject bad descriptions with codes before touching the
+    GPU, and their tile counts (= rows of the caller's `partials` buffer) follow the documented tilings."""
+    from models._native import ConvDesc
+    assert lib.vad_convt_conv_score(None, None, None, None) == -1
+    assert lib.vad_convt2_score(None, None, None, None) == -1
+    assert lib.vad_convlstm2_sequence(None, None, 4, None) == -1
+    assert lib.vad_convt_conv_score_tiles(None) == -1 and lib.vad_convt2_score_tiles(None) == -1
+    d = ConvDesc()
+    d.B, d.H, d.W, d.ntaps, d.c0, d.n_total, d.cout = 3, 128, 128, 1, 32, 128, 32
+    # image tail: tile (th, tw) scores output rows [14 th - 1, 14 th + 13) x columns [30 tw - 1, 30 tw + 29) of 2H x 2W
+    assert lib.vad_convt_conv_score_tiles(ctypes.byref(d)) == 3 * 19 * 9
+    d.H, d.W = 8, 8
+    assert lib.vad_convt_conv_score_tiles(ctypes.byref(d)) == 3 * 2 * 1
+    d.c0 = 64  # the image tail is the 32 -> 32 -> 3 block only
+    assert lib.vad_convt_conv_score_tiles(ctypes.byref(d)) == -3
+    assert lib.vad_convt_conv_score(ctypes.byref(d), None, None, None) == -1  # (null pointers are reported first)
+    # video tail: 64 -> 32 -> 3, one 128-pixel tile inside one frame
+    assert lib.vad_convt2_score_tiles(ctypes.byref(d)) == 3 * lib.vad_conv_m_tiles(1, 8, 8, 1)
+    d.H, d.W = 180, 320
+    assert lib.vad_convt2_score_tiles(ctypes.byref(d)) == lib.vad_conv_m_tiles(3, 180, 320, 1)
+    d.cout, d.n_total = 16, 64
+    assert lib.vad_convt2_score_tiles(ctypes.byref(d)) == -3
+    d.ntaps = 9
+    assert lib.vad_convt2_score_tiles(ctypes.byref(d)) == -1
+
+
 def test_no_cpu_fallback():
     import torch
     from models import ConvAutoencoder

@@ -4,7 +4,8 @@
 //                                        over [B][T][H][W][C] with out-of-bounds zero fill = conv padding)
 //                                     x  B[BN, CK] (bf16, smem via TMA, weights K-major)
 //
-// Seven kernels share one set of epilogues (section markers below, in file order):
+// Seven single-layer kernels share one set of epilogues; three more fuse neighbouring layers (section markers below, in
+// file order):
 //   epilogue              — STORE / POOL / CONVT / LSTM / TANH_SCORE / CONVT_TANH_SCORE on one finished accumulator
 //                           tile; EpiLane (per-lane constants), TileIter (division-free tile walking), epilogue_loop.
 //   conv_umma_kernel      — "streaming": one (A tile, B tile) pair per tap and channel chunk through an mbarrier ring.
@@ -15,8 +16,13 @@
 //   conv_hs_kernel        — wide 3x3 layers: patches for pairs of tiles (M = 256) + streamed weight tiles.
 //   convlstm_seq_kernel   — all T steps of a ConvLSTM layer in one launch (cell state in registers), streamed A tiles.
 //   convlstm_patch_kernel — the same with A patches, a separate weight ring / producer and an 8-warp gate epilogue.
+//   convlstm2_patch_kernel — both ConvLSTM layers in one launch as a wavefront (layer 2 one step behind layer 1).
 //   conv_first_kernel     — 3 -> 32 first conv from the fp32 NCHW input: TMA patch -> converter warps (im2col, bf16,
 //                           they also issue the MMAs) -> epilogue.
+//   convt2_score_kernel   — video decoder tail: ConvT(64->32)+ReLU -> ConvT(32->3)+tanh -> score; the two GEMMs are
+//                           chained through shared memory (epilogue 1 writes the second GEMM's A operands).
+//   convt_conv_score_kernel — image decoder tail: ConvT(32->32)+ReLU -> conv3x3(32->3)+tanh -> score; the transposed
+//                           conv's output lives as a 16 x 32 pixel patch in shared memory.
 // All are persistent and warp-specialised (TMA producer(s), tcgen05.mma issuer(s), TMEM allocator, 1-6 epilogue groups
 // of four warps: TMEM -> registers -> bias/activation/pool/pixel-shuffle/gates/score -> registers or swizzled smem ->
 // global / TMA store); 2-4 accumulator stages in TMEM let epilogues overlap the next tiles' MMAs.  Host-side launchers
