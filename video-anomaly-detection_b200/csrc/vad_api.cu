@@ -980,6 +980,7 @@ static int build_convt_conv_score(const vad_conv_desc* d, const void* weight2_kx
   if (d->ntaps != 1 || d->c1 != 0 || d->T0 > 1) return VAD_ERR_ARG;
   if (!convt_conv_score_shape_ok(d)) return VAD_ERR_UNSUPPORTED;
   if (d->w_ctap != 0 && d->w_ctap != 32) return VAD_ERR_ARG;
+  if (12LL * d->H * d->W >= 2147483647LL) return VAD_ERR_SHAPE;  // the kernel indexes a frame's three planes with ints
   ensure_trap_slot();
   std::memset(&a, 0, sizeof(a));
   int rc = encode_act_map_box(&a.mapA0, d->src0, 32, d->W, d->H, 1, d->B, 32, 16, 8, 1);

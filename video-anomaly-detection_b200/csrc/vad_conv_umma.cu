@@ -2737,6 +2737,8 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
     uint8_t* patch = s_p + g * kI2PatchBytes;
     const int Ho = 2 * a.H, Wo = 2 * a.W;
     const long long plane = static_cast<long long>(Ho) * Wo;
+    const int plane_i = Ho * Wo;
+    const bool want_recon = a.recon != nullptr, want_heat = a.heat != nullptr;
     const float* b2 = s_bias + 128;
     const bool relu = a.slope == 0.f;     // (the model's case: ReLU folded into the bf16 conversion)
     const int iy = r >> 4, ix = r & 15;   // ep 1: this accumulator row's input pixel inside the 8 x 16 block
@@ -2747,16 +2749,21 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
       const int fb = ti.tb;
       const int m_tile = (ti.tb * a.tiles_h + ti.th) * a.tiles_w + ti.tw;
       // the model-input pixels this lane scores in the five sub-tiles (in flight while both GEMM stages run)
-      const int oy = oy0 + 1 + srow;
+      // (one 64-bit pixel offset per tile; everything else is 32-bit index arithmetic from there — the host checks that
+      // a frame's three planes fit an int — and the five validity tests are done once, as a bit mask)
+      const int oy = oy0 + 1 + srow, oxb = ox0 + 1 + scol;  // this lane's output pixel in sub-tile s: (oy, oxb + 6 s)
       const bool row_ok = scol < 6 && srow < 14 && oy >= 0 && oy < Ho;
-      const long long xrow = static_cast<long long>(fb) * 3 * plane + static_cast<long long>(oy) * Wo;
+      const long long pix = static_cast<long long>(oy) * Wo + oxb;             // (never dereferenced when !row_ok)
+      const float* xt = a.x + static_cast<long long>(fb) * 3 * plane + pix;
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) okmask |= (row_ok && oxb + 6 * s >= 0 && oxb + 6 * s < Wo) ? (1u << s) : 0u;
+      if (a.dbg & 128) okmask = 0;  // ablation: no x loads (and nothing scored)
       float xs[5][3];
 #pragma unroll
       for (int s = 0; s < 5; ++s) {
-        const int ox = ox0 + 1 + 6 * s + scol;
-        const bool ok = row_ok && ox >= 0 && ox < Wo;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) xs[s][ch] = (ok && !(a.dbg & 128)) ? __ldg(a.x + xrow + ch * plane + ox) : 0.f;
+        for (int ch = 0; ch < 3; ++ch) xs[s][ch] = ((okmask >> s) & 1u) ? __ldg(xt + ch * plane_i + 6 * s) : 0.f;
       }
 
       // ---- ep 1: transposed conv's bias + ReLU -> bf16 patch (zeros outside the image: the 3x3 conv's padding).
@@ -2825,21 +2832,25 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
           __syncwarp();
           if (lane == 0) mbar_arrive_a(acce);
         }
-        const int ox = ox0 + 1 + 6 * s + scol;
-        const bool ok = row_ok && ox >= 0 && ox < Wo && !(a.dbg & 64);  // (ablation bit 64: no stores / reduction)
+        const bool ok = ((okmask >> s) & 1u) != 0u && !(a.dbg & 64);  // (ablation bit 64: no stores / reduction)
         if (a.dbg & 256) continue;  // ablation: no ep 2 math
         float sq = 0.f;
+        float rec[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[3 + ch]), 1);
           const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[6 + ch]), 2);
-          const float rec = tanh_fn(((__uint_as_float(v[ch]) + s1) + s2) + b2[ch]);
-          const float d = xs[s][ch] - rec;
+          rec[ch] = tanh_fn(((__uint_as_float(v[ch]) + s1) + s2) + b2[ch]);
+          const float d = xs[s][ch] - rec[ch];
           sq += d * d;
-          if (ok && a.recon) a.recon[xrow + ch * plane + ox] = rec;
         }
         if (ok) {
-          if (a.heat) a.heat[static_cast<long long>(fb) * plane + static_cast<long long>(oy) * Wo + ox] = sq * (1.f / 3.f);
+          if (want_recon) {
+            float* rt = a.recon + static_cast<long long>(fb) * 3 * plane + pix;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) rt[ch * plane_i + 6 * s] = rec[ch];
+          }
+          if (want_heat) a.heat[static_cast<long long>(fb) * plane + pix + 6 * s] = sq * (1.f / 3.f);
           ssum += sq;
           smin = fminf(smin, sq);
           smax = fmaxf(smax, sq);
