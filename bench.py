@@ -277,7 +277,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    from models import _engine as eng, _native as nat
+    from models import _native as nat
     model = build_model(kind, dev)
     x = synth_input(kind, B, T, H, W, dev, seed=1234 + rank)
     flush = None if B * T * 3 * H * W * 4 > 126e6 else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -328,26 +328,39 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
 
-    # ---- per-kernel timing for the roofline (CUDA events around every launch, same inputs)
-    eng.PROFILE = []
-    for _ in range(5):
+    # ---- per-kernel timing for the roofline: the library brackets every layer launch of the model-level call with CUDA
+    # events on the launching stream (vad_profile_enable / vad_profile_dump), same inputs
+    reps = 5
+    nat.profile_enable(True)
+    for _ in range(reps):
         run_model(model, kind, x)
     torch.cuda.synchronize()
+    rows = nat.profile_dump()
+    nat.profile_enable(False)
+    per_run = len(rows) // reps
     per = {}
-    for name, e0, e1 in eng.PROFILE:
-        per.setdefault(name, []).append(e0.elapsed_time(e1))
-    eng.PROFILE = None
-    # ConvLSTM steps are one kernel launched 2T times: fold them into one entry per (layer, first/rest)
+    for r in range(reps):
+        acc = {}
+        for name, ms in rows[r * per_run:(r + 1) * per_run]:
+            a = acc.setdefault(name, [0.0, 0])
+            a[0] += ms
+            a[1] += 1
+        for name, (ms, n) in acc.items():
+            per.setdefault(name, []).append((ms, n))
+    # one entry per layer name; a layer launched several times per step (ConvLSTM groups of clips) keeps its launch count
     kern = {}
-    for name, ts in per.items():
-        key = name
-        d = kern.setdefault(key, {"ms": 0.0, "launches": 0, "rep": name})
-        d["ms"] += statistics.median(ts)
-        d["launches"] += 1
+    small = {}
+    for name, vals in per.items():
+        ms = statistics.median(v[0] for v in vals)
+        if name in ("finalize", "latent_out"):
+            small[name] = ms
+            continue
+        kern[name] = {"ms": ms, "launches": vals[0][1], "rep": name}
     total_kernel_ms = sum(d["ms"] for d in kern.values())
     top_name, top = max(kern.items(), key=lambda kv: kv[1]["ms"])
     pk = peaks()
     flops, byts = layer_cost(kind, top["rep"], B, T, H, W)
+    flops, byts = flops / top["launches"], byts / top["launches"]
     avg_ms = top["ms"] / top["launches"]
     ai = flops / byts
     if ai >= pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9):
@@ -365,7 +378,7 @@ def main():
     per_kernel = {}
     for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
         kf, kb = layer_cost(kind, v["rep"], B, T, H, W)
-        kms = v["ms"] / v["launches"]
+        kms = v["ms"]  # (whole layer: all its launches of one step)
         if kf / kb >= ridge:
             per_kernel[k] = {"ms": round(v["ms"], 4), "bound": "tensor",
                              "frac": round(kf / (kms * 1e-3) / 1e12 / pk["bf16_tflops"], 3)}

@@ -100,6 +100,10 @@ typedef struct vad_conv_desc {
    * (*_SCORE: Cout = 3 -> 9 rows padded to 16).  When present the library may fold the horizontal taps into the
    * GEMM N extent (3 instead of 9 shifted MMAs per K step); NULL keeps the tap-per-MMA kernels. */
   const void* weight_kx;
+  /* optional device scratch of >= 8 bytes for vad_convlstm_sequence / vad_convlstm2_sequence: the grid-wide step
+   * counters of the persistent kernels live there (zeroed by the library on `stream`; must not be shared by two calls
+   * in flight).  NULL: a slot of the library's own rotating pool is used. */
+  void* scratch;
 } vad_conv_desc;
 
 int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
@@ -188,6 +192,109 @@ int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int 
 size_t vad_ssim_scratch_bytes(int frames, int H, int W);
 int vad_ssim_loss(const float* pred, const float* target, int frames, int H, int W, float* loss, float* ssim_map,
                   void* scratch, vad_stream_t stream);
+
+/* =================================================================================================================
+ * Model-level entry points: ONE call per reference method.  These are what the drop-in Python classes bind; the
+ * per-layer entry points above stay public for layer-level tests and tuning.
+ *
+ * Weights are the host-prepared GEMM operands (eval-mode BatchNorm folded, bf16 K-major; models/_prepare.py), passed as
+ * device pointers.  Every call enqueues its whole layer schedule on `stream`, allocates nothing and never synchronises:
+ * intermediate activations, score partials and the ConvLSTM step counters live in the caller-supplied workspace `ws`
+ * (>= the matching *_workspace_bytes(); 256-byte aligned; must not be shared by two calls in flight on different streams).
+ * All entry points are re-entrant per (stream, workspace) and use the CUDA device that is current on the calling thread.
+ * ================================================================================================================= */
+typedef struct vad_gemm_weights {
+  const void* w;     /* bf16 [n_total][ntaps*ctap] (vad_conv_desc.weight) */
+  const void* w_kx;  /* optional kx-folded layout of a narrow 3x3 layer (vad_conv_desc.weight_kx) */
+  const float* bias; /* fp32 [n_total] */
+  int ntaps, ctap, n_total, cout;
+} vad_gemm_weights;
+
+typedef struct vad_first_weights {
+  const float* w;    /* fp32 [27][cout] (vad_first_conv) */
+  const void* w_tc;  /* bf16 [cout][32] (vad_first_conv_tc); NULL: CUDA-core kernel */
+  const float* bias; /* fp32 [cout] */
+  int cout;
+} vad_first_weights;
+
+#define VAD_FLAG_NO_FUSED_TAIL 1     /* run the decoder's last two layers one by one (test / tuning aid) */
+#define VAD_FLAG_NO_LSTM_WAVEFRONT 2 /* one launch per ConvLSTM layer instead of the two-layer wavefront kernel */
+
+/* ConvAutoencoder — reference models/autoencoder.py:24-221 */
+typedef struct vad_image_model {
+  int has_encoder, has_decoder, flags, reserved;
+  vad_first_weights enc1_0; /* encoder.enc1.0 (+BN .1) */
+  vad_gemm_weights enc[7];  /* enc1.3, enc2.0, enc2.3, enc3.0, enc3.3, enc4.0, enc4.3 */
+  vad_gemm_weights dec[8];  /* dec1.0 (ConvT), dec1.3, dec2.0, dec2.3, dec3.0, dec3.3, dec4.0, dec4.3 (-> 3 ch, n_total 16) */
+} vad_image_model;
+
+/* VideoAutoencoder — reference models/video_autoencoder.py:24-384 */
+#define VAD_MAX_LSTM_LAYERS 8
+typedef struct vad_video_model {
+  int has_encoder, lstm_layers, has_proj, has_decoder, flags, reserved;
+  vad_first_weights enc0;                     /* encoder.encoder.0 (+BN .1, pooled) */
+  vad_gemm_weights enc[3];                    /* encoder.encoder.4 / .8 / .12 */
+  vad_gemm_weights lstm[VAD_MAX_LSTM_LAYERS]; /* convlstm.cells.i.conv, gate rows permuted (see _prepare.py) */
+  vad_gemm_weights proj;                      /* 1x1 conv when lstm_hidden_dim != latent_dim */
+  vad_gemm_weights dec[4];                    /* decoder.decoder.0 / .3 / .6 / .9 (-> 3 ch, n_total 16) */
+} vad_video_model;
+
+enum vad_op {
+  VAD_OP_FORWARD = 0,       /* vad_image_forward / vad_video_forward */
+  VAD_OP_ENCODE = 1,        /* vad_image_forward with only `latent` requested / vad_video_encode */
+  VAD_OP_DECODE = 2,        /* vad_image_decode / vad_video_decode */
+  VAD_OP_CONVLSTM = 3,      /* vad_convlstm_forward */
+  VAD_OP_SCORE_LATENTS = 4  /* vad_video_score_latents */
+};
+/* Workspace the given entry point needs for this shape (T ignored by the image model); 0 = invalid arguments. */
+size_t vad_image_workspace_bytes(const vad_image_model* m, int op, int B, int H, int W);
+size_t vad_video_workspace_bytes(const vad_video_model* m, int op, int B, int T, int H, int W);
+
+/* ConvAutoencoder.forward / get_latent / get_reconstruction_error in one pass — models/autoencoder.py:181-221.
+ * x fp32 [B,3,H,W].  Every output is optional (NULL = not produced; the reconstruction then never reaches HBM):
+ *   recon fp32 [B,3,H,W] · latent fp32 [B,latent,H/16,W/16] · score fp32 [B] (mean over C,H,W of (x-recon)^2) ·
+ *   minmax fp32 [B][2] (min / max of the per-pixel map) · heat fp32 [B,H,W] (the `per_pixel=True` map).
+ * Only `latent` requested: the encoder alone runs (Encoder.forward, :81-86). */
+int vad_image_forward(const vad_image_model* m, const float* x, int B, int H, int W, float* recon, float* latent,
+                      float* score, float* minmax, float* heat, void* ws, size_t ws_bytes, vad_stream_t stream);
+/* Decoder.forward — models/autoencoder.py:141-146: z fp32 [B,latent,h,w] -> recon fp32 [B,3,16h,16w]. */
+int vad_image_decode(const vad_image_model* m, const float* z, int B, int h, int w, float* recon, void* ws,
+                     size_t ws_bytes, vad_stream_t stream);
+
+/* VideoAutoencoder.forward / get_reconstruction_error in one pass — models/video_autoencoder.py:329-384.
+ * x fp32 [B,T,3,H,W]; recon fp32 [B,T,3,H,W], score fp32 [B*T] per frame, minmax fp32 [B*T][2], heat fp32 [B*T,H,W]
+ * (all optional).  The per-sequence score is the mean of a clip's frame scores (equal-sized frames).  The ConvLSTM
+ * starts from the zero state for every call (:144-145); batches whose recurrent tiles exceed the SM count are run
+ * in resident-size groups of clips. */
+int vad_video_forward(const vad_video_model* m, const float* x, int B, int T, int H, int W, float* recon, float* score,
+                      float* minmax, float* heat, void* ws, size_t ws_bytes, vad_stream_t stream);
+/* VideoEncoder.forward — :217-231: frames fp32 [F,3,H,W] -> latent fp32 [F,latent,H/16,W/16] and / or the bf16 NHWC
+ * [F,H/16,W/16,latent] tensor vad_video_score_latents consumes (either may be NULL). */
+int vad_video_encode(const vad_video_model* m, const float* x, int F, int H, int W, float* latent, void* latent_bf16,
+                     void* ws, size_t ws_bytes, vad_stream_t stream);
+/* ConvLSTM -> proj -> decoder -> scoring from cached encoder features (overlap-aware streaming):
+ * z bf16 NHWC [B,T,h,w,latent], x fp32 [B,T,3,16h,16w]; outputs as vad_video_forward. */
+int vad_video_score_latents(const vad_video_model* m, const void* z_bf16, const float* x, int B, int T, int h, int w,
+                            float* recon, float* score, float* minmax, float* heat, void* ws, size_t ws_bytes,
+                            vad_stream_t stream);
+/* VideoDecoder.forward — :263-276: z fp32 [F,latent,h,w] -> recon fp32 [F,3,16h,16w]. */
+int vad_video_decode(const vad_video_model* m, const float* z, int F, int h, int w, float* recon, void* ws,
+                     size_t ws_bytes, vad_stream_t stream);
+/* ConvLSTM.forward (zero initial state, last layer's outputs) — :127-172: x fp32 [B,T,C,h,w] -> out fp32 [B,T,hid,h,w];
+ * optional final state of the last layer: h_last, c_last fp32 [B,hid,h,w]. */
+int vad_convlstm_forward(const vad_video_model* m, const float* x, int B, int T, int h, int w, float* out,
+                         float* h_last, float* c_last, void* ws, size_t ws_bytes, vad_stream_t stream);
+/* ConvLSTMCell.forward(x, (h, c)) -> (h_next, c_next) — :54-85.  One gate GEMM with the state update in its epilogue;
+ * x fp32 [B,cin,h,w], h_cur / c_cur / h_next / c_next fp32 [B,hid,h,w] (h is rounded to bf16, the MMA operand type). */
+size_t vad_convlstm_cell_workspace_bytes(const vad_gemm_weights* cell, int B, int h, int w);
+int vad_convlstm_cell(const vad_gemm_weights* cell, const float* x, const float* h_cur, const float* c_cur, int B,
+                      int h, int w, float* h_next, float* c_next, void* ws, size_t ws_bytes, vad_stream_t stream);
+
+/* Per-layer timing of the model-level calls (bench.py's roofline): while enabled every layer launch is bracketed by
+ * CUDA events on the call's stream.  vad_profile_dump synchronises those events, writes "name\tms\n" lines (in launch
+ * order) into buf, clears the log and returns the number of bytes written (excluding the NUL), or a negative error. */
+int vad_profile_enable(int on);
+int vad_profile_dump(char* buf, size_t buf_bytes);
 
 #ifdef __cplusplus
 }

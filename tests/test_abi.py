@@ -33,19 +33,62 @@ def test_header_and_binding_agree(lib):
 
 
 def test_struct_layout_matches_c(tmp_path, lib):
-    """sizeof/offsetof of vad_conv_desc as the C compiler sees it == the ctypes mirror."""
+    """sizeof/offsetof of every ABI struct as the C compiler sees it == the ctypes mirror."""
     import subprocess
-    from models._native import ConvDesc
+    from models import _native as nat
+    structs = [("vad_conv_desc", nat.ConvDesc), ("vad_gemm_weights", nat.GemmW), ("vad_first_weights", nat.FirstW),
+               ("vad_image_model", nat.ImageModel), ("vad_video_model", nat.VideoModel)]
+    body = ""
+    for cname, cls in structs:
+        body += f'printf("%zu\\n", sizeof({cname}));'
+        body += "".join(f'printf("%zu\\n", offsetof({cname}, {f[0]}));' for f in cls._fields_)
     prog = tmp_path / "sz.c"
-    fields = [f[0] for f in ConvDesc._fields_]
-    body = "".join(f'printf("%zu\\n", offsetof(vad_conv_desc, {f}));' for f in fields)
     prog.write_text('#include "vad_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
-                    f'int main(){{printf("%zu\\n", sizeof(vad_conv_desc));{body}return 0;}}')
+                    f'int main(){{{body}return 0;}}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert vals[0] == ctypes.sizeof(ConvDesc)
-    assert vals[1:] == [getattr(ConvDesc, f).offset for f in fields]
+    want = []
+    for _, cls in structs:
+        want.append(ctypes.sizeof(cls))
+        want += [getattr(cls, f[0]).offset for f in cls._fields_]
+    assert vals == want
+
+
+def test_model_entry_points_reject_bad_arguments(lib):
+    """Model-level entries: argument errors are codes, the workspace query needs no GPU."""
+    from models import _native as nat
+    m = nat.ImageModel()
+    assert lib.vad_image_workspace_bytes(ctypes.byref(m), nat.OP_FORWARD, 4, 64, 64) == 0      # no weights
+    assert lib.vad_image_forward(ctypes.byref(m), None, 4, 64, 64, None, None, None, None, None, None, 0, None) == -1
+    v = nat.VideoModel()
+    assert lib.vad_video_workspace_bytes(ctypes.byref(v), nat.OP_FORWARD, 1, 4, 64, 64) == 0
+    assert lib.vad_video_forward(ctypes.byref(v), None, 1, 4, 64, 64, None, None, None, None, None, 0, None) == -1
+    assert lib.vad_profile_enable(0) in (0, 1)
+    buf = ctypes.create_string_buffer(64)
+    assert lib.vad_profile_dump(buf, 64) == 0
+
+
+def test_workspace_query_matches_the_schedule(lib):
+    """vad_*_workspace_bytes on real (CPU-resident) prepared weights: pointers are only stored, nothing is launched.
+    cfg2: two ping-pong regions (1.07 GB for enc1.0's output + 0.27 GB) and the score partials — not the sum of all
+    layer outputs (2.9 GB)."""
+    import torch
+    from models import _engine as eng, _native as nat, _prepare as prep
+    from models import ConvAutoencoder
+    from models.video_autoencoder import VideoAutoencoder
+    torch.manual_seed(0)
+    ie = eng.ImageEngine(prep.prepare_image(ConvAutoencoder().state_dict()))
+    full = ie._ws(nat.OP_FORWARD, 256, 256, 256)
+    assert 1.3e9 < full < 1.45e9, full
+    assert ie._ws(nat.OP_ENCODE, 256, 256, 256) <= full
+    assert ie._ws(nat.OP_FORWARD, 1, 40, 64) == 0                                               # H not a multiple of 16
+    small = ie._ws(nat.OP_FORWARD, 2, 32, 32)
+    assert 0 < small < 1 << 20
+    ve = eng.VideoEngine(prep.prepare_video(VideoAutoencoder().state_dict()))
+    w = ve._ws(nat.OP_FORWARD, 1, 64, 720, 1280)
+    assert 1.4e9 < w < 1.8e9, w
+    assert 0 < ve._ws(nat.OP_SCORE_LATENTS, 1, 16, 8, 8) < ve._ws(nat.OP_FORWARD, 1, 16, 128, 128)
 
 
 def test_argument_errors_are_codes_not_crashes(lib):

@@ -1,0 +1,107 @@
+"""INTEGRATION.md §2 as an executed test: the reference's own evaluation code, unmodified, runs on the drop-in classes.
+
+Checkpoints are written by the REFERENCE classes (`torch.save` of their `state_dict`, as train.py / train_video.py do);
+then the reference's `evaluate.load_model` + `evaluate.compute_auroc` (evaluate.py:26-91) and the whole
+`evaluate_video.evaluate` (evaluate_video.py:69-248: checkpoint load, IPADDataset + DataLoader, the scoring loop
+:138-154, AUROC, generate_visualizations) are executed twice from `baseline/_ref` (a byte-for-byte copy made by
+tools/vendor_ref.sh, checked against its SHA256SUMS):
+
+  * with the reference's `models` package on the CPU            -> ground truth
+  * with `video-anomaly-detection_b200/models` first on the path -> the sm_100a kernels on the GPU
+
+and the observables north_star names are compared: AUROC to 3 decimals, scores within 1e-3 relative, identical
+`score > 0.004` and `score > mean + 2 std` flags, identical ranking of pairs the reference separates.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import vad_oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+PKG = os.path.join(ROOT, "video-anomaly-detection_b200")
+RUNNER = os.path.join(ROOT, "tests", "dropin_runner.py")
+
+
+def _run(pythonpath, *args, env_extra=None):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join(pythonpath)
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    env.update(env_extra or {})
+    p = subprocess.run([sys.executable, RUNNER, *args], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, f"{args}: rc={p.returncode}\n{p.stdout[-3000:]}\n{p.stderr[-3000:]}"
+    return p
+
+
+@pytest.fixture(scope="module")
+def dropin_results(tmp_path_factory, cuda_device):
+    if not os.path.isdir(os.path.join(REF, "models")):
+        pytest.fail("baseline/_ref is missing: run tools/vendor_ref.sh in the build container (build() does) — the "
+                    "reference's own evaluation code is the harness of this test")
+    # the vendored copy is the unmodified reference
+    for line in open(os.path.join(REF, "SHA256SUMS")):
+        digest, name = line.split()
+        assert hashlib.sha256(open(os.path.join(REF, name), "rb").read()).hexdigest() == digest, name
+    work = str(tmp_path_factory.mktemp("dropin"))
+    _run([REF], "make", work)
+    _run([REF], "eval", work, os.path.join(work, "ref.json"), "--device", "cpu", env_extra={"CUDA_VISIBLE_DEVICES": ""})
+    _run([PKG, REF], "eval", work, os.path.join(work, "ours.json"), "--device", "cuda")
+    ref = json.load(open(os.path.join(work, "ref.json")))
+    ours = json.load(open(os.path.join(work, "ours.json")))
+    return ref, ours
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-30)))
+
+
+def test_reference_callers_load_the_dropin(dropin_results):
+    ref, ours = dropin_results
+    assert "baseline/_ref/models" in ref["models_file"]
+    assert "video-anomaly-detection_b200/models" in ours["models_file"]         # `from models import ConvAutoencoder`
+    assert "video-anomaly-detection_b200/models" in ours["image_init"]["model_file"]
+    assert "baseline/_ref/evaluate.py" in ours["evaluate_file"]                  # ... inside the reference's own script
+    assert ours["device"] == "cuda" and ref["device"] == "cpu"
+
+
+@pytest.mark.parametrize("tag,rtol,gap", [("image_init", 1e-3, 1e-5), ("image_stress", 1e-3, 1e-3)])
+def test_reference_compute_auroc_on_dropin(dropin_results, tag, rtol, gap):
+    """evaluate.load_model + evaluate.compute_auroc (evaluate.py:26-91) on the repo's synthetic test set (config 1)."""
+    ref, ours = dropin_results
+    r, o = ref[tag], ours[tag]
+    assert r["labels"] == o["labels"] and len(r["scores"]) == 30
+    print(f"\n{tag}: AUROC ref {r['auroc']:.4f} ours {o['auroc']:.4f}; score rel err {_rel(o['scores'], r['scores']):.3g}")
+    assert round(r["auroc"], 3) == round(o["auroc"], 3)
+    if tag == "image_init":
+        assert round(o["auroc"], 3) == 0.615                                     # SURVEY §6 [measured], goldens
+    assert _rel(o["scores"], r["scores"]) <= rtol
+    assert np.array_equal(vad_oracle.image_flags(o["scores"]), vad_oracle.image_flags(r["scores"]))   # main.py:282
+    assert np.array_equal(vad_oracle.video_flags(o["scores"]), vad_oracle.video_flags(r["scores"]))   # main.py:375-376
+    checked, bad = vad_oracle.tie_aware_rank_agreement(r["scores"], o["scores"], rel_gap=gap)
+    assert checked > 100 and bad == 0
+    for k, v in r["defects"].items():
+        assert abs(o["defects"][k] - v) <= rtol * abs(v)
+
+
+def test_reference_evaluate_video_on_dropin(dropin_results):
+    """The whole of evaluate_video.evaluate (evaluate_video.py:69-248), stress weights, IPAD-format clips at 256x256."""
+    ref, ours = dropin_results
+    r, o = ref["video_stress"], ours["video_stress"]
+    assert r["labels"] == o["labels"] and len(r["scores"]) == 8 and sum(r["labels"]) == 2
+    print(f"\nvideo: AUROC ref {r['auroc']:.4f} ours {o['auroc']:.4f}; sequence-score rel err "
+          f"{_rel(o['scores'], r['scores']):.3g}")
+    assert round(r["auroc"], 3) == round(o["auroc"], 3)
+    assert _rel(o["scores"], r["scores"]) <= 2e-3
+    assert np.array_equal(vad_oracle.video_flags(o["scores"]), vad_oracle.video_flags(r["scores"]))
+    checked, bad = vad_oracle.tie_aware_rank_agreement(r["scores"], o["scores"], rel_gap=5e-3)
+    assert checked >= 20 and bad == 0
+    assert "Sequence-level AUROC" in o["results_txt"]                            # the reference wrote its own report

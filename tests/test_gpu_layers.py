@@ -15,7 +15,7 @@ OUT_ATOL = 2e-2
 
 
 def _mods():
-    from models import _engine as eng
+    from models import _layers as eng
     from models import _native as nat
     from models import _prepare as prep
     return eng, nat, prep
@@ -422,8 +422,8 @@ def test_standalone_score_and_heatmap_u8(cuda_device, N, H, W):
     e = heat.cpu().numpy()
     import numpy as np
     ref_u8 = np.stack([(((m - m.min()) / (m.max() - m.min() + 1e-8)) * 255).astype(np.uint8) for m in e])
-    diff = np.abs(ref_u8.astype(np.int32) - u8.cpu().numpy().astype(np.int32))
-    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    # byte output: bit-exact (the kernel performs numpy's four fp32 operations, each correctly rounded, then truncates)
+    assert np.array_equal(ref_u8, u8.cpu().numpy())
 
 
 def test_layout_round_trip(cuda_device):

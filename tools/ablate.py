@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "video-anomaly-detection_b200"))
 import torch  # noqa: E402
-from models import _engine as eng, _prepare as prep  # noqa: E402
+from models import _layers as eng, _prepare as prep  # noqa: E402
 
 cin, cout, H, W, B, pool = (int(v) for v in (sys.argv[1:7] + ["32", "32", "256", "256", "256", "1"][len(sys.argv) - 1:]))
 dev = torch.device("cuda:0")

@@ -28,7 +28,7 @@ def summarize(name, got, ref):
 def run_stage(stage):
     import torch
     import torch.nn.functional as F
-    from models import _engine as eng, _native as nat, _prepare as prep
+    from models import _layers as eng, _native as nat, _prepare as prep
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
 

@@ -5,7 +5,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "video-anomaly-detection_b200"))
 import torch  # noqa: E402
-from models import _engine as eng, _native as nat, _prepare as prep  # noqa: E402
+from models import _layers as eng, _native as nat, _prepare as prep  # noqa: E402
 
 # needs a library built with the stamps compiled in:  python video-anomaly-detection_b200/build.py --timeline
 B, H, W, pool = 64, 256, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 0

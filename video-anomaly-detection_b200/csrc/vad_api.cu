@@ -1,6 +1,7 @@
 // C-ABI entry points of libvad_b200.so (see include/vad_b200.h) and the small CUDA-core kernels around the
 // tcgen05 GEMM: first 3-channel convolution, standalone scoring pass, score finalisation, layout helpers.
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,28 +17,47 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // Host-mapped slot a timed-out mbarrier wait writes before trapping (readable even after the context is poisoned).
+// All per-device state (the trap slot's device symbol, the SM count, constant-memory tables) is cached per device index,
+// so a process that drives several GPUs gets each of them set up (the caller makes the tensors' device current).
+constexpr int kMaxDevices = 64;
+static int current_device_index() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+static std::mutex g_setup_mutex;
 static unsigned long long* g_trap_host = nullptr;
+static std::atomic<bool> g_trap_ready[kMaxDevices];
 static void ensure_trap_slot() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  unsigned long long* h = nullptr;
-  if (cudaHostAlloc(reinterpret_cast<void**>(&h), 4 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) return;
-  std::memset(h, 0, 4 * sizeof(unsigned long long));
-  unsigned long long* d = nullptr;
-  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) return;
-  if (set_trap_slot(d) == 0) g_trap_host = h;
+  const int dev = current_device_index();
+  if (g_trap_ready[dev].load(std::memory_order_acquire)) return;
+  std::lock_guard<std::mutex> lock(g_setup_mutex);
+  if (g_trap_ready[dev].load(std::memory_order_relaxed)) return;
+  if (!g_trap_host) {  // one host-mapped record shared by all devices (portable pinned memory)
+    unsigned long long* h = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 4 * sizeof(unsigned long long),
+                      cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      std::memset(h, 0, 4 * sizeof(unsigned long long));
+      g_trap_host = h;
+    }
+  }
+  if (g_trap_host) {
+    unsigned long long* d = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), g_trap_host, 0) == cudaSuccess) set_trap_slot(d);
+  }
+  g_trap_ready[dev].store(true, std::memory_order_release);
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device_index();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -403,8 +423,10 @@ __global__ void heatmap_u8_kernel(const float* __restrict__ heat, const float* _
   if (i >= total) return;
   const long long f = i / plane;
   const float mn = minmax[2 * f], mx = minmax[2 * f + 1];
-  const float norm = (heat[i] - mn) / (mx - mn + 1e-8f);
-  out[i] = static_cast<uint8_t>(norm * 255.f);
+  // numpy float32 semantics of evaluate_video.py:56-57, one correctly rounded operation each (no contraction, no
+  // reciprocal tricks): the bytes are bit-exact against `((e - e.min()) / (e.max() - e.min() + 1e-8) * 255).astype(uint8)`
+  const float norm = __fdiv_rn(__fsub_rn(heat[i], mn), __fadd_rn(__fsub_rn(mx, mn), 1e-8f));
+  out[i] = static_cast<uint8_t>(__fmul_rn(norm, 255.f));
 }
 
 // ------------------------------------------------------------------------------------------------ frame I/O helpers
@@ -493,8 +515,8 @@ __global__ void __launch_bounds__(256) heatmap_jet_kernel(const float* __restric
   if (i >= total) return;
   const long long f = i / plane;
   const float mn = minmax[2 * f], mx = minmax[2 * f + 1];
-  const float norm = (heat[i] - mn) / (mx - mn + 1e-8f);
-  const uint32_t c = c_jet_rgb[static_cast<uint8_t>(norm * 255.f)];
+  const float norm = __fdiv_rn(__fsub_rn(heat[i], mn), __fadd_rn(__fsub_rn(mx, mn), 1e-8f));  // as heatmap_u8_kernel
+  const uint32_t c = c_jet_rgb[static_cast<uint8_t>(__fmul_rn(norm, 255.f))];
   out[i * 3 + 0] = static_cast<uint8_t>(c);
   out[i * 3 + 1] = static_cast<uint8_t>(c >> 8);
   out[i * 3 + 2] = static_cast<uint8_t>(c >> 16);
@@ -1028,7 +1050,8 @@ int vad_convt_conv_score_tiles(const vad_conv_desc* d) {
 
 // Validates one ConvLSTM layer description and fills the kernel argument block; `patch_ok` tells whether the arguments
 // were set up for the persistent patch kernel (every tile has its own resident CTA, tile shapes apply, mode 1).
-static int build_lstm_layer(const vad_conv_desc* d, int T, ConvLaunch& L, bool& patch_ok, int& seq) {
+static int build_lstm_layer(const vad_conv_desc* d, int T, ConvLaunch& L, bool& patch_ok, int& seq,
+                            bool allow_patch = true) {
   // d describes a generic step t >= 1: src0 = layer input sequence [B][T][h][w][c0], src1 = out = hidden sequence
   // [B][T][h][w][hid] (step t reads h_{t-1} from it and writes h_t into it), c_state fp32 [B][h][w][hid].
   patch_ok = false;
@@ -1054,7 +1077,7 @@ static int build_lstm_layer(const vad_conv_desc* d, int T, ConvLaunch& L, bool& 
   seq = g_lstm_mode_override >= 0 ? g_lstm_mode_override : seq_env;
   // Patch variant (A operand through one patch per chunk, weights through their own ring): 8x8 frames (two per tile) or
   // tiles of 8 x 16 pixels inside larger frames.  VAD_LSTM_SEQ=2 disables it (streaming sequence kernel instead).
-  if (seq == 1 && a.tma_store && L.CK == 64 && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
+  if (allow_patch && seq == 1 && a.tma_store && L.CK == 64 && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
     const bool geo1 = d->H == 8 && d->W == 8;
     const bool geo2 = !geo1 && d->H >= 8 && d->W >= 8;
     TileGeom g;
@@ -1114,7 +1137,8 @@ int vad_convlstm2_sequence(const vad_conv_desc* d1, const vad_conv_desc* d2, int
   rc = build_lstm_layer(d2, T, L2, ok2, seq);
   if (rc != VAD_OK) return rc;
   if (!ok1 || !ok2 || L1.a.total_tiles != L2.a.total_tiles || L1.a.n_tiles != L2.a.n_tiles) return VAD_ERR_UNSUPPORTED;
-  return launch_convlstm2_patch(L1.a, L2.a, T, L1.a.total_tiles, static_cast<cudaStream_t>(stream_));
+  return launch_convlstm2_patch(L1.a, L2.a, T, L1.a.total_tiles, static_cast<unsigned int*>(d1->scratch),
+                                static_cast<cudaStream_t>(stream_));
 }
 
 int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
@@ -1127,10 +1151,16 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   const long long step_elems = static_cast<long long>(d->H) * d->W * d->out_cpitch;
   const int chunks1 = a.chunks1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (patch_ok) return launch_convlstm_patch(a, T, a.total_tiles, stream);
-  if (seq && a.tma_store && a.total_tiles <= sm_count() && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
+  unsigned int* counters = static_cast<unsigned int*>(d->scratch);
+  if (patch_ok) {
+    rc = launch_convlstm_patch(a, T, a.total_tiles, counters, stream);
+    if (rc != VAD_ERR_UNSUPPORTED) return rc;  // (unsupported = the grid cannot be co-resident here: per-step launches)
+    rc = build_lstm_layer(d, T, L, patch_ok, seq, /*allow_patch=*/false);  // back to the per-step tile geometry / maps
+    if (rc != VAD_OK) return rc;
+  } else if (seq && a.tma_store && a.total_tiles <= sm_count() && T <= 4096 && !L.use_halo && !L.use_kx && !L.use_hs) {
     a.out = d->out;
-    return launch_convlstm_seq(L.CK, a, T, a.total_tiles, stream);
+    rc = launch_convlstm_seq(L.CK, a, T, a.total_tiles, counters, stream);
+    if (rc != VAD_ERR_UNSUPPORTED) return rc;
   }
   static const int pdl = env_int("VAD_PDL", 1);  // 0: plain stream order between the steps
   for (int t = 0; t < T; ++t) {
@@ -1345,8 +1375,9 @@ int vad_ssim_loss(const float* pred, const float* target, int frames, int H, int
                   void* scratch, vad_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!pred || !target || !loss || !scratch || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
-  static bool window_ready = false;
-  if (!window_ready) {  // the reference's window: normalised exp(-x^2 / (2 * 1.5^2)), x = -5..5 (utils/losses.py:38-41)
+  static std::atomic<bool> window_ready[kMaxDevices];  // __constant__ memory is per device
+  const int dev_index = current_device_index();
+  if (!window_ready[dev_index].load(std::memory_order_acquire)) {  // the reference's window: normalised exp(-x^2 / (2 * 1.5^2)), x = -5..5 (utils/losses.py:38-41)
     float g[11], sum = 0.f;
     for (int i = 0; i < 11; ++i) {
       const float x = static_cast<float>(i - 5);
@@ -1356,7 +1387,7 @@ int vad_ssim_loss(const float* pred, const float* target, int frames, int H, int
     for (int i = 0; i < 11; ++i) g[i] /= sum;
     cudaError_t e = cudaMemcpyToSymbol(c_ssim_gauss, g, sizeof(g));
     if (e != cudaSuccess) return static_cast<int>(e);
-    window_ready = true;
+    window_ready[dev_index].store(true, std::memory_order_release);
   }
   const int tiles_x = (W + kSsimTile - 1) / kSsimTile, tiles_y = (H + kSsimTile - 1) / kSsimTile;
   const long long blocks = static_cast<long long>(tiles_x) * tiles_y * 3 * frames;
@@ -1376,3 +1407,19 @@ int vad_ssim_loss(const float* pred, const float* target, int frames, int H, int
 }  // extern "C"
 
 
+
+namespace vad {
+int lstm_persistent_tiles(int B, int H, int W, int c0, int c1, int n_total) {
+  const int n_tiles = n_total / 128 > 0 ? n_total / 128 : 1;
+  static const int seq_env = env_int("VAD_LSTM_SEQ", 1);
+  const int mode = g_lstm_mode_override >= 0 ? g_lstm_mode_override : seq_env;
+  if (mode == 1 && c0 % 64 == 0 && c1 % 64 == 0 && H >= 8 && W >= 8) {  // patch kernel (build_lstm_layer)
+    const bool geo1 = H == 8 && W == 8;
+    const int tiles_w = (W + 7) >> 3;
+    const int tiles_h = geo1 ? 1 : (H + 15) >> 4;
+    const int tiles_b = geo1 ? (B + 1) >> 1 : B;
+    return tiles_w * tiles_h * tiles_b * n_tiles;
+  }
+  return pick_tile_geometry(B, H, W, false).m_tiles() * n_tiles;
+}
+}  // namespace vad

@@ -32,6 +32,8 @@
 // models/autoencoder.py:104-134 and models/video_autoencoder.py:244-259; ConvLSTMCell.forward
 // models/video_autoencoder.py:54-85; the error reduction models/autoencoder.py:214-221 and
 // models/video_autoencoder.py:371-384 (fused onto the last decoder layer).
+#include <atomic>
+
 #include "vad_internal.h"
 #include "vad_ptx.cuh"
 
@@ -1390,7 +1392,7 @@ __global__ void __launch_bounds__(256, 1) convlstm_seq_kernel(const __grid_const
           if (lane == 0) {
             const long long t0 = clock64();
             while (ld_acquire_gpu(step_counter) < target) {
-              if (clock64() - t0 > 2000000000LL) {
+              if (clock64() - t0 > VAD_WAIT_TIMEOUT_CLOCKS) {
                 if (g_vad_trap_slot) {
                   g_vad_trap_slot[0] = 11;
                   g_vad_trap_slot[1] = blockIdx.x;
@@ -1622,7 +1624,7 @@ __global__ void __launch_bounds__(384, 1) convlstm_patch_kernel(const __grid_con
           if (lane == 0) {
             const long long t0 = clock64();
             while (ld_acquire_gpu(step_counter) < target) {
-              if (clock64() - t0 > 2000000000LL) {
+              if (clock64() - t0 > VAD_WAIT_TIMEOUT_CLOCKS) {
                 if (g_vad_trap_slot) {
                   g_vad_trap_slot[0] = 12;
                   g_vad_trap_slot[1] = blockIdx.x;
@@ -1814,7 +1816,7 @@ __device__ __forceinline__ void lstm_wait_counter(const unsigned int* counter, u
   if (lane == 0) {
     const long long t0 = clock64();
     while (ld_acquire_gpu(counter) < target) {
-      if (clock64() - t0 > 2000000000LL) {
+      if (clock64() - t0 > VAD_WAIT_TIMEOUT_CLOCKS) {
         if (g_vad_trap_slot) {
           g_vad_trap_slot[0] = static_cast<unsigned long long>(tag);
           g_vad_trap_slot[1] = blockIdx.x;
@@ -2880,6 +2882,53 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
 // while its predecessor in the stream is still draining; every kernel launched this way runs its prologue (barrier
 // init, TMEM allocation, descriptor prefetch, bias load — constants only) and then `griddepcontrol.wait`s before it
 // touches anything the predecessor wrote.
+// Per-device launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) setting, so
+// the "already configured" caches are indexed by the current device; a second GPU used from the same process gets its
+// own configuration call instead of failing its first >48 KB launch.
+constexpr int kMaxDevices = 64;
+static int current_device_index() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+struct SmemConfig {
+  std::atomic<int> bytes[kMaxDevices];  // largest dynamic shared-memory size configured so far (zero-initialised statics)
+};
+template <typename Kernel>
+static int ensure_smem(Kernel kernel, SmemConfig& c, int smem) {
+  std::atomic<int>& cur = c.bytes[current_device_index()];
+  if (smem <= cur.load(std::memory_order_acquire)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int prev = cur.load(std::memory_order_relaxed);
+  while (prev < smem && !cur.compare_exchange_weak(prev, smem, std::memory_order_release)) {}
+  return 0;
+}
+
+// Cooperative launch: the driver either makes every CTA of the grid resident at once or fails the launch
+// (cudaErrorCooperativeLaunchTooLarge); two such grids on different streams are serialised instead of interleaved.  The
+// persistent ConvLSTM kernels spin on a grid-wide step counter, which is only safe under that guarantee.
+template <typename Kernel, typename... Args>
+static int launch_cooperative(Kernel kernel, int grid, int block, int smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    (void)cudaGetLastError();  // not sticky: the caller falls back to one launch per step
+    return VAD_ERR_UNSUPPORTED;
+  }
+  return static_cast<int>(e);
+}
+
 template <typename Kernel>
 static int launch_conv_kernel(Kernel kernel, const ConvArgs& a, int grid, int block, int smem, cudaStream_t stream) {
   count_launch();
@@ -2903,32 +2952,20 @@ static int launch_conv_kernel(Kernel kernel, const ConvArgs& a, int grid, int bl
 template <int EPI>
 static int launch_first_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   constexpr int smem = 1024 + 2048 + kFirstStages * (kTileM * 64 + kPatchStride) + staging_bytes(32, EPI, kFirstGroupsC);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_first_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static SmemConfig cfg;
+  if (int e = ensure_smem(conv_first_kernel<EPI>, cfg, smem)) return e;
   return launch_conv_kernel(conv_first_kernel<EPI>, a, grid, kFirstThreads, smem, stream);
 }
 
 int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convt2_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static SmemConfig cfg;
+  if (int e = ensure_smem(convt2_score_kernel, cfg, kC2SmemBytes)) return e;
   return launch_conv_kernel(convt2_score_kernel, a, grid, kC2Threads, kC2SmemBytes, stream);
 }
 
 int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convt_conv_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kI2SmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static SmemConfig cfg;
+  if (int e = ensure_smem(convt_conv_score_kernel, cfg, kI2SmemBytes)) return e;
   return launch_conv_kernel(convt_conv_score_kernel, a, grid, kI2Threads, kI2SmemBytes, stream);
 }
 
@@ -2946,13 +2983,8 @@ int set_trap_slot(unsigned long long* device_ptr) {
 template <int CK, int BN, int EPI>
 static int launch_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   using C = Cfg<CK, BN, EPI>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CK, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static SmemConfig cfg;  // per instantiation
+  if (int e = ensure_smem(conv_umma_kernel<CK, BN, EPI>, cfg, C::kSmemBytes)) return e;
   return launch_conv_kernel(conv_umma_kernel<CK, BN, EPI>, a, grid, block_threads(BN, EPI), C::kSmemBytes, stream);
 }
 
@@ -2991,13 +3023,8 @@ static constexpr int halo_fixed_bytes() {
 template <int CK, int BN, int EPI>
 static int launch_halo_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   const int smem = halo_fixed_bytes<CK, BN, EPI>() + a.halo_stages * a.halo_patch_bytes * a.halo_npatch;
-  static int configured = 0;  // largest size configured so far, per instantiation
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CK, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = smem;
-  }
+  static SmemConfig cfg;  // per instantiation
+  if (int e = ensure_smem(conv_halo_kernel<CK, BN, EPI>, cfg, smem)) return e;
   return launch_conv_kernel(conv_halo_kernel<CK, BN, EPI>, a, grid, block_threads(BN), smem, stream);
 }
 
@@ -3036,12 +3063,8 @@ static constexpr int kx_fixed_bytes() {
 template <int CK, int BN, int EPI>
 static int launch_kx_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   const int smem = kx_fixed_bytes<CK, BN, EPI>() + a.halo_stages * (8 * 18 * CK * 2);
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_kx_kernel<CK, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = smem;
-  }
+  static SmemConfig cfg;
+  if (int e = ensure_smem(conv_kx_kernel<CK, BN, EPI>, cfg, smem)) return e;
   return launch_conv_kernel(conv_kx_kernel<CK, BN, EPI>, a, grid, 128 + 128 * kx_groups(BN, EPI), smem, stream);
 }
 
@@ -3075,12 +3098,8 @@ int launch_conv_kx(int CK, int BN, int EPI, const ConvArgs& a, int grid, cudaStr
 template <int EPI>
 static int launch_hs_one(const ConvArgs& a, int grid, cudaStream_t stream) {
   const int smem = 1024 + kHsBRing * kHsBBytes + a.halo_stages * kHsPatchPitch + 2 * staging_group_bytes(128, EPI);
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_hs_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = smem;
-  }
+  static SmemConfig cfg;
+  if (int e = ensure_smem(conv_hs_kernel<EPI>, cfg, smem)) return e;
   return launch_conv_kernel(conv_hs_kernel<EPI>, a, grid, 384, smem, stream);
 }
 
@@ -3097,79 +3116,61 @@ int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {
   return VAD_ERR_UNSUPPORTED;
 }
 
-// per-call step counters of the persistent ConvLSTM kernel (a rotating pool so that calls on different streams do not
-// share one; each call zeroes its slot on its own stream first)
-__device__ unsigned int g_lstm_counters[64];
+// Step counters of the persistent ConvLSTM kernels.  Callers that own scratch memory (the model-level entry points:
+// their workspace) pass `counters`; otherwise a slot of a rotating per-device pool is used (slot index taken atomically,
+// so concurrent host threads never share one).  Either way the counters are zeroed on the call's own stream first.
+__device__ unsigned int g_lstm_counters[256];
+static std::atomic<unsigned int> g_lstm_next_slot{0};
 
-template <int CK>
-static int launch_lstm_seq_one(const ConvArgs& a, int T, int grid, cudaStream_t stream) {
-  using C = Cfg<CK, 128, VAD_EPI_LSTM>;
-  constexpr int smem = C::kStages * C::kStageBytes + 8192 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_seq_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+static int lstm_counters(unsigned int* caller, int n, cudaStream_t stream, unsigned int** out) {
+  unsigned int* c = caller;
+  if (!c) {
+    unsigned int* base = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm_counters);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    c = base + 2 * (g_lstm_next_slot.fetch_add(1, std::memory_order_relaxed) & 127u);
   }
-  static unsigned int next_slot = 0;
-  unsigned int* base = nullptr;
-  cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm_counters);
+  cudaError_t e = cudaMemsetAsync(c, 0, n * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return static_cast<int>(e);
-  unsigned int* counter = base + (next_slot++ & 63u);
-  e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  convlstm_seq_kernel<CK><<<grid, 256, smem, stream>>>(a, T, counter);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  *out = c;
+  return 0;
 }
 
-int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t stream) {
-  if (CK == 64) return launch_lstm_seq_one<64>(a, T, grid, stream);
-  if (CK == 32) return launch_lstm_seq_one<32>(a, T, grid, stream);
+template <int CK>
+static int launch_lstm_seq_one(const ConvArgs& a, int T, int grid, unsigned int* counters, cudaStream_t stream) {
+  using C = Cfg<CK, 128, VAD_EPI_LSTM>;
+  constexpr int smem = C::kStages * C::kStageBytes + 8192 + 1024;
+  static SmemConfig cfg;
+  if (int e = ensure_smem(convlstm_seq_kernel<CK>, cfg, smem)) return e;
+  unsigned int* counter = nullptr;
+  if (int e = lstm_counters(counters, 1, stream, &counter)) return e;
+  return launch_cooperative(convlstm_seq_kernel<CK>, grid, 256, smem, stream, a, T, counter);
+}
+
+int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, unsigned int* counters, cudaStream_t stream) {
+  if (CK == 64) return launch_lstm_seq_one<64>(a, T, grid, counters, stream);
+  if (CK == 32) return launch_lstm_seq_one<32>(a, T, grid, counters, stream);
   return VAD_ERR_UNSUPPORTED;
 }
 
-int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t stream) {
+int launch_convlstm_patch(const ConvArgs& a, int T, int grid, unsigned int* counters, cudaStream_t stream) {
   constexpr int smem = kLpBRing * 128 * 128 + kLpPatches * kLpPatchPitch + 8192 + 1024;
   static_assert(smem <= kSmemBudget, "ConvLSTM patch kernel shared memory");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
-  static unsigned int next_slot = 32;
-  unsigned int* base = nullptr;
-  cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm_counters);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  unsigned int* counter = base + (next_slot++ & 63u);
-  e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  convlstm_patch_kernel<<<grid, 384, smem, stream>>>(a, T, counter);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  static SmemConfig cfg;
+  if (int e = ensure_smem(convlstm_patch_kernel, cfg, smem)) return e;
+  unsigned int* counter = nullptr;
+  if (int e = lstm_counters(counters, 1, stream, &counter)) return e;
+  return launch_cooperative(convlstm_patch_kernel, grid, 384, smem, stream, a, T, counter);
 }
 
-__device__ unsigned int g_lstm2_counters[64];  // pairs {layer 1, layer 2}, a rotating pool as above
-
-int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int grid, cudaStream_t stream) {
+int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int grid, unsigned int* counters,
+                           cudaStream_t stream) {
   constexpr int smem = kLpBRing * 128 * 128 + kLpPatches * kLpPatchPitch + 8192 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convlstm2_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
-  static unsigned int next_slot = 0;
-  unsigned int* base = nullptr;
-  cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_lstm2_counters);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  unsigned int* counters = base + 2 * (next_slot++ & 31u);
-  e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  convlstm2_patch_kernel<<<grid, 384, smem, stream>>>(a1, a2, T, counters);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  static SmemConfig cfg;
+  if (int e = ensure_smem(convlstm2_patch_kernel, cfg, smem)) return e;
+  unsigned int* pair = nullptr;  // {layer 1, layer 2}
+  if (int e = lstm_counters(counters, 2, stream, &pair)) return e;
+  return launch_cooperative(convlstm2_patch_kernel, grid, 384, smem, stream, a1, a2, T, pair);
 }
 
 }  // namespace vad

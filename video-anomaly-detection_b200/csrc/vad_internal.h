@@ -76,9 +76,13 @@ int kx_fixed_smem_bytes(int CK, int BN, int EPI);
 int kx_mma_columns(int BN, int EPI);
 int launch_conv_hs(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int hs_patch_stages(int EPI);
-int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, cudaStream_t stream);
-int launch_convlstm_patch(const ConvArgs& a, int T, int grid, cudaStream_t stream);
-int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int grid, cudaStream_t stream);
+// persistent ConvLSTM kernels (cooperative launches).  `counters`: device scratch for the grid-wide step counters (one
+// unsigned per layer; zeroed by the launcher on `stream`), or nullptr to take a slot of the library's rotating pool.
+// VAD_ERR_UNSUPPORTED when the grid cannot be co-resident on this device (callers fall back to one launch per step).
+int launch_convlstm_seq(int CK, const ConvArgs& a, int T, int grid, unsigned int* counters, cudaStream_t stream);
+int launch_convlstm_patch(const ConvArgs& a, int T, int grid, unsigned int* counters, cudaStream_t stream);
+int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int grid, unsigned int* counters,
+                           cudaStream_t stream);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream);
@@ -87,5 +91,9 @@ int halo_smem_bytes(int CK, int BN, int EPI, int patch_bytes_total, int stages);
 int set_trap_slot(unsigned long long* device_ptr);
 void count_launch();
 int sm_count();
+// M x N tiles (= CTAs) the persistent ConvLSTM path would use for a batch of B clips with an h x w latent: the patch
+// kernel's geometry where it applies, the generic one otherwise.  The model-level schedule splits batches whose tiles
+// exceed the SM count into resident-size groups of clips.
+int lstm_persistent_tiles(int B, int H, int W, int c0, int c1, int n_total);
 
 }  // namespace vad

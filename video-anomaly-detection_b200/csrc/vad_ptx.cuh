@@ -54,12 +54,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // (one copy per translation unit; vad_conv_umma.cu, which holds every waiting kernel, sets its own)
 static __device__ unsigned long long* g_vad_trap_slot = nullptr;
 
+// Every bounded wait gives up after this many SM clocks (~10 s at 2 GHz).  It only exists so that a protocol bug becomes a
+// reported error instead of a hung GPU; it is far above anything a legitimate wait can take (the persistent ConvLSTM
+// kernels are launched cooperatively, so the CTAs a grid-wide wait depends on are guaranteed to be resident).
+#ifndef VAD_WAIT_TIMEOUT_CLOCKS
+#define VAD_WAIT_TIMEOUT_CLOCKS 20000000000LL
+#endif
+
 // Bounded wait: a protocol bug becomes a trap (sticky CUDA error) instead of a hung GPU.  `tag` names the wait site.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {  // ~1 s at 2 GHz
+    if (clock64() - t0 > VAD_WAIT_TIMEOUT_CLOCKS) {
       if (g_vad_trap_slot) {
         g_vad_trap_slot[0] = tag;
         g_vad_trap_slot[1] = blockIdx.x;
@@ -106,7 +113,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
   while (!mbar_try_wait_a(bar, parity)) {
     // the clock is read every 256th poll only: the polling loops of idle warps were a quarter of all executed
     // instructions of the epilogue-heavy kernels (ncu source page), and they share the issue slots with the working warps
-    if ((++polls & 255u) == 0u && clock64() - t0 > 2000000000LL) {
+    if ((++polls & 255u) == 0u && clock64() - t0 > VAD_WAIT_TIMEOUT_CLOCKS) {
       if (g_vad_trap_slot) {
         g_vad_trap_slot[0] = tag;
         g_vad_trap_slot[1] = blockIdx.x;

@@ -1,8 +1,13 @@
-"""Layer schedules of the two autoencoders on top of libvad_b200 (one C-ABI call per fused layer).
+"""Binding of the model-level entry points of libvad_b200 (one C call per reference method).
 
-Activations are bf16 NHWC buffers cached per input shape; the model input `x` (fp32 NCHW) is read directly by the
-first conv kernel and again by the fused scoring epilogue of the last decoder layer, so the reconstruction itself
-only touches HBM when the caller asks for it.
+`ImageEngine` / `VideoEngine` own the prepared weights of one model (or of one stand-alone sub-module) as the
+`vad_image_model` / `vad_video_model` structs of include/vad_b200.h and turn each reference method into ONE call:
+the whole layer schedule is enqueued by the library on the current CUDA stream of the input's device.  PyTorch only
+provides device memory here: outputs are fresh tensors, and the per-call workspace (intermediate activations, score
+partials, ConvLSTM step counters) comes from torch's stream-aware caching allocator — so concurrent calls on different
+streams or threads never share a buffer, and nothing is cached per shape.
+
+There is no CPU fallback: CPU tensors, a missing library or unsupported shapes raise.
 """
 from __future__ import annotations
 
@@ -16,21 +21,13 @@ import torch
 from . import _native as nat
 from ._prepare import FirstConvWeights, GemmWeights
 
-LEAKY, RELU, IDENT = 0.2, 0.0, 1.0
-
-# bench.py sets this to a list to get (layer name, start event, end event) for every kernel launch
-PROFILE: Optional[list] = None
-
-
-def _timed(what: str, fn) -> None:
-    if PROFILE is None:
-        fn()
-        return
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fn()
-    e1.record()
-    PROFILE.append((what, e0, e1))
+# VAD_FUSE_DEC=0: run the decoders' last two layers one by one instead of the fused tail kernels
+# (video: vad_convt2_score, image: vad_convt_conv_score).  Tests flip the module attribute.
+FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
+# VAD_LSTM2=0: one launch per ConvLSTM layer instead of the two-layer wavefront kernel
+FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
+# VAD_FIRST_TC=0: CUDA-core first conv (fp32 operands) instead of the tensor-core one
+FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
 
 
 @dataclass
@@ -39,6 +36,7 @@ class ScoreOutputs:
     minmax: torch.Tensor                # [frames, 2] fp32: min / max of the per-pixel map (heat-map normalisation)
     heat: Optional[torch.Tensor]        # [frames, H, W] fp32 per-pixel channel-mean squared error
     recon: Optional[torch.Tensor]       # [frames, 3, H, W] fp32
+    latent: Optional[torch.Tensor] = None  # [frames, latent, H/16, W/16] fp32 (image model, on request)
 
 
 def _require_cuda_input(x: torch.Tensor, ndim: Tuple[int, ...]) -> torch.Tensor:
@@ -52,332 +50,279 @@ def _require_cuda_input(x: torch.Tensor, ndim: Tuple[int, ...]) -> torch.Tensor:
     return x.contiguous()
 
 
-class _Buffers:
-    """Shape-keyed cache of device buffers (the library itself never allocates)."""
-
-    def __init__(self) -> None:
-        self._bufs: Dict[Tuple, torch.Tensor] = {}
-
-    def get(self, name: str, shape: Tuple[int, ...], dtype: torch.dtype, device) -> torch.Tensor:
-        key = (name, tuple(shape), dtype, str(device))
-        t = self._bufs.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=dtype, device=device)
-            self._bufs[key] = t
-        return t
-
-
-def _gemm_desc(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: int, slope: float,
-                out: Optional[torch.Tensor], *, c0: int = 0, T0: int = 1, t0: int = 0, src1: Optional[torch.Tensor] = None,
-                c1: int = 0, T1: int = 1, t1: int = 0, out_frame_stride: int = 0, out_cpitch: int = 0,
-                out_offset_elems: int = 0, c_state: Optional[torch.Tensor] = None, lstm_first: bool = False,
-                x: Optional[torch.Tensor] = None, recon: Optional[torch.Tensor] = None,
-                heat: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None) -> "nat.ConvDesc":
-    d = nat.ConvDesc()
-    d.src0 = src.data_ptr()
-    d.src1 = nat.ptr(src1)
-    d.c0 = c0 if c0 else w.ctap  # channels read from source 0 (ConvLSTM: the x half of cat[x, h])
-    d.c1 = c1 if src1 is not None else 0
-    d.T0, d.T1, d.t0, d.t1 = T0, T1, t0, t1
-    d.B, d.H, d.W = B, H, W
-    d.ntaps = w.ntaps
-    d.weight = w.w.data_ptr()
-    d.weight_kx = nat.ptr(w.w_kx)
-    d.bias = w.bias.data_ptr()
-    d.w_ctap = w.ctap
-    d.n_total = w.n_total
-    d.cout = w.cout
-    d.epilogue = epi
-    d.slope = slope
-    if out is not None:
-        d.out = out.data_ptr() + out_offset_elems * out.element_size()
-    d.out_frame_stride = out_frame_stride
-    d.out_cpitch = out_cpitch
-    d.c_state = nat.ptr(c_state)
-    d.lstm_first = 1 if lstm_first else 0
-    d.x, d.recon, d.heat, d.partials = nat.ptr(x), nat.ptr(recon), nat.ptr(heat), nat.ptr(partials)
-    return d
-
-
-def _gemm_layer(w: GemmWeights, src: torch.Tensor, B: int, H: int, W: int, epi: int, slope: float,
-                out: Optional[torch.Tensor], *, what: str = "", **kw) -> None:
-    d = _gemm_desc(w, src, B, H, W, epi, slope, out, **kw)
-    _timed(what or "vad_conv_layer", lambda: nat.conv_layer(d, what or "vad_conv_layer"))
-
-
-def _score_layer(w: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int, epi: int, x: torch.Tensor,
-                 want_recon: bool, want_heat: bool, Ho: int, Wo: int, bufs: "_Buffers", what: str) -> "ScoreOutputs":
-    """Last decoder layer with the fused tanh + (x - recon)^2 reduction, then the per-frame finalisation."""
-    dev = x.device
-    recon = torch.empty(frames, 3, Ho, Wo, dtype=torch.float32, device=dev) if want_recon else None
-    heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
-    d = _gemm_desc(w, src, frames, H, W, epi, IDENT, None, x=x, recon=recon, heat=heat, partials=x)
-    tiles = nat.layer_tiles(d)  # the tiling (and so the number of per-tile partials) is the library's choice
-    partials = bufs.get("partials", (tiles, 4, 4), torch.float32, dev)  # one (sum, min, max, -) per tile and warp quarter
-    d.partials = partials.data_ptr()
-    _timed(what, lambda: nat.conv_layer(d, what))
-    score, minmax = _finalize(partials, frames, 4 * (tiles // frames), Ho, Wo, bufs, dev)
-    return ScoreOutputs(score, minmax, heat, recon)
-
-
-def _fused_tail(w6: GemmWeights, w9: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int, x: torch.Tensor,
-                want_recon: bool, want_heat: bool, Ho: int, Wo: int, bufs: "_Buffers") -> "ScoreOutputs":
-    """Video decoder.6 (ConvT 64->32 + BN + ReLU) + decoder.9 (ConvT 32->3 + Tanh) + scoring: `vad_convt2_score`."""
-    dev = x.device
-    recon = torch.empty(frames, 3, Ho, Wo, dtype=torch.float32, device=dev) if want_recon else None
-    heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
-    d = _gemm_desc(w6, src, frames, H, W, nat.EPI_CONVT, RELU, None, x=x, recon=recon, heat=heat, partials=x)
-    tiles = nat.load().vad_convt2_score_tiles(C.byref(d))
-    if tiles <= 0:
-        nat.check(tiles if tiles < 0 else -1, "vad_convt2_score_tiles")
-    partials = bufs.get("partials", (tiles, 4, 4), torch.float32, dev)
-    d.partials = partials.data_ptr()
-    _timed("decoder.6+9+score", lambda: nat.check(
-        nat.load().vad_convt2_score(C.byref(d), w9.w.data_ptr(), w9.bias.data_ptr(), nat.stream_ptr()),
-        "vad_convt2_score"))
-    score, minmax = _finalize(partials, frames, 4 * (tiles // frames), Ho, Wo, bufs, dev)
-    return ScoreOutputs(score, minmax, heat, recon)
-
-
-def _fused_image_tail(wt: GemmWeights, wc: GemmWeights, src: torch.Tensor, frames: int, H: int, W: int,
-                      x: torch.Tensor, want_recon: bool, want_heat: bool, bufs: "_Buffers") -> "ScoreOutputs":
-    """Image dec4.0 (ConvT 32->32 + BN + ReLU) + dec4.3 (Conv3x3 32->3 + Tanh) + scoring: `vad_convt_conv_score`.
-    src bf16 NHWC [frames,H,W,32]; x fp32 [frames,3,2H,2W]."""
-    dev = x.device
-    Ho, Wo = 2 * H, 2 * W
-    recon = torch.empty(frames, 3, Ho, Wo, dtype=torch.float32, device=dev) if want_recon else None
-    heat = torch.empty(frames, Ho, Wo, dtype=torch.float32, device=dev) if want_heat else None
-    d = _gemm_desc(wt, src, frames, H, W, nat.EPI_CONVT, RELU, None, x=x, recon=recon, heat=heat, partials=x)
-    tiles = nat.load().vad_convt_conv_score_tiles(C.byref(d))
-    if tiles <= 0:
-        nat.check(tiles if tiles < 0 else -1, "vad_convt_conv_score_tiles")
-    partials = bufs.get("partials", (tiles, 4, 4), torch.float32, dev)
-    d.partials = partials.data_ptr()
-    _timed("dec4.0+4.3+score", lambda: nat.check(
-        nat.load().vad_convt_conv_score(C.byref(d), wc.w_kx.data_ptr(), wc.bias.data_ptr(), nat.stream_ptr()),
-        "vad_convt_conv_score"))
-    score, minmax = _finalize(partials, frames, 4 * (tiles // frames), Ho, Wo, bufs, dev)
-    return ScoreOutputs(score, minmax, heat, recon)
-
-
-FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
-# VAD_FUSE_DEC=0: run the decoders' last two layers one by one (vad_conv_layer) instead of the fused tail kernels
-# (video: vad_convt2_score, image: vad_convt_conv_score)
-FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
-# VAD_LSTM2=0: one launch per ConvLSTM layer (vad_convlstm_sequence) instead of the two-layer wavefront kernel
-FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
-
-
-def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
-    if FIRST_CONV_TC and w.cout == 32 and w.w_tc is not None:
-        _timed("first_conv", lambda: nat.check(
-            nat.load().vad_first_conv_tc(x.data_ptr(), w.w_tc.data_ptr(), w.bias.data_ptr(), LEAKY, 1 if pool else 0,
-                                         B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv_tc"))
-        return
-    _timed("first_conv", lambda: nat.check(
-        nat.load().vad_first_conv(x.data_ptr(), w.w.data_ptr(), w.bias.data_ptr(), w.cout, LEAKY, 1 if pool else 0,
-                                  B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv"))
-
-
-def _conv(w: GemmWeights, src, B, H, W, out, slope, pool=False, what=""):
-    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-    _gemm_layer(w, src, B, H, W, nat.EPI_POOL if pool else nat.EPI_STORE, slope, out,
-                out_frame_stride=Ho * Wo * w.n_total, out_cpitch=w.n_total, what=what)
-
-
-def _convt(w: GemmWeights, src, B, H, W, out, slope, what=""):
-    _gemm_layer(w, src, B, H, W, nat.EPI_CONVT, slope, out, out_frame_stride=4 * H * W * w.cout, out_cpitch=w.cout,
-                what=what)
-
-
 def _check_hw(H: int, W: int) -> None:
     if H % 16 or W % 16 or H <= 0 or W <= 0:
         # the reference fails here too (x - recon shape mismatch, SURVEY §0.10); fail before launching anything
         raise RuntimeError(f"input height/width must be positive multiples of 16, got {H}x{W}")
 
 
-def _finalize(partials, frames, tiles_per_frame, H, W, bufs: _Buffers, device) -> Tuple[torch.Tensor, torch.Tensor]:
-    score = torch.empty(frames, dtype=torch.float32, device=device)
-    minmax = torch.empty(frames, 2, dtype=torch.float32, device=device)
-    nat.check(nat.load().vad_score_finalize(partials.data_ptr(), frames, tiles_per_frame, H, W, score.data_ptr(),
-                                            minmax.data_ptr(), nat.stream_ptr()), "vad_score_finalize")
-    return score, minmax
+def _gemm_struct(w: GemmWeights) -> "nat.GemmW":
+    g = nat.GemmW()
+    g.w, g.w_kx, g.bias = w.w.data_ptr(), nat.ptr(w.w_kx), w.bias.data_ptr()
+    g.ntaps, g.ctap, g.n_total, g.cout = w.ntaps, w.ctap, w.n_total, w.cout
+    return g
+
+
+def _first_struct(w: FirstConvWeights) -> "nat.FirstW":
+    f = nat.FirstW()
+    f.w, f.bias, f.cout = w.w.data_ptr(), w.bias.data_ptr(), w.cout
+    f.w_tc = nat.ptr(w.w_tc) if FIRST_CONV_TC else None
+    return f
+
+
+def _flags() -> int:
+    return (0 if FUSE_DEC_TAIL else nat.FLAG_NO_FUSED_TAIL) | (0 if FUSE_LSTM_LAYERS else nat.FLAG_NO_LSTM_WAVEFRONT)
+
+
+def _packed_device(packed: Dict[str, object]) -> torch.device:
+    for v in packed.values():
+        if isinstance(v, (GemmWeights, FirstConvWeights)):
+            return v.bias.device
+    raise RuntimeError("no prepared weights")
+
+
+class _Call:
+    """One model-level call: makes the tensors' device current, picks its stream and allocates the workspace."""
+
+    def __init__(self, device: torch.device, ws_bytes: int, what: str):
+        if ws_bytes == 0:
+            raise RuntimeError(f"libvad_b200: {what}: unsupported model / shape (workspace query returned 0)")
+        self.guard = torch.cuda.device(device)
+        self.device = device
+        self.ws_bytes = ws_bytes
+
+    def __enter__(self):
+        self.guard.__enter__()
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        return self.guard.__exit__(*exc)
 
 
 class ImageEngine:
-    """ConvAutoencoder forward + fused scoring (reference models/autoencoder.py:181-221)."""
+    """ConvAutoencoder forward + fused scoring (reference models/autoencoder.py:181-221) behind `vad_image_forward`;
+    a stand-alone `Encoder` / `Decoder` builds one from its own parameters (only that half is populated)."""
+
+    _ENC = ("enc1.3", "enc2.0", "enc2.3", "enc3.0", "enc3.3", "enc4.0", "enc4.3")
+    _DEC = ("dec1.0", "dec1.3", "dec2.0", "dec2.3", "dec3.0", "dec3.3", "dec4.0", "dec4.3")
 
     def __init__(self, packed: Dict[str, object]) -> None:
-        self.p = packed
-        self.bufs = _Buffers()
+        self.p = packed  # keeps the device tensors behind the raw pointers alive
+        self.device = _packed_device(packed)
+        m = nat.ImageModel()
+        m.has_encoder = 1 if "enc1.0" in packed else 0
+        m.has_decoder = 1 if "dec1.0" in packed else 0
+        if m.has_encoder:
+            m.enc1_0 = _first_struct(packed["enc1.0"])
+            for i, k in enumerate(self._ENC):
+                m.enc[i] = _gemm_struct(packed[k])
+        if m.has_decoder:
+            for i, k in enumerate(self._DEC):
+                m.dec[i] = _gemm_struct(packed[k])
+        self.m = m
+        self.lib = nat.load()
 
-    def encode(self, x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
-        """x fp32 [B,3,H,W] -> latent bf16 NHWC [B,H/16,W/16,latent]."""
-        p, dev = self.p, x.device
-        B, _, H, W = x.shape
+    @property
+    def latent_dim(self) -> int:
+        return (self.p["enc4.3"].n_total if self.m.has_encoder else self.p["dec1.0"].ctap)
+
+    def _ws(self, op: int, B: int, H: int, W: int) -> int:
+        return int(self.lib.vad_image_workspace_bytes(C.byref(self.m), op, B, H, W))
+
+    def run(self, x: torch.Tensor, want_recon: bool, want_heat: bool, want_latent: bool = False) -> ScoreOutputs:
+        x = _require_cuda_input(x, (4,))
+        B, cin, H, W = x.shape
+        if cin != 3:
+            raise RuntimeError(f"expected 3 input channels, got {cin}")
         _check_hw(H, W)
-        g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
-        a = g("e1a", (B, H, W, 32))
-        _first_conv(p["enc1.0"], x, B, H, W, False, a)
-        h, w, cur = H, W, a
-        for blk in ("enc1", "enc2", "enc3", "enc4"):
-            if blk != "enc1":
-                w0: GemmWeights = p[f"{blk}.0"]
-                nxt = g(f"{blk}a", (B, h, w, w0.n_total))
-                _conv(w0, cur, B, h, w, nxt, LEAKY, what=f"{blk}.0")
-                cur = nxt
-            w3: GemmWeights = p[f"{blk}.3"]
-            nxt = g(f"{blk}b", (B, h // 2, w // 2, w3.n_total))
-            _conv(w3, cur, B, h, w, nxt, LEAKY, pool=True, what=f"{blk}.3")
-            cur, h, w = nxt, h // 2, w // 2
-        return cur, h, w
+        dev = x.device
+        self.m.flags = _flags()
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        minmax = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        heat = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_heat else None
+        recon = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
+        latent = torch.empty(B, self.latent_dim, H // 16, W // 16, dtype=torch.float32, device=dev) if want_latent else None
+        with _Call(dev, self._ws(nat.OP_FORWARD, B, H, W), "vad_image_forward") as c:
+            nat.check(self.lib.vad_image_forward(C.byref(self.m), x.data_ptr(), B, H, W, nat.ptr(recon), nat.ptr(latent),
+                                                 score.data_ptr(), minmax.data_ptr(), nat.ptr(heat), c.ws.data_ptr(),
+                                                 c.ws_bytes, c.stream), "vad_image_forward")
+        return ScoreOutputs(score, minmax, heat, recon, latent)
 
     def latent(self, x: torch.Tensor) -> torch.Tensor:
+        """Encoder.forward / get_latent: fp32 [B,3,H,W] -> fp32 [B,latent,H/16,W/16]."""
         x = _require_cuda_input(x, (4,))
-        z, h, w = self.encode(x)
-        B, C = x.shape[0], z.shape[-1]
-        out = torch.empty(B, C, h, w, dtype=torch.float32, device=x.device)
-        nat.check(nat.load().vad_nhwc_bf16_to_nchw_f32(z.data_ptr(), B, h, w, C, out.data_ptr(), nat.stream_ptr()),
-                  "vad_nhwc_bf16_to_nchw_f32")
+        B, cin, H, W = x.shape
+        if cin != 3:
+            raise RuntimeError(f"expected 3 input channels, got {cin}")
+        _check_hw(H, W)
+        out = torch.empty(B, self.latent_dim, H // 16, W // 16, dtype=torch.float32, device=x.device)
+        with _Call(x.device, self._ws(nat.OP_ENCODE, B, H, W), "vad_image_forward(latent)") as c:
+            nat.check(self.lib.vad_image_forward(C.byref(self.m), x.data_ptr(), B, H, W, None, out.data_ptr(), None, None,
+                                                 None, c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_image_forward")
         return out
 
-    def run(self, x: torch.Tensor, want_recon: bool, want_heat: bool) -> ScoreOutputs:
-        x = _require_cuda_input(x, (4,))
-        p, dev = self.p, x.device
-        B, _, H, W = x.shape
-        z, h, w = self.encode(x)
-        g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
-        cur = z
-        w40: GemmWeights = p["dec4.0"]
-        w43: GemmWeights = p["dec4.3"]
-        fuse_tail = FUSE_DEC_TAIL and w43.w_kx is not None and \
-            (w40.ctap, w40.n_total, w40.cout, w43.ctap, w43.n_total) == (32, 128, 32, 32, 16)
-        for blk in ("dec1", "dec2", "dec3", "dec4"):
-            if blk == "dec4" and fuse_tail:
-                # dec4.0 + dec4.3 + score in one kernel: the 32-channel full-resolution tensor never reaches HBM
-                return _fused_image_tail(w40, w43, cur, B, h, w, x, want_recon, want_heat, self.bufs)
-            wt: GemmWeights = p[f"{blk}.0"]
-            up = g(f"{blk}a", (B, 2 * h, 2 * w, wt.cout))
-            _convt(wt, cur, B, h, w, up, RELU, what=f"{blk}.0")
-            h, w, cur = 2 * h, 2 * w, up
-            if blk != "dec4":
-                wc: GemmWeights = p[f"{blk}.3"]
-                nxt = g(f"{blk}b", (B, h, w, wc.n_total))
-                _conv(wc, cur, B, h, w, nxt, RELU, what=f"{blk}.3")
-                cur = nxt
-        return _score_layer(p["dec4.3"], cur, B, H, W, nat.EPI_TANH_SCORE, x, want_recon, want_heat, H, W, self.bufs,
-                            "dec4.3+score")
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """Decoder.forward: fp32 [B,latent,h,w] -> fp32 [B,3,16h,16w]."""
+        z = _require_cuda_input(z, (4,))
+        B, cz, h, w = z.shape
+        if cz != self.latent_dim:
+            raise RuntimeError(f"expected {self.latent_dim} latent channels, got {cz}")
+        self.m.flags = _flags()
+        recon = torch.empty(B, 3, 16 * h, 16 * w, dtype=torch.float32, device=z.device)
+        with _Call(z.device, self._ws(nat.OP_DECODE, B, h, w), "vad_image_decode") as c:
+            nat.check(self.lib.vad_image_decode(C.byref(self.m), z.data_ptr(), B, h, w, recon.data_ptr(), c.ws.data_ptr(),
+                                                c.ws_bytes, c.stream), "vad_image_decode")
+        return recon
 
 
 class VideoEngine:
-    """VideoAutoencoder forward + fused scoring (reference models/video_autoencoder.py:329-384)."""
+    """VideoAutoencoder forward + fused scoring (reference models/video_autoencoder.py:329-384) behind
+    `vad_video_forward`; stand-alone sub-modules populate only their part of the struct."""
 
     def __init__(self, packed: Dict[str, object]) -> None:
         self.p = packed
-        self.bufs = _Buffers()
+        self.device = _packed_device(packed)
+        m = nat.VideoModel()
+        m.has_encoder = 1 if "enc.0" in packed else 0
+        m.has_decoder = 1 if "dec.0" in packed else 0
+        m.lstm_layers = int(packed.get("lstm_layers", 0))
+        if m.lstm_layers > nat.MAX_LSTM_LAYERS:
+            raise ValueError(f"at most {nat.MAX_LSTM_LAYERS} ConvLSTM layers are supported")
+        if m.has_encoder:
+            m.enc0 = _first_struct(packed["enc.0"])
+            for i, k in enumerate((4, 8, 12)):
+                m.enc[i] = _gemm_struct(packed[f"enc.{k}"])
+        for l in range(m.lstm_layers):
+            m.lstm[l] = _gemm_struct(packed[f"lstm.{l}"])
+        m.has_proj = 1 if "proj" in packed else 0
+        if m.has_proj:
+            m.proj = _gemm_struct(packed["proj"])
+        if m.has_decoder:
+            for i, k in enumerate((0, 3, 6, 9)):
+                m.dec[i] = _gemm_struct(packed[f"dec.{k}"])
+        self.m = m
+        self.lib = nat.load()
 
-    # ---- pieces (also used by the sub-module wrappers) ---------------------------------------------------------
-    def encode(self, x4: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
-        """frames fp32 [F,3,H,W] -> bf16 NHWC [F,H/16,W/16,latent]."""
-        p, dev = self.p, x4.device
-        F, _, H, W = x4.shape
-        _check_hw(H, W)
-        g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
-        cur = g("e0", (F, H // 2, W // 2, 32))
-        _first_conv(p["enc.0"], x4, F, H, W, True, cur)
-        h, w = H // 2, W // 2
-        for i in (4, 8, 12):
-            wt: GemmWeights = p[f"enc.{i}"]
-            nxt = g(f"e{i}", (F, h // 2, w // 2, wt.n_total))
-            _conv(wt, cur, F, h, w, nxt, LEAKY, pool=True, what=f"encoder.{i}")
-            cur, h, w = nxt, h // 2, w // 2
-        return cur, h, w
+    def _ws(self, op: int, B: int, T: int, H: int, W: int) -> int:
+        return int(self.lib.vad_video_workspace_bytes(C.byref(self.m), op, B, T, H, W))
 
-    def _lstm_desc(self, layer: int, cur: torch.Tensor, B: int, T: int, h: int, w: int):
-        p, dev = self.p, cur.device
-        wt: GemmWeights = p[f"lstm.{layer}"]
-        hid = wt.cout
-        cin = wt.ctap - hid
-        hseq = self.bufs.get(f"hseq{layer}", (B, T, h, w, hid), torch.bfloat16, dev)
-        cst = self.bufs.get(f"c{layer}", (B, h, w, hid), torch.float32, dev)
-        d = nat.ConvDesc()
-        d.src0, d.src1, d.out = cur.data_ptr(), hseq.data_ptr(), hseq.data_ptr()
-        d.c0, d.c1, d.T0, d.T1 = cin, hid, T, T
-        d.B, d.H, d.W, d.ntaps = B, h, w, 9
-        d.weight, d.bias, d.w_ctap = wt.w.data_ptr(), wt.bias.data_ptr(), wt.ctap
-        d.n_total, d.cout, d.epilogue, d.slope = wt.n_total, hid, nat.EPI_LSTM, IDENT
-        d.out_frame_stride, d.out_cpitch = T * h * w * hid, hid
-        d.c_state = cst.data_ptr()
-        return d, hseq
+    @property
+    def latent_dim(self) -> int:
+        return self.p["enc.12"].n_total if self.m.has_encoder else self.p["dec.0"].ctap
 
-    def convlstm(self, seq: torch.Tensor, B: int, T: int, h: int, w: int) -> torch.Tensor:
-        """seq bf16 [B,T,h,w,C] -> last layer's hidden sequence bf16 [B,T,h,w,hid] (zero initial state)."""
-        p = self.p
-        cur = seq
-        layer = 0
-        while layer < p["lstm_layers"]:
-            d, hseq = self._lstm_desc(layer, cur, B, T, h, w)
-            if FUSE_LSTM_LAYERS and layer + 1 < p["lstm_layers"]:
-                # two layers as one wavefront launch (layer 2's step t runs next to layer 1's step t+1)
-                d2, hseq2 = self._lstm_desc(layer + 1, hseq, B, T, h, w)
-                rc = [0]
+    @property
+    def hidden_dim(self) -> int:
+        return self.p[f"lstm.{self.m.lstm_layers - 1}"].cout
 
-                def both():
-                    rc[0] = nat.load().vad_convlstm2_sequence(C.byref(d), C.byref(d2), T, nat.stream_ptr())
-                    if rc[0] != nat.ERR_UNSUPPORTED:
-                        nat.check(rc[0], f"convlstm.{layer}+{layer + 1}")
-                _timed(f"convlstm.{layer}+{layer + 1}", both)
-                if rc[0] == 0:
-                    cur = hseq2
-                    layer += 2
-                    continue
-                if PROFILE is not None:
-                    PROFILE.pop()  # nothing was launched
-            _timed(f"convlstm.{layer}", lambda: nat.check(
-                nat.load().vad_convlstm_sequence(C.byref(d), T, nat.stream_ptr()), f"convlstm.{layer}"))
-            cur = hseq
-            layer += 1
-        return cur
-
-    def project(self, seq: torch.Tensor, F: int, h: int, w: int) -> torch.Tensor:
-        if "proj" not in self.p:
-            return seq
-        wt: GemmWeights = self.p["proj"]
-        out = self.bufs.get("proj", (F, h, w, wt.n_total), torch.bfloat16, seq.device)
-        _conv(wt, seq, F, h, w, out, IDENT, what="proj")
-        return out
-
-    def decode_to(self, z: torch.Tensor, F: int, h: int, w: int, layers=(0, 3, 6)) -> Tuple[torch.Tensor, int, int]:
-        """bf16 NHWC [F,h,w,latent] -> input of the last ConvT, bf16 NHWC [F,8h,8w,32] (or of an earlier one)."""
-        cur = z
-        for i in layers:
-            wt: GemmWeights = self.p[f"dec.{i}"]
-            up = self.bufs.get(f"d{i}", (F, 2 * h, 2 * w, wt.cout), torch.bfloat16, z.device)
-            _convt(wt, cur, F, h, w, up, RELU, what=f"decoder.{i}")
-            cur, h, w = up, 2 * h, 2 * w
-        return cur, h, w
+    def _outputs(self, F: int, H: int, W: int, want_recon: bool, want_heat: bool, dev):
+        score = torch.empty(F, dtype=torch.float32, device=dev)
+        minmax = torch.empty(F, 2, dtype=torch.float32, device=dev)
+        heat = torch.empty(F, H, W, dtype=torch.float32, device=dev) if want_heat else None
+        recon = torch.empty(F, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
+        return score, minmax, heat, recon
 
     def run(self, x: torch.Tensor, want_recon: bool, want_heat: bool) -> ScoreOutputs:
         x = _require_cuda_input(x, (5,))
-        B, T, Cin, H, W = x.shape
-        F = B * T
-        dev = x.device
-        x4 = x.view(F, Cin, H, W)
-        z, h, w = self.encode(x4)
-        seq = self.convlstm(z.view(B, T, h, w, z.shape[-1]), B, T, h, w)
-        zp = self.project(seq.view(F, h, w, seq.shape[-1]), F, h, w)
-        return self.decode_and_score(zp, F, h, w, x4, want_recon, want_heat)
+        B, T, cin, H, W = x.shape
+        if cin != 3:
+            raise RuntimeError(f"expected 3 input channels, got {cin}")
+        _check_hw(H, W)
+        self.m.flags = _flags()
+        score, minmax, heat, recon = self._outputs(B * T, H, W, want_recon, want_heat, x.device)
+        with _Call(x.device, self._ws(nat.OP_FORWARD, B, T, H, W), "vad_video_forward") as c:
+            nat.check(self.lib.vad_video_forward(C.byref(self.m), x.data_ptr(), B, T, H, W, nat.ptr(recon),
+                                                 score.data_ptr(), minmax.data_ptr(), nat.ptr(heat), c.ws.data_ptr(),
+                                                 c.ws_bytes, c.stream), "vad_video_forward")
+        return ScoreOutputs(score, minmax, heat, recon)
 
-    def decode_and_score(self, zp: torch.Tensor, F: int, h: int, w: int, x4: torch.Tensor, want_recon: bool,
-                         want_heat: bool) -> ScoreOutputs:
-        """Decoder + fused scoring of F frames: zp bf16 NHWC [F,h,w,latent], x4 fp32 [F,3,16h,16w]."""
-        H, W = x4.shape[-2], x4.shape[-1]
-        w6: GemmWeights = self.p["dec.6"]
-        w9: GemmWeights = self.p["dec.9"]
-        if FUSE_DEC_TAIL and (w6.ctap, w6.n_total, w6.cout, w9.ctap, w9.n_total) == (64, 128, 32, 32, 16):
-            # decoder.6 + decoder.9 + score in one kernel: the 32-channel half-resolution tensor never reaches HBM
-            d, hd, wd = self.decode_to(zp, F, h, w, layers=(0, 3))
-            return _fused_tail(w6, w9, d, F, hd, wd, x4, want_recon, want_heat, H, W, self.bufs)
-        d, hd, wd = self.decode_to(zp, F, h, w)
-        return _score_layer(w9, d, F, hd, wd, nat.EPI_CONVT_TANH_SCORE, x4, want_recon, want_heat, H, W,
-                            self.bufs, "decoder.9+score")
+    def encode(self, x4: torch.Tensor, want_f32: bool = False, want_bf16: bool = True):
+        """frames fp32 [F,3,H,W] -> (bf16 NHWC [F,h,w,latent] or None, fp32 NCHW [F,latent,h,w] or None)."""
+        x4 = _require_cuda_input(x4, (4,))
+        F, cin, H, W = x4.shape
+        if cin != 3:
+            raise RuntimeError(f"expected 3 input channels, got {cin}")
+        _check_hw(H, W)
+        h, w, Cz = H // 16, W // 16, self.latent_dim
+        zb = torch.empty(F, h, w, Cz, dtype=torch.bfloat16, device=x4.device) if want_bf16 else None
+        zf = torch.empty(F, Cz, h, w, dtype=torch.float32, device=x4.device) if want_f32 else None
+        with _Call(x4.device, self._ws(nat.OP_ENCODE, F, 1, H, W), "vad_video_encode") as c:
+            nat.check(self.lib.vad_video_encode(C.byref(self.m), x4.data_ptr(), F, H, W, nat.ptr(zf), nat.ptr(zb),
+                                                c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_video_encode")
+        return zb, zf
+
+    def score_latents(self, z: torch.Tensor, x: torch.Tensor, want_recon: bool, want_heat: bool) -> ScoreOutputs:
+        """ConvLSTM -> proj -> decoder -> scoring from cached encoder features: z bf16 [B,T,h,w,latent],
+        x fp32 [B,T,3,16h,16w]."""
+        if z.dtype != torch.bfloat16 or z.dim() != 5 or not z.is_cuda:
+            raise RuntimeError("score_latents expects a CUDA bf16 tensor [B,T,h,w,C]")
+        z = z.contiguous()
+        x = _require_cuda_input(x, (5,))
+        B, T, h, w, _ = z.shape
+        if tuple(x.shape) != (B, T, 3, 16 * h, 16 * w):
+            raise RuntimeError(f"frames {tuple(x.shape)} do not match latents {tuple(z.shape)}")
+        self.m.flags = _flags()
+        score, minmax, heat, recon = self._outputs(B * T, 16 * h, 16 * w, want_recon, want_heat, x.device)
+        with _Call(x.device, self._ws(nat.OP_SCORE_LATENTS, B, T, h, w), "vad_video_score_latents") as c:
+            nat.check(self.lib.vad_video_score_latents(C.byref(self.m), z.data_ptr(), x.data_ptr(), B, T, h, w,
+                                                       nat.ptr(recon), score.data_ptr(), minmax.data_ptr(), nat.ptr(heat),
+                                                       c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_video_score_latents")
+        return ScoreOutputs(score, minmax, heat, recon)
+
+    def decode(self, z4: torch.Tensor) -> torch.Tensor:
+        """VideoDecoder.forward on frames: fp32 [F,latent,h,w] -> fp32 [F,3,16h,16w]."""
+        z4 = _require_cuda_input(z4, (4,))
+        F, cz, h, w = z4.shape
+        if cz != self.latent_dim:
+            raise RuntimeError(f"expected {self.latent_dim} latent channels, got {cz}")
+        self.m.flags = _flags()
+        recon = torch.empty(F, 3, 16 * h, 16 * w, dtype=torch.float32, device=z4.device)
+        with _Call(z4.device, self._ws(nat.OP_DECODE, F, 1, h, w), "vad_video_decode") as c:
+            nat.check(self.lib.vad_video_decode(C.byref(self.m), z4.data_ptr(), F, h, w, recon.data_ptr(),
+                                                c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_video_decode")
+        return recon
+
+    def convlstm(self, x5: torch.Tensor):
+        """ConvLSTM.forward (zero initial state): fp32 [B,T,C,h,w] -> (out fp32 [B,T,hid,h,w], c_last fp32 [B,hid,h,w])."""
+        x5 = _require_cuda_input(x5, (5,))
+        B, T, cin, h, w = x5.shape
+        w0: GemmWeights = self.p["lstm.0"]
+        if cin != w0.ctap - w0.cout:
+            raise RuntimeError(f"expected {w0.ctap - w0.cout} input channels, got {cin}")
+        self.m.flags = _flags()
+        hid = self.hidden_dim
+        out = torch.empty(B, T, hid, h, w, dtype=torch.float32, device=x5.device)
+        c_last = torch.empty(B, hid, h, w, dtype=torch.float32, device=x5.device)
+        with _Call(x5.device, self._ws(nat.OP_CONVLSTM, B, T, h, w), "vad_convlstm_forward") as c:
+            nat.check(self.lib.vad_convlstm_forward(C.byref(self.m), x5.data_ptr(), B, T, h, w, out.data_ptr(), None,
+                                                    c_last.data_ptr(), c.ws.data_ptr(), c.ws_bytes, c.stream),
+                      "vad_convlstm_forward")
+        return out, c_last
+
+
+class CellEngine:
+    """One ConvLSTMCell step (reference models/video_autoencoder.py:54-85) behind `vad_convlstm_cell`."""
+
+    def __init__(self, w: GemmWeights) -> None:
+        self.w = w
+        self.g = _gemm_struct(w)
+        self.lib = nat.load()
+
+    def step(self, x: torch.Tensor, h_cur: torch.Tensor, c_cur: torch.Tensor):
+        x = _require_cuda_input(x, (4,))
+        h_cur = _require_cuda_input(h_cur, (4,))
+        c_cur = _require_cuda_input(c_cur, (4,))
+        B, cin, h, w = x.shape
+        hid = self.w.cout
+        if cin != self.w.ctap - hid or tuple(h_cur.shape) != (B, hid, h, w) or tuple(c_cur.shape) != (B, hid, h, w):
+            raise RuntimeError(f"ConvLSTMCell shapes: x {tuple(x.shape)}, h {tuple(h_cur.shape)}, c {tuple(c_cur.shape)} "
+                               f"do not match input_dim {self.w.ctap - hid} / hidden_dim {hid}")
+        h_next = torch.empty_like(h_cur)
+        c_next = torch.empty_like(c_cur)
+        nbytes = int(self.lib.vad_convlstm_cell_workspace_bytes(C.byref(self.g), B, h, w))
+        with _Call(x.device, nbytes, "vad_convlstm_cell") as c:
+            nat.check(self.lib.vad_convlstm_cell(C.byref(self.g), x.data_ptr(), h_cur.data_ptr(), c_cur.data_ptr(), B, h, w,
+                                                 h_next.data_ptr(), c_next.data_ptr(), c.ws.data_ptr(), c.ws_bytes,
+                                                 c.stream), "vad_convlstm_cell")
+        return h_next, c_next

@@ -22,7 +22,15 @@ EXPORTS = (
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8", "vad_u8_hwc_to_f32_nchw", "vad_f32_nchw_to_u8_hwc",
     "vad_heatmap_jet_rgb", "vad_ssim_scratch_bytes", "vad_ssim_loss",
+    # model-level entry points (one call per reference method)
+    "vad_image_workspace_bytes", "vad_image_forward", "vad_image_decode", "vad_video_workspace_bytes",
+    "vad_video_forward", "vad_video_encode", "vad_video_score_latents", "vad_video_decode", "vad_convlstm_forward",
+    "vad_convlstm_cell_workspace_bytes", "vad_convlstm_cell", "vad_profile_enable", "vad_profile_dump",
 )
+
+FLAG_NO_FUSED_TAIL, FLAG_NO_LSTM_WAVEFRONT = 1, 2
+OP_FORWARD, OP_ENCODE, OP_DECODE, OP_CONVLSTM, OP_SCORE_LATENTS = range(5)
+MAX_LSTM_LAYERS = 8
 
 
 class ConvDesc(C.Structure):
@@ -43,7 +51,33 @@ class ConvDesc(C.Structure):
         ("c_state", C.c_void_p), ("lstm_first", C.c_int),
         ("x", C.c_void_p), ("recon", C.c_void_p), ("heat", C.c_void_p), ("partials", C.c_void_p),
         ("weight_kx", C.c_void_p),
+        ("scratch", C.c_void_p),
     ]
+
+
+class GemmW(C.Structure):
+    """Mirror of `struct vad_gemm_weights`."""
+    _fields_ = [("w", C.c_void_p), ("w_kx", C.c_void_p), ("bias", C.c_void_p),
+                ("ntaps", C.c_int), ("ctap", C.c_int), ("n_total", C.c_int), ("cout", C.c_int)]
+
+
+class FirstW(C.Structure):
+    """Mirror of `struct vad_first_weights`."""
+    _fields_ = [("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("cout", C.c_int)]
+
+
+class ImageModel(C.Structure):
+    """Mirror of `struct vad_image_model`."""
+    _fields_ = [("has_encoder", C.c_int), ("has_decoder", C.c_int), ("flags", C.c_int), ("reserved", C.c_int),
+                ("enc1_0", FirstW), ("enc", GemmW * 7), ("dec", GemmW * 8)]
+
+
+class VideoModel(C.Structure):
+    """Mirror of `struct vad_video_model`."""
+    _fields_ = [("has_encoder", C.c_int), ("lstm_layers", C.c_int), ("has_proj", C.c_int), ("has_decoder", C.c_int),
+                ("flags", C.c_int), ("reserved", C.c_int),
+                ("enc0", FirstW), ("enc", GemmW * 3), ("lstm", GemmW * MAX_LSTM_LAYERS), ("proj", GemmW),
+                ("dec", GemmW * 4)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -94,6 +128,23 @@ def load() -> C.CDLL:
     lib.vad_ssim_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.vad_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
+    P, I, Z = C.c_void_p, C.c_int, C.c_size_t
+    lib.vad_image_workspace_bytes.restype = Z
+    lib.vad_image_workspace_bytes.argtypes = [C.POINTER(ImageModel), I, I, I, I]
+    lib.vad_image_forward.argtypes = [C.POINTER(ImageModel), P, I, I, I, P, P, P, P, P, P, Z, P]
+    lib.vad_image_decode.argtypes = [C.POINTER(ImageModel), P, I, I, I, P, P, Z, P]
+    lib.vad_video_workspace_bytes.restype = Z
+    lib.vad_video_workspace_bytes.argtypes = [C.POINTER(VideoModel), I, I, I, I, I]
+    lib.vad_video_forward.argtypes = [C.POINTER(VideoModel), P, I, I, I, I, P, P, P, P, P, Z, P]
+    lib.vad_video_encode.argtypes = [C.POINTER(VideoModel), P, I, I, I, P, P, P, Z, P]
+    lib.vad_video_score_latents.argtypes = [C.POINTER(VideoModel), P, P, I, I, I, I, P, P, P, P, P, Z, P]
+    lib.vad_video_decode.argtypes = [C.POINTER(VideoModel), P, I, I, I, P, P, Z, P]
+    lib.vad_convlstm_forward.argtypes = [C.POINTER(VideoModel), P, I, I, I, I, P, P, P, P, Z, P]
+    lib.vad_convlstm_cell_workspace_bytes.restype = Z
+    lib.vad_convlstm_cell_workspace_bytes.argtypes = [C.POINTER(GemmW), I, I, I]
+    lib.vad_convlstm_cell.argtypes = [C.POINTER(GemmW), P, P, P, I, I, I, P, P, P, Z, P]
+    lib.vad_profile_enable.argtypes = [I]
+    lib.vad_profile_dump.argtypes = [C.c_char_p, Z]
     _lib = lib
     return lib
 
@@ -107,8 +158,26 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"libvad_b200: {what} failed with code {rc}: {msg}")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def profile_enable(on: bool) -> None:
+    """Bracket every layer launch of the model-level calls with CUDA events (bench.py's per-kernel roofline)."""
+    load().vad_profile_enable(1 if on else 0)
+
+
+def profile_dump():
+    """[(layer name, ms)] in launch order since the last dump; synchronises the recorded events."""
+    buf = C.create_string_buffer(1 << 20)
+    n = load().vad_profile_dump(buf, len(buf))
+    if n < 0:
+        check(n, "vad_profile_dump")
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, _, ms = line.partition("\t")
+        out.append((name, float(ms)))
+    return out
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

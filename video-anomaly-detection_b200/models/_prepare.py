@@ -142,40 +142,75 @@ def pack_first_conv(w: torch.Tensor, b: torch.Tensor) -> FirstConvWeights:
                             w_tc.to(torch.bfloat16).contiguous())
 
 
+def prepare_image_encoder(sd: Mapping[str, torch.Tensor], prefix: str = "encoder.") -> Dict[str, object]:
+    """`Encoder` parameters (keys `<prefix>enc{1..4}.{0,1,3,4}.*`) -> packed layers."""
+    out: Dict[str, object] = {}
+    out["enc1.0"] = pack_first_conv(*fold_conv(sd, f"{prefix}enc1.0", f"{prefix}enc1.1"))
+    out["enc1.3"] = pack_conv3x3(*fold_conv(sd, f"{prefix}enc1.3", f"{prefix}enc1.4"))
+    for blk in ("enc2", "enc3", "enc4"):
+        out[f"{blk}.0"] = pack_conv3x3(*fold_conv(sd, f"{prefix}{blk}.0", f"{prefix}{blk}.1"))
+        out[f"{blk}.3"] = pack_conv3x3(*fold_conv(sd, f"{prefix}{blk}.3", f"{prefix}{blk}.4"))
+    return out
+
+
+def prepare_image_decoder(sd: Mapping[str, torch.Tensor], prefix: str = "decoder.") -> Dict[str, object]:
+    """`Decoder` parameters (keys `<prefix>dec{1..4}.{0,1,3,4}.*`) -> packed layers."""
+    out: Dict[str, object] = {}
+    for blk in ("dec1", "dec2", "dec3"):
+        out[f"{blk}.0"] = pack_convt2x2(*fold_convt(sd, f"{prefix}{blk}.0", f"{prefix}{blk}.1"))
+        out[f"{blk}.3"] = pack_conv3x3(*fold_conv(sd, f"{prefix}{blk}.3", f"{prefix}{blk}.4"))
+    out["dec4.0"] = pack_convt2x2(*fold_convt(sd, f"{prefix}dec4.0", f"{prefix}dec4.1"))
+    out["dec4.3"] = pack_conv3x3(*fold_conv(sd, f"{prefix}dec4.3", None), pad_n_to=16)
+    return out
+
+
 def prepare_image(sd: Mapping[str, torch.Tensor]) -> Dict[str, object]:
     """ConvAutoencoder state_dict (SURVEY Appendix D keys) -> packed layers, in execution order."""
+    out = prepare_image_encoder(sd)
+    out.update(prepare_image_decoder(sd))
+    return out
+
+
+def prepare_video_encoder(sd: Mapping[str, torch.Tensor], prefix: str = "encoder.encoder.") -> Dict[str, object]:
     out: Dict[str, object] = {}
-    out["enc1.0"] = pack_first_conv(*fold_conv(sd, "encoder.enc1.0", "encoder.enc1.1"))
-    out["enc1.3"] = pack_conv3x3(*fold_conv(sd, "encoder.enc1.3", "encoder.enc1.4"))
-    for blk in ("enc2", "enc3", "enc4"):
-        out[f"{blk}.0"] = pack_conv3x3(*fold_conv(sd, f"encoder.{blk}.0", f"encoder.{blk}.1"))
-        out[f"{blk}.3"] = pack_conv3x3(*fold_conv(sd, f"encoder.{blk}.3", f"encoder.{blk}.4"))
-    for blk in ("dec1", "dec2", "dec3"):
-        out[f"{blk}.0"] = pack_convt2x2(*fold_convt(sd, f"decoder.{blk}.0", f"decoder.{blk}.1"))
-        out[f"{blk}.3"] = pack_conv3x3(*fold_conv(sd, f"decoder.{blk}.3", f"decoder.{blk}.4"))
-    out["dec4.0"] = pack_convt2x2(*fold_convt(sd, "decoder.dec4.0", "decoder.dec4.1"))
-    out["dec4.3"] = pack_conv3x3(*fold_conv(sd, "decoder.dec4.3", None), pad_n_to=16)
+    out["enc.0"] = pack_first_conv(*fold_conv(sd, f"{prefix}0", f"{prefix}1"))
+    for i in (4, 8, 12):
+        out[f"enc.{i}"] = pack_conv3x3(*fold_conv(sd, f"{prefix}{i}", f"{prefix}{i + 1}"))
+    return out
+
+
+def prepare_lstm_cell(sd: Mapping[str, torch.Tensor], prefix: str) -> GemmWeights:
+    """One `ConvLSTMCell` (keys `<prefix>conv.{weight,bias}`) -> row-permuted gate GEMM operand."""
+    w = sd[f"{prefix}conv.weight"].double()
+    b = sd[f"{prefix}conv.bias"].double()
+    return pack_lstm(w, b, w.shape[0] // 4)
+
+
+def prepare_convlstm(sd: Mapping[str, torch.Tensor], prefix: str = "convlstm.") -> Dict[str, object]:
+    out: Dict[str, object] = {}
+    layer = 0
+    while f"{prefix}cells.{layer}.conv.weight" in sd:
+        out[f"lstm.{layer}"] = prepare_lstm_cell(sd, f"{prefix}cells.{layer}.")
+        layer += 1
+    out["lstm_layers"] = layer
+    return out
+
+
+def prepare_video_decoder(sd: Mapping[str, torch.Tensor], prefix: str = "decoder.decoder.") -> Dict[str, object]:
+    out: Dict[str, object] = {}
+    for i in (0, 3, 6):
+        out[f"dec.{i}"] = pack_convt2x2(*fold_convt(sd, f"{prefix}{i}", f"{prefix}{i + 1}"))
+    out["dec.9"] = pack_convt2x2(*fold_convt(sd, f"{prefix}9", None), pad_n_to=16)
     return out
 
 
 def prepare_video(sd: Mapping[str, torch.Tensor]) -> Dict[str, object]:
     """VideoAutoencoder state_dict -> packed layers."""
-    out: Dict[str, object] = {}
-    out["enc.0"] = pack_first_conv(*fold_conv(sd, "encoder.encoder.0", "encoder.encoder.1"))
-    for i in (4, 8, 12):
-        out[f"enc.{i}"] = pack_conv3x3(*fold_conv(sd, f"encoder.encoder.{i}", f"encoder.encoder.{i + 1}"))
-    layer = 0
-    while f"convlstm.cells.{layer}.conv.weight" in sd:
-        w = sd[f"convlstm.cells.{layer}.conv.weight"].double()
-        b = sd[f"convlstm.cells.{layer}.conv.bias"].double()
-        out[f"lstm.{layer}"] = pack_lstm(w, b, w.shape[0] // 4)
-        layer += 1
-    out["lstm_layers"] = layer
+    out = prepare_video_encoder(sd)
+    out.update(prepare_convlstm(sd))
     if "proj.weight" in sd:
         out["proj"] = pack_conv1x1(sd["proj.weight"].double(), sd["proj.bias"].double())
-    for i in (0, 3, 6):
-        out[f"dec.{i}"] = pack_convt2x2(*fold_convt(sd, f"decoder.decoder.{i}", f"decoder.decoder.{i + 1}"))
-    out["dec.9"] = pack_convt2x2(*fold_convt(sd, "decoder.decoder.9", None), pad_n_to=16)
+    out.update(prepare_video_decoder(sd))
     return out
 
 

@@ -8,7 +8,7 @@ CUDA only — anything else raises.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -20,9 +20,85 @@ _ENC_WIDTHS = (32, 64, 128)  # enc4 width is latent_dim
 _DEC_WIDTHS = (128, 64, 32, 32)
 
 
-def _state_signature(module: nn.Module):
-    """Cheap change detector for the prepared-weight cache: (storage pointer, in-place version) of every tensor."""
-    return tuple((t.data_ptr(), t._version, t.device) for t in module.state_dict(keep_vars=True).values())
+class _PreparedCache:
+    """Prepared-weight cache of one module: the engine built from its parameters plus a cheap change detector.
+
+    Per call only (in-place version, storage pointer) of the tensors seen at build time are compared (~20 us for the
+    image model; walking `state_dict()` costs 300 us).  `load_state_dict` (a post hook) and `.to()` / `.cuda()` /
+    `.float()` (`_apply`) drop the cache outright, which also covers parameters being REPLACED rather than updated."""
+
+    def __init__(self) -> None:
+        self.engine = None
+        self.tensors: List[torch.Tensor] = []
+        self.sig: Tuple = ()
+
+    @staticmethod
+    def _signature(tensors) -> Tuple:
+        return tuple((t._version, t.data_ptr()) for t in tensors)
+
+    def get(self, module: nn.Module, device: torch.device, build):
+        _refuse_training(module)
+        _refuse_cpu(device)
+        if self.engine is not None and self._signature(self.tensors) == self.sig:
+            if self.engine.device != device:
+                raise RuntimeError(f"model parameters live on {self.engine.device} but the input is on {device}")
+            return self.engine
+        sd: Dict[str, torch.Tensor] = {k: v.detach() for k, v in module.state_dict().items()}
+        for k, v in sd.items():
+            if v.device != device:
+                raise RuntimeError(f"model parameter {k} lives on {v.device} but the input is on {device}")
+        tensors = [t for t in module.state_dict(keep_vars=True).values()]
+        self.engine, self.tensors, self.sig = build(sd), tensors, self._signature(tensors)
+        return self.engine
+
+    def drop(self) -> None:
+        self.engine, self.tensors, self.sig = None, [], ()
+
+
+def _drop_prepared(module: nn.Module, incompatible_keys) -> None:
+    module._vad_cache.drop()
+
+
+class _Prepared(nn.Module):
+    """nn.Module whose compute runs on prepared weights (see `_PreparedCache`); sub-classes implement `_build(sd)`."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        # kept out of the module's attribute dicts that state_dict / deepcopy / pickle walk
+        object.__setattr__(self, "_vad_cache", _PreparedCache())
+        self.register_load_state_dict_post_hook(_drop_prepared)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._vad_cache.drop()
+        return super()._apply(fn, *args, **kwargs)
+
+    def __deepcopy__(self, memo):
+        cache = self.__dict__.pop("_vad_cache")
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            import copy
+            new.__dict__ = copy.deepcopy(self.__dict__, memo)
+        finally:
+            object.__setattr__(self, "_vad_cache", cache)
+        object.__setattr__(new, "_vad_cache", _PreparedCache())
+        return new
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_vad_cache", None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        object.__setattr__(self, "_vad_cache", _PreparedCache())
+
+    def _build(self, sd: Dict[str, torch.Tensor]):
+        raise NotImplementedError
+
+    def _get_engine(self, device: torch.device):
+        return self._vad_cache.get(self, device, self._build)
 
 
 def _xavier_like_reference(module: nn.Module) -> None:
@@ -51,11 +127,16 @@ def _refuse_cpu(device: torch.device) -> None:
                            f"got a tensor on {device}")
 
 
-class Encoder(nn.Module):
-    """4 x [conv3x3-BN-LeakyReLU x2, maxpool2]: 3 -> 32 -> 64 -> 128 -> latent_dim, spatial / 16."""
+class Encoder(_Prepared):
+    """4 x [conv3x3-BN-LeakyReLU x2, maxpool2]: 3 -> 32 -> 64 -> 128 -> latent_dim, spatial / 16 (reference
+    models/autoencoder.py:24-86).  Callable on its own or as `model.encoder`."""
 
     def __init__(self, in_channels: int = 3, latent_dim: int = 256):
         super().__init__()
+        if in_channels != 3:
+            raise ValueError("vad_b200 kernels are specialised for 3-channel input (as every reference dataset is)")
+        if latent_dim % 32 != 0:
+            raise ValueError("latent_dim must be a multiple of 32 for the tcgen05 tile shapes")
         widths = _ENC_WIDTHS + (latent_dim,)
         cin = in_channels
         for i, cout in enumerate(widths, start=1):
@@ -66,19 +147,26 @@ class Encoder(nn.Module):
                 cin = cout
             layers.append(nn.MaxPool2d(2, 2))
             setattr(self, f"enc{i}", nn.Sequential(*layers))
-        self._owner: Optional["ConvAutoencoder"] = None
 
+    def _build(self, sd):
+        return ImageEngine(prep.prepare_image_encoder(sd, prefix=""))
+
+    @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self._owner is None:
-            raise RuntimeError("Encoder runs through its ConvAutoencoder (weights are prepared per model)")
-        return self._owner.get_latent(x)
+        """fp32 [B,3,H,W] -> fp32 [B,latent,H/16,W/16] (autoencoder.py:81-86)."""
+        return self._get_engine(x.device).latent(x)
 
 
-class Decoder(nn.Module):
-    """4 x [convT k2 s2-BN-ReLU, conv3x3-BN-ReLU]; the last conv goes to `out_channels` and ends in Tanh."""
+class Decoder(_Prepared):
+    """4 x [convT k2 s2-BN-ReLU, conv3x3-BN-ReLU]; the last conv goes to `out_channels` and ends in Tanh (reference
+    models/autoencoder.py:89-146).  Callable on its own or as `model.decoder`."""
 
     def __init__(self, out_channels: int = 3, latent_dim: int = 256):
         super().__init__()
+        if out_channels != 3:
+            raise ValueError("vad_b200 kernels are specialised for 3-channel output (as every reference dataset is)")
+        if latent_dim % 32 != 0:
+            raise ValueError("latent_dim must be a multiple of 32 for the tcgen05 tile shapes")
         cin = latent_dim
         for i, cout in enumerate(_DEC_WIDTHS, start=1):
             layers = [nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2), nn.BatchNorm2d(cout),
@@ -91,8 +179,16 @@ class Decoder(nn.Module):
             setattr(self, f"dec{i}", nn.Sequential(*layers))
             cin = cout
 
+    def _build(self, sd):
+        return ImageEngine(prep.prepare_image_decoder(sd, prefix=""))
 
-class ConvAutoencoder(nn.Module):
+    @torch.no_grad()
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        """fp32 [B,latent,h,w] -> fp32 [B,3,16h,16w] (autoencoder.py:141-146)."""
+        return self._get_engine(z.device).decode(z)
+
+
+class ConvAutoencoder(_Prepared):
     """Image autoencoder whose scoring calls run as fused sm_100a kernels.
 
     API parity: `forward`, `get_latent`, `get_reconstruction_error(x, per_pixel=False)` behave like the reference
@@ -101,30 +197,12 @@ class ConvAutoencoder(nn.Module):
 
     def __init__(self, in_channels: int = 3, latent_dim: int = 256):
         super().__init__()
-        if in_channels != 3:
-            raise ValueError("vad_b200 kernels are specialised for 3-channel input (as every reference dataset is)")
-        if latent_dim % 32 != 0:
-            raise ValueError("latent_dim must be a multiple of 32 for the tcgen05 tile shapes")
         self.encoder = Encoder(in_channels, latent_dim)
         self.decoder = Decoder(in_channels, latent_dim)
         _xavier_like_reference(self)
-        object.__setattr__(self.encoder, "_owner", self)
-        self._engine: Optional[ImageEngine] = None
-        self._engine_sig = None
 
-    # ---- prepared-weight cache -----------------------------------------------------------------------------
-    def _get_engine(self, device: torch.device) -> ImageEngine:
-        _refuse_training(self)
-        _refuse_cpu(device)
-        sig = _state_signature(self)
-        if self._engine is None or sig != self._engine_sig:
-            sd: Dict[str, torch.Tensor] = {k: v.detach() for k, v in self.state_dict().items()}
-            for k, v in sd.items():
-                if v.device != device:
-                    raise RuntimeError(f"model parameter {k} lives on {v.device} but the input is on {device}")
-            self._engine = ImageEngine(prep.prepare_image(sd))
-            self._engine_sig = sig
-        return self._engine
+    def _build(self, sd):
+        return ImageEngine(prep.prepare_image(sd))
 
     # ---- reference API -------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -144,6 +222,7 @@ class ConvAutoencoder(nn.Module):
 
     # ---- single-pass extension --------------------------------------------------------------
     @torch.no_grad()
-    def score_all(self, x: torch.Tensor, want_recon: bool = True, want_heat: bool = True) -> ScoreOutputs:
-        """One forward producing score [B], min/max [B,2] and optionally the heat map [B,H,W] and recon."""
-        return self._get_engine(x.device).run(x, want_recon=want_recon, want_heat=want_heat)
+    def score_all(self, x: torch.Tensor, want_recon: bool = True, want_heat: bool = True,
+                  want_latent: bool = False) -> ScoreOutputs:
+        """One forward producing score [B], min/max [B,2] and optionally the heat map [B,H,W], recon and latent."""
+        return self._get_engine(x.device).run(x, want_recon=want_recon, want_heat=want_heat, want_latent=want_latent)

@@ -12,53 +12,45 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from . import _native as nat
 from . import _prepare as prep
-from ._engine import ScoreOutputs, VideoEngine, _require_cuda_input
-from .autoencoder import _refuse_cpu, _refuse_training, _state_signature, _xavier_like_reference
+from ._engine import CellEngine, ScoreOutputs, VideoEngine
+from .autoencoder import _Prepared, _xavier_like_reference
 
 
-def _owner_required(owner, name: str):
-    if owner is None:
-        raise RuntimeError(f"{name} runs through its VideoAutoencoder (weights are prepared per model)")
-    return owner
-
-
-def _to_nhwc_bf16(x4: torch.Tensor) -> torch.Tensor:
-    n, c, h, w = x4.shape
-    out = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=x4.device)
-    nat.check(nat.load().vad_nchw_f32_to_nhwc_bf16(x4.data_ptr(), n, c, h, w, out.data_ptr(), nat.stream_ptr()),
-              "vad_nchw_f32_to_nhwc_bf16")
-    return out
-
-
-def _to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
-    n, h, w, c = x.shape
-    out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
-    nat.check(nat.load().vad_nhwc_bf16_to_nchw_f32(x.data_ptr(), n, h, w, c, out.data_ptr(), nat.stream_ptr()),
-              "vad_nhwc_bf16_to_nchw_f32")
-    return out
-
-
-class ConvLSTMCell(nn.Module):
-    """Holds the gate convolution over cat[x, h] (input_dim + hidden_dim -> 4 * hidden_dim, i/f/g/o order)."""
+class ConvLSTMCell(_Prepared):
+    """One ConvLSTM cell (reference models/video_autoencoder.py:24-91): gate convolution over cat[x, h]
+    (input_dim + hidden_dim -> 4 * hidden_dim, i/f/g/o order), sigma/sigma/tanh/sigma, c' = f*c + i*g, h' = o*tanh(c')."""
 
     def __init__(self, input_dim: int, hidden_dim: int, kernel_size: int = 3):
         super().__init__()
         if kernel_size != 3:
             raise ValueError("vad_b200 ConvLSTM kernels implement kernel_size=3 (the only size the reference uses)")
+        if input_dim % 32 or hidden_dim % 32:
+            raise ValueError("ConvLSTM input_dim and hidden_dim must be multiples of 32 for the tcgen05 tile shapes")
         self.input_dim = input_dim
         self.hidden_dim = hidden_dim
         self.conv = nn.Conv2d(input_dim + hidden_dim, 4 * hidden_dim, kernel_size=kernel_size,
                               padding=kernel_size // 2, bias=True)
+
+    def _build(self, sd):
+        return CellEngine(prep.prepare_lstm_cell(sd, prefix=""))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, hidden_state: Tuple[torch.Tensor, torch.Tensor]
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """x fp32 [B,input_dim,H,W], (h, c) fp32 [B,hidden_dim,H,W] -> (h_next, c_next) (:54-85): one gate GEMM with
+        the state update in its epilogue."""
+        h_cur, c_cur = hidden_state
+        return self._get_engine(x.device).step(x, h_cur, c_cur)
 
     def init_hidden(self, batch_size: int, height: int, width: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
         z = torch.zeros(batch_size, self.hidden_dim, height, width, device=device)
         return z, z.clone()
 
 
-class ConvLSTM(nn.Module):
-    """Stack of ConvLSTM cells; `forward` takes fp32 [B,T,C,H,W] and returns the last layer's hidden sequence."""
+class ConvLSTM(_Prepared):
+    """Stack of ConvLSTM cells (reference :94-179); `forward` takes fp32 [B,T,C,H,W] and returns the last layer's hidden
+    sequence and final (h, c)."""
 
     def __init__(self, input_dim: int, hidden_dims, kernel_size: int = 3, num_layers: int = 2,
                  batch_first: bool = True, return_all_layers: bool = False):
@@ -71,37 +63,36 @@ class ConvLSTM(nn.Module):
         self.cells = nn.ModuleList(
             ConvLSTMCell(input_dim if i == 0 else self.hidden_dims[i - 1], self.hidden_dims[i], kernel_size)
             for i in range(self.num_layers))
-        self._owner: Optional["VideoAutoencoder"] = None
+
+    def _build(self, sd):
+        return VideoEngine(prep.prepare_convlstm(sd, prefix=""))
 
     def _init_hidden(self, batch_size: int, height: int, width: int, device) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         return [cell.init_hidden(batch_size, height, width, device) for cell in self.cells]
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, hidden_state=None):
-        owner = _owner_required(self._owner, "ConvLSTM")
         if hidden_state is not None:
-            raise RuntimeError("vad_b200 ConvLSTM always starts from the zero state, as every reference caller does "
-                               "(video_autoencoder.py:144-145, :343)")
+            raise RuntimeError("vad_b200 ConvLSTM.forward always starts from the zero state, as every reference caller "
+                               "does (video_autoencoder.py:144-145, :343); step a ConvLSTMCell for custom states")
         if self.return_all_layers:
             raise RuntimeError("return_all_layers=True is not on the scoring path")
         if not self.batch_first:
             x = x.permute(1, 0, 2, 3, 4)
-        x = _require_cuda_input(x, (5,))
-        b, t, c, h, w = x.shape
-        eng = owner._get_engine(x.device)
-        seq = _to_nhwc_bf16(x.view(b * t, c, h, w))
-        out = eng.convlstm(seq.view(b, t, h, w, c), b, t, h, w)
-        hid = out.shape[-1]
-        out5 = _to_nchw_f32(out.view(b * t, h, w, hid)).view(b, t, hid, h, w)
-        cst = eng.bufs.get(f"c{self.num_layers - 1}", (b, h, w, hid), torch.float32, x.device)
-        return out5, (out5[:, -1], cst.permute(0, 3, 1, 2).contiguous())
+        out, c_last = self._get_engine(x.device).convlstm(x)
+        return out, (out[:, -1], c_last)
 
 
-class VideoEncoder(nn.Module):
-    """4 x [conv3x3-BN-LeakyReLU-maxpool2]: 3 -> 32 -> 64 -> 128 -> latent_dim; 5-D input folds T into the batch."""
+class VideoEncoder(_Prepared):
+    """4 x [conv3x3-BN-LeakyReLU-maxpool2]: 3 -> 32 -> 64 -> 128 -> latent_dim (reference :182-231); 5-D input folds T
+    into the batch."""
 
     def __init__(self, in_channels: int = 3, latent_dim: int = 128):
         super().__init__()
+        if in_channels != 3:
+            raise ValueError("vad_b200 kernels are specialised for 3-channel input (as every reference dataset is)")
+        if latent_dim % 32:
+            raise ValueError("latent_dim must be a multiple of 32 for the tcgen05 tile shapes")
         layers = []
         cin = in_channels
         for cout in (32, 64, 128, latent_dim):
@@ -109,24 +100,29 @@ class VideoEncoder(nn.Module):
                        nn.LeakyReLU(0.2, inplace=True), nn.MaxPool2d(2, 2)]
             cin = cout
         self.encoder = nn.Sequential(*layers)
-        self._owner: Optional["VideoAutoencoder"] = None
+
+    def _build(self, sd):
+        return VideoEngine(prep.prepare_video_encoder(sd, prefix="encoder."))
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        owner = _owner_required(self._owner, "VideoEncoder")
-        x = _require_cuda_input(x, (4, 5))
-        five_d = x.dim() == 5
-        x4 = x.view(-1, *x.shape[-3:])
-        z, h, w = owner._get_engine(x.device).encode(x4)
-        out = _to_nchw_f32(z)
-        return out.view(x.shape[0], x.shape[1], *out.shape[1:]) if five_d else out
+        if x.dim() not in (4, 5):
+            raise RuntimeError(f"expected a 4-D or 5-D input, got shape {tuple(x.shape)}")
+        x4 = x.reshape(-1, *x.shape[-3:])
+        _, out = self._get_engine(x.device).encode(x4, want_f32=True, want_bf16=False)
+        return out.view(x.shape[0], x.shape[1], *out.shape[1:]) if x.dim() == 5 else out
 
 
-class VideoDecoder(nn.Module):
-    """4 x convT k2 s2: latent_dim -> 128 -> 64 -> 32 -> out_channels (BN+ReLU on the first three, Tanh last)."""
+class VideoDecoder(_Prepared):
+    """4 x convT k2 s2: latent_dim -> 128 -> 64 -> 32 -> out_channels (BN+ReLU on the first three, Tanh last; reference
+    :234-276); accepts [B,C,h,w] frames or [B,T,C,h,w] sequences."""
 
     def __init__(self, out_channels: int = 3, latent_dim: int = 128):
         super().__init__()
+        if out_channels != 3:
+            raise ValueError("vad_b200 kernels are specialised for 3-channel output (as every reference dataset is)")
+        if latent_dim % 32:
+            raise ValueError("latent_dim must be a multiple of 32 for the tcgen05 tile shapes")
         layers = []
         cin = latent_dim
         for cout in (128, 64, 32):
@@ -135,10 +131,20 @@ class VideoDecoder(nn.Module):
             cin = cout
         layers += [nn.ConvTranspose2d(cin, out_channels, kernel_size=2, stride=2), nn.Tanh()]
         self.decoder = nn.Sequential(*layers)
-        self._owner: Optional["VideoAutoencoder"] = None
+
+    def _build(self, sd):
+        return VideoEngine(prep.prepare_video_decoder(sd, prefix="decoder."))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() not in (4, 5):
+            raise RuntimeError(f"expected a 4-D or 5-D input, got shape {tuple(x.shape)}")
+        z4 = x.reshape(-1, *x.shape[-3:])
+        out = self._get_engine(x.device).decode(z4)
+        return out.view(x.shape[0], x.shape[1], *out.shape[1:]) if x.dim() == 5 else out
 
 
-class VideoAutoencoder(nn.Module):
+class VideoAutoencoder(_Prepared):
     """Encoder -> ConvLSTM -> (1x1 proj if hidden != latent) -> decoder, scored by fused sm_100a kernels.
 
     `forward`, `get_reconstruction_error(x, per_frame, per_pixel)` follow the reference (:329-384) including
@@ -148,10 +154,6 @@ class VideoAutoencoder(nn.Module):
     def __init__(self, in_channels: int = 3, latent_dim: int = 128, lstm_hidden_dim: int = 128,
                  lstm_num_layers: int = 2):
         super().__init__()
-        if in_channels != 3:
-            raise ValueError("vad_b200 kernels are specialised for 3-channel input (as every reference dataset is)")
-        if latent_dim % 32 or lstm_hidden_dim % 32:
-            raise ValueError("latent_dim and lstm_hidden_dim must be multiples of 32 for the tcgen05 tile shapes")
         self.encoder = VideoEncoder(in_channels, latent_dim)
         self.convlstm = ConvLSTM(input_dim=latent_dim, hidden_dims=[lstm_hidden_dim] * lstm_num_layers, kernel_size=3,
                                  num_layers=lstm_num_layers, batch_first=True, return_all_layers=False)
@@ -159,23 +161,9 @@ class VideoAutoencoder(nn.Module):
             else nn.Identity()
         self.decoder = VideoDecoder(in_channels, latent_dim)
         _xavier_like_reference(self)
-        for sub in (self.encoder, self.convlstm, self.decoder):
-            object.__setattr__(sub, "_owner", self)
-        self._engine: Optional[VideoEngine] = None
-        self._engine_sig = None
 
-    def _get_engine(self, device: torch.device) -> VideoEngine:
-        _refuse_training(self)
-        _refuse_cpu(device)
-        sig = _state_signature(self)
-        if self._engine is None or sig != self._engine_sig:
-            sd: Dict[str, torch.Tensor] = {k: v.detach() for k, v in self.state_dict().items()}
-            for k, v in sd.items():
-                if v.device != device:
-                    raise RuntimeError(f"model parameter {k} lives on {v.device} but the input is on {device}")
-            self._engine = VideoEngine(prep.prepare_video(sd))
-            self._engine_sig = sig
-        return self._engine
+    def _build(self, sd):
+        return VideoEngine(prep.prepare_video(sd))
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
