@@ -73,7 +73,7 @@ def test_reference_callers_load_the_dropin(dropin_results):
     assert ours["device"] == "cuda" and ref["device"] == "cpu"
 
 
-@pytest.mark.parametrize("tag,rtol,gap", [("image_init", 1e-3, 1e-5), ("image_stress", 1e-3, 1e-3)])
+@pytest.mark.parametrize("tag,rtol,gap", [("image_init", 1e-3, 1e-5), ("image_stress", 5e-3, 1e-2)])
 def test_reference_compute_auroc_on_dropin(dropin_results, tag, rtol, gap):
     """evaluate.load_model + evaluate.compute_auroc (evaluate.py:26-91) on the repo's synthetic test set (config 1)."""
     ref, ours = dropin_results

@@ -652,3 +652,35 @@ def test_concurrent_streams_and_threads(cuda_device):
             assert torch.equal(oi.score, want_i[k].score) and torch.equal(oi.heat, want_i[k].heat)
             assert torch.equal(ov.score, want_v[k].score) and torch.equal(ov.heat, want_v[k].heat)
             assert torch.equal(ov.recon, want_v[k].recon)
+
+
+def test_stress_error_budget_over_seeds(cuda_device):
+    """Where the bf16 error of the path comes from, as a number: six independently drawn trained-like weight sets.
+    The deviation from the fp32 reference is dominated by the rounding of the WEIGHTS to bf16 (a fixed perturbation of
+    the network, so it does not average out over pixels the way activation rounding does; tools/bf16_error_budget.py
+    separates the two on the CPU: all-weights-fp32 leaves 2e-4, all-activations-fp32 leaves 2.6e-3 for seed 1).  It is
+    a random draw per checkpoint: the kernels must sit inside the band the CPU emulation of "bf16 weights, bf16
+    activations, fp32 accumulate" predicts — median <= 1.5e-3, every seed <= 5e-3 — and must agree with that
+    emulation itself far more tightly than with the fp32 oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bf16_error_budget as budget
+    from models import ConvAutoencoder
+    errs, vs_emul = [], []
+    x = image_input(808, 8, 128, 128)
+    for seed in range(1, 7):
+        torch.manual_seed(0)
+        m = ConvAutoencoder()
+        sd = stress_state_dict(m.state_dict(), seed=seed)
+        m.load_state_dict(sd)
+        m = m.eval().to(cuda_device)
+        got = m.get_reconstruction_error(x.to(cuda_device)).cpu()
+        with torch.no_grad():
+            ref = vad_oracle.image_reconstruction_error(sd, x)
+            emu = budget.image_emulated(sd, x)
+        errs.append(rel_err(got.numpy(), ref.numpy()))
+        vs_emul.append(rel_err(got.numpy(), emu.numpy()))
+    print("\nstress seeds 1..6: score rel err vs fp32 oracle " + " ".join(f"{e:.2e}" for e in errs)
+          + " | vs the bf16 CPU emulation " + " ".join(f"{e:.2e}" for e in vs_emul))
+    assert max(errs) <= SCORE_RTOL_STRESS and float(np.median(errs)) <= 1.5e-3
+    assert max(vs_emul) <= 5e-4

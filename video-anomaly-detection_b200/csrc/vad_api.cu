@@ -1164,7 +1164,11 @@ int vad_convlstm_sequence(const vad_conv_desc* d, int T, vad_stream_t stream_) {
   }
   static const int pdl = env_int("VAD_PDL", 1);  // 0: plain stream order between the steps
   for (int t = 0; t < T; ++t) {
-    a.pdl = pdl ? (t == 0 ? 1 : 2) : 0;
+    // Step t >= 1 (pdl 2) starts its x half of the K loop BEFORE waiting for the previous launch, and every kernel
+    // releases its dependents as soon as it starts, so a whole run of step kernels can be resident while whatever
+    // produced the x sequence (the encoder's last layer; layer 1 for layer 2) is still running.  Step 0 is therefore a
+    // plain stream-ordered launch: it — and with it every later step — starts only after ALL earlier work completed.
+    a.pdl = (pdl && t > 0) ? 2 : 0;
     a.tA0 = t;
     a.tA1 = t > 0 ? t - 1 : 0;
     a.chunks1 = t > 0 ? chunks1 : 0;  // step 0: h_{-1} = 0, skip the h half of K

@@ -306,6 +306,7 @@ class CellEngine:
 
     def __init__(self, w: GemmWeights) -> None:
         self.w = w
+        self.device = w.bias.device
         self.g = _gemm_struct(w)
         self.lib = nat.load()
 
