@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the anomaly-scoring hot path (recon + heat map + score) — prints ONE JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1..cfg5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1..cfg5] [--impl ours|reference|reference_cuda]
 
 A "step" is one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json configs[1]
-(cfg2): image ConvAutoencoder, 256 x 3x256x256, random-init weights (torch.manual_seed(0)), fp32 input in [-1,1].
+(cfg2): image ConvAutoencoder, 256 x 3x256x256, random-init weights (torch.manual_seed(0)), SURVEY §8d's input recipe.
   value  : frames/s with the batch resident in HBM (CUDA events, max over ranks), all outputs produced
            (per-frame score + min/max + per-pixel heat map; the reconstruction stays on-chip).
-  e2e    : frames/s through the public Python API from PINNED HOST memory, H2D + D2H inside the timed region.
+  e2e    : frames/s through the public Python API from PINNED HOST memory: H2D of every step's frames, the scoring
+           call, D2H of its scores and heat maps — all inside the timed region, pipelined over three buffers.
   roofline: the dominant kernel of the step, timed live with CUDA events, against MEASURED_PEAKS.json.
-  cpu_baseline: the oracle's restatement of the reference path on the host cores (bounded sample).
+  cpu_baseline / gpu_library_baseline: the UNMODIFIED reference (baseline/_ref, vendored by tools/vendor_ref.sh) on the
+           host cores / through torch eager + cuDNN on this GPU; each runs in its own interpreter (`--impl reference`,
+           `--impl reference_cuda`) because its package is also called `models`.
 N > 1 (torchrun): each rank scores its own batch (weak scaling); per-frame scores are gathered to rank 0 with NCCL
-inside the timed step.  `--impl reference` times the reference's CPU path (oracle port) instead.
+inside the timed step, and rank 0 re-scores rank 1's batch to check the gathered row bit for bit (`sharding_check`).
+`--impl reference` times the reference's own CPU path: each step is a bounded sample of the workload (the reference's
+own call shape), `ms_per_step` is what a step really took.
 """
 import argparse
 import json
@@ -23,11 +28,12 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "video-anomaly-detection_b200"))
-sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "video-anomaly-detection_b200")
+REF = os.path.join(ROOT, "baseline", "_ref")
 
 import torch  # noqa: E402
 
+METRIC = "frames/sec scored (recon+heatmap+score)"
 WORKLOADS = {
     # name: (kind, batch, T, H, W, GFLOP per frame [SURVEY §8d], description)
     "cfg1": ("image", 32, 1, 256, 256, 8.1118, "image AE, synthetic 256x256 RGB, batch 32"),
@@ -39,6 +45,10 @@ WORKLOADS = {
     "cfg5": ("video", 1, 64, 720, 1280, 42.349, "720p clips sharded over the GPUs (one 64-frame clip per GPU and step), "
                                                   "per-frame score gather"),
 }
+# what one step of the reference arm covers: the reference's own call shapes (evaluate.py:238-243 batch 16;
+# evaluate_video.py:123-128 batch 4 x 16 frames; 720p: 8 frames of one stream — the per-frame cost does not depend on T)
+REFERENCE_SAMPLE = {"cfg1": (16, 1), "cfg2": (16, 1), "cfg3": (4, 16), "cfg4": (1, 8), "cfg5": (1, 8)}
+ANOMALY_FRACTION = 0.76  # 63 of the 83 MVTec-bottle test images are anomalous
 
 
 def peaks():
@@ -49,15 +59,24 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
 
 
+def use_package(path):
+    """Put ONE of the two packages called `models` (ours / the reference's) first on the import path."""
+    for p in (path, ROOT):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, path)
+
+
 def synth_input(kind, B, T, H, W, device, seed=1234):
-    """SURVEY §8d recipe: per-frame amplitude a~U[0.3,1], low-passed noise + fine noise, clamp [-1,1]."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    n = B * T
-    amp = 0.3 + 0.7 * torch.rand(n, 1, 1, 1, generator=g, device=device)
-    coarse = torch.rand(n, 3, H // 8, W // 8, generator=g, device=device) * 2 - 1
-    x = amp * torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=False)
-    x = (x + 0.05 * torch.randn(n, 3, H, W, generator=g, device=device)).clamp_(-1, 1)
-    return x.view(B, T, 3, H, W) if kind == "video" else x
+    """SURVEY §8d recipe (runtime/synthetic.py, loaded by path: it only needs torch): per-frame amplitude, low-passed
+    noise + fine noise, anomaly patches on 76 % of the frames."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vad_synthetic", os.path.join(PKG, "runtime", "synthetic.py"))
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    x, labels = syn.synth_frames(B * T, H, W, device, seed=seed, anomaly_fraction=ANOMALY_FRACTION)
+    return (x.view(B, T, 3, H, W) if kind == "video" else x), labels
 
 
 def build_model(kind, device):
@@ -117,13 +136,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "power_w_max": max(pw) if pw else None}
 
 
-def run_model(model, kind, x, want_heat=True):
-    out = model.score_all(x, want_recon=False, want_heat=want_heat)
-    return out.score
-
-
 def layer_cost(kind, name, B, T, H, W):
-    """(algorithmic FLOPs, algorithmic HBM bytes) of one launch, by layer name — SURVEY Appendix A conventions:
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one layer of one step, by layer name — SURVEY Appendix A conventions:
     2*M*N*K with un-padded K, N; bytes = input + output activations (bf16 NHWC; model input fp32) + outputs."""
     F = B * T
     img = {  # name: (cin, cout, H_in divisor, taps, kind, pooled)
@@ -141,7 +155,7 @@ def layer_cost(kind, name, B, T, H, W):
         "decoder.3": (128, 64, 8, 1, "convt", False), "decoder.6": (64, 32, 4, 1, "convt", False),
         "decoder.9+score": (32, 3, 2, 1, "scoret", False),
     }
-    if name.startswith("convlstm."):  # one launch group = the T steps of one layer (step 0 skips the h half of K)
+    if name.startswith("convlstm."):  # one entry = the T steps of one layer (step 0 skips the h half of K)
         h, w = H // 16, W // 16
         flops = 2.0 * B * h * w * 512 * 9 * (128 + 256 * (T - 1))
         byts = B * h * w * ((128 * 2 * 2 + 128 * 2 + 128 * 4 * 2) * T - 128 * 2 - 128 * 4)
@@ -175,89 +189,127 @@ def layer_cost(kind, name, B, T, H, W):
     return flops, in_b + out_b
 
 
-def cpu_baseline(kind, T, H, W, budget_s=12.0):
-    """The reference's CPU path (oracle restatement: same torch ops, fp32) on the host cores, bounded sample."""
-    from oracle import vad_oracle
+def base_config(workload):
+    kind, B, T, H, W, _, desc = WORKLOADS[workload]
+    return {"workload": f"{workload}: {desc}", "frames_per_step_per_gpu": B * T,
+            "input": f"{B}x{'%dx' % T if kind == 'video' else ''}3x{H}x{W} fp32",
+            "weights": "random init, torch.manual_seed(0)",
+            "l2": f"batch input {B * T * 3 * H * W * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
+            if B * T * 3 * H * W * 4 > 126e6 else "L2 flushed between steps by a 256 MB memset",
+            "outputs": "per-frame score + min/max + per-pixel heat map"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arms (own interpreter: the reference's package is called `models` too)
+# ------------------------------------------------------------------------------------------------------------------
+def reference_main(args, on_cuda):
+    """The reference's own implementation of the path: baseline/_ref (unmodified, `kind: reference`) when vendored, else
+    the oracle's restatement (`kind: port`).  CPU arm: all host threads; one step = REFERENCE_SAMPLE frames."""
+    kind, B, T, H, W, _, _ = WORKLOADS[args.workload]
+    nb, nt = REFERENCE_SAMPLE[args.workload]
+    if on_cuda:
+        nb = min(B, 64 if kind == "image" else 8)  # eager fp32 activations of a full cfg2 batch would be ~20 GB
+        nt = T if H * W <= 256 * 256 else min(T, 8)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if on_cuda else torch.device("cpu")
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    m = build_model(kind, "cpu")
-    sd = vad_oracle.cpu_sd(m.state_dict())
-    nb = 8 if kind == "image" else 2
-    if H * W > 256 * 256:  # 720p: one window of 8 frames (the per-frame cost does not depend on T, SURVEY §8d)
-        nb, T = 1, min(T, 8)
-    x = synth_input(kind, nb, T, H, W, "cpu")
-    fn = (lambda: vad_oracle.image_reconstruction_error(sd, x)) if kind == "image" else \
-         (lambda: vad_oracle.video_reconstruction_error(sd, x, per_frame=True))
+    x, _ = synth_input(kind, nb, nt, H, W, "cpu")
+    x = x.to(dev)
+    have_ref = os.path.isdir(os.path.join(REF, "models"))
+    if have_ref:
+        use_package(REF)
+        sys.dont_write_bytecode = True
+        torch.manual_seed(0)
+        if kind == "image":
+            from models import ConvAutoencoder
+            m = ConvAutoencoder().eval().to(dev)
+            fn = lambda: m.get_reconstruction_error(x, per_pixel=False)                 # evaluate.py:63
+        else:
+            from models.video_autoencoder import VideoAutoencoder
+            m = VideoAutoencoder().eval().to(dev)
+            fn = lambda: m.get_reconstruction_error(x, per_frame=True)                  # evaluate_video.py:150
+        import models as ref_models
+        assert "baseline/_ref" in ref_models.__file__.replace("\\", "/"), ref_models.__file__
+        impl_kind, what = "reference", "baseline/_ref (the unmodified reference classes)"
+    else:
+        use_package(PKG)
+        from oracle import vad_oracle
+        sd = {k: v.to(dev) for k, v in vad_oracle.cpu_sd(build_model(kind, "cpu").state_dict()).items()}
+        fn = (lambda: vad_oracle.image_reconstruction_error(sd, x)) if kind == "image" else \
+             (lambda: vad_oracle.video_reconstruction_error(sd, x, per_frame=True))
+        impl_kind, what = "port", "oracle/vad_oracle.py (baseline/_ref not vendored)"
+    warm = max(1, min(args.warmup, 5))
     with torch.no_grad():
-        fn()  # warm-up
-        best, t_all, reps = float("inf"), time.perf_counter(), 0
-        while reps < 3 or (time.perf_counter() - t_all < budget_s and reps < 50):
-            t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0); reps += 1
-    return {"value": round(nb * T / best, 2), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{nb} x {'%dx' % T if kind == 'video' else ''}3x{H}x{W} fp32, best of {reps}, "
-                      f"oracle/vad_oracle.py (torch {torch.__version__} CPU ops)"}
-
-
-def gpu_library_baseline(kind, B, T, H, W, dev, x):
-    """The reference's own GPU path — the same torch ops in eager mode on cuDNN (fp32, TF32 allowed as by default) —
-    timed with CUDA events on this GPU: the library bar the hand-written kernels are measured against.
-    Uses the oracle's restatement of the reference forward on CUDA tensors; scores only (one forward)."""
-    from oracle import vad_oracle
-    m = build_model(kind, "cpu")
-    sd = {k: v.to(dev) for k, v in vad_oracle.cpu_sd(m.state_dict()).items()}
-    nb = min(B, 64 if kind == "image" else 8)  # eager fp32 activations of the full batch would not all fit comfortably
-    xs = x[:nb]
-    fn = (lambda: vad_oracle.image_reconstruction_error(sd, xs)) if kind == "image" else \
-         (lambda: vad_oracle.video_reconstruction_error(sd, xs, per_frame=True))
-    with torch.no_grad():
-        for _ in range(3):
+        for _ in range(warm):
             fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 10
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    return {"value": round(nb * T / (ms * 1e-3), 1), "unit": "frames/s", "kind": "torch eager + cuDNN on the same GPU",
-            "sample": f"{nb} x {'%dx' % T if kind == 'video' else ''}3x{H}x{W} fp32, scores only, torch {torch.__version__}"}
+        if on_cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = fn()
+        if on_cuda:
+            out.cpu()
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    frames = nb * nt * args.steps
+    value = round(frames / dt, 2)
+    sample = (f"each step = {nb} x {'%dx' % nt if kind == 'video' else ''}3x{H}x{W} fp32 "
+              f"({'the reference caller batch' if not on_cuda else 'sub-batch'}), {args.steps} timed steps after {warm} "
+              f"warm-up, {what}, torch {torch.__version__} "
+              + ("eager + cuDNN (TF32 convs as by default), scores only" if on_cuda else "CPU ops, scores only"))
+    base = {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": impl_kind, "sample": sample}
+    line = {"metric": METRIC, "value": value, "unit": "frames/s",
+            "impl": "reference" if not on_cuda else "reference_cuda", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * dt / args.steps, 3),
+            "frames_per_step": nb * nt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": base_config(args.workload), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
 
 
+def run_reference_subprocess(workload, impl, steps, warmup, timeout=600):
+    """-> the JSON line of `bench.py --impl <impl>` run in its own interpreter (an {"error": ...} dict if it failed)."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "PYTHONPATH"):
+        env.pop(k, None)
+    if impl == "reference":
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", impl, "--workload", workload, "--steps",
+                            str(steps), "--warmup", str(warmup)], env=env, capture_output=True, text=True, timeout=timeout)
+        return json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gpu-library-baseline", action="store_true",
-                    help="also time the reference's torch/cuDNN eager path on this GPU (extra key, rank 0, N=1)")
+    ap.add_argument("--no-gpu-library-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained / latency / score-only extras")
     args = ap.parse_args()
     kind, B, T, H, W, gflop_per_frame, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: {desc}", "frames_per_step_per_gpu": B * T, "input": f"{B}x{'%dx' % T if kind == 'video' else ''}3x{H}x{W} fp32",
-              "weights": "random init, torch.manual_seed(0)",
-              "l2": f"batch input {B * T * 3 * H * W * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
-              if B * T * 3 * H * W * 4 > 126e6 else "L2 flushed between steps by a 256 MB memset",
-              "outputs": "per-frame score + min/max + per-pixel heat map"}
 
-    if args.impl == "reference":
+    if args.impl != "ours":
         if rank != 0:
             return
-        base = cpu_baseline(kind, T, H, W, budget_s=max(10.0, 2.0 * args.steps))
-        line = {"metric": "frames/sec scored (recon+heatmap+score)", "value": base["value"], "unit": "frames/s",
-                "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(1000.0 * B * T / base["value"], 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": base,
-                "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+        reference_main(args, on_cuda=(args.impl == "reference_cuda"))
         return
 
+    use_package(PKG)
+    config = base_config(args.workload)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the scoring path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -279,12 +331,15 @@ def main():
 
     from models import _native as nat
     model = build_model(kind, dev)
-    x = synth_input(kind, B, T, H, W, dev, seed=1234 + rank)
+    x, labels = synth_input(kind, B, T, H, W, dev, seed=1234 + rank)
     flush = None if B * T * 3 * H * W * 4 > 126e6 else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = [torch.empty(B * T, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
+    def run_model(inp, want_heat=True):
+        return model.score_all(inp, want_recon=False, want_heat=want_heat)
+
     def step():
-        s = run_model(model, kind, x)
+        s = run_model(x).score
         if world > 1:
             dist.gather(s, gathered, dst=0)   # the path's only exchange: per-frame scores to rank 0 (NCCL / NVLink)
         return s
@@ -328,12 +383,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
 
+    # ---- multi-GPU correctness, driver-visible: rank 0 re-creates rank 1's seeded batch, scores it itself and compares
+    # the row NCCL delivered bit for bit (sharding must not change a single score bit: same kernels, other partition)
+    sharding_check = None
+    if world > 1:
+        if rank == 0:
+            x1, _ = synth_input(kind, B, T, H, W, dev, seed=1234 + 1)
+            mine = run_model(x1).score
+            sharding_check = bool(torch.equal(mine, gathered[1])) and bool(torch.equal(run_model(x).score, gathered[0]))
+            del x1
+        dist.barrier()
+
     # ---- per-kernel timing for the roofline: the library brackets every layer launch of the model-level call with CUDA
     # events on the launching stream (vad_profile_enable / vad_profile_dump), same inputs
     reps = 5
     nat.profile_enable(True)
     for _ in range(reps):
-        run_model(model, kind, x)
+        run_model(x)
     torch.cuda.synchronize()
     rows = nat.profile_dump()
     nat.profile_enable(False)
@@ -348,74 +414,81 @@ def main():
         for name, (ms, n) in acc.items():
             per.setdefault(name, []).append((ms, n))
     # one entry per layer name; a layer launched several times per step (ConvLSTM groups of clips) keeps its launch count
-    kern = {}
-    small = {}
+    kern, small = {}, {}
     for name, vals in per.items():
         ms = statistics.median(v[0] for v in vals)
         if name in ("finalize", "latent_out"):
             small[name] = ms
             continue
         kern[name] = {"ms": ms, "launches": vals[0][1], "rep": name}
-    total_kernel_ms = sum(d["ms"] for d in kern.values())
+    total_kernel_ms = sum(d["ms"] for d in kern.values()) + sum(small.values())
     top_name, top = max(kern.items(), key=lambda kv: kv[1]["ms"])
     pk = peaks()
     flops, byts = layer_cost(kind, top["rep"], B, T, H, W)
     flops, byts = flops / top["launches"], byts / top["launches"]
     avg_ms = top["ms"] / top["launches"]
-    ai = flops / byts
-    if ai >= pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9):
+    ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+    if flops / byts >= ridge:
         roof = {"bound": "tensor", "achieved": round(flops / (avg_ms * 1e-3) / 1e12, 2), "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s"}
     else:
         roof = {"bound": "hbm", "achieved": round(byts / (avg_ms * 1e-3) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s"}
     traffic = None
-    for tname in ("r01d_dram_traffic.json", "r01c_dram_traffic.json"):  # newest capture that has this kernel
+    for tname in ("r02_dram_traffic.json", "r01d_dram_traffic.json", "r01c_dram_traffic.json"):  # newest capture first
         tpath = os.path.join(ROOT, "profiles", tname)
         if traffic is None and os.path.exists(tpath):  # measured with ncu --set full at this exact shape (see profiles/)
             traffic = json.load(open(tpath)).get(args.workload, {}).get(top["rep"])
     # every kernel of the step against the roof its arithmetic intensity puts it under (same definitions as above)
-    ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
     per_kernel = {}
+    floor_ms = 0.0
     for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
         kf, kb = layer_cost(kind, v["rep"], B, T, H, W)
-        kms = v["ms"]  # (whole layer: all its launches of one step)
-        if kf / kb >= ridge:
-            per_kernel[k] = {"ms": round(v["ms"], 4), "bound": "tensor",
-                             "frac": round(kf / (kms * 1e-3) / 1e12 / pk["bf16_tflops"], 3)}
-        else:
-            per_kernel[k] = {"ms": round(v["ms"], 4), "bound": "hbm",
-                             "frac": round(kb / (kms * 1e-3) / 1e9 / pk["hbm_gbs"], 3)}
+        kms = v["ms"]  # whole layer: all its launches of one step
+        t_floor = max(kf / (pk["bf16_tflops"] * 1e12), kb / (pk["hbm_gbs"] * 1e9)) * 1e3
+        floor_ms += t_floor
+        per_kernel[k] = {"ms": round(kms, 4), "bound": "tensor" if kf / kb >= ridge else "hbm",
+                         "frac": round(t_floor / kms, 3)}
     roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": traffic, "kernel": top_name,
                  "launch_ms": round(avg_ms, 4), "share_of_step": round(top["ms"] / total_kernel_ms, 3),
                  "peak_src": pk["src"], "alg_flops_per_launch": flops, "alg_bytes_per_launch": byts,
-                 "per_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
+                 "step_floor_ms": round(floor_ms, 4), "step_frac_of_layerwise_roofline": round(floor_ms / total_kernel_ms, 3),
+                 "per_kernel_ms": {**{k: round(v["ms"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
+                                   **{k: round(v, 4) for k, v in small.items()}},
                  "per_kernel": per_kernel})
-    if top["rep"] in ("dec4.0+4.3+score",):
-        roof["note"] = ("fused decoder tail: algorithmic bytes are a third of the two layers it replaces, so the HBM "
-                        "fraction is low by construction; the kernel is bound by shared-memory bandwidth (N=16 MMAs "
-                        "stream a 4 KB A slab each; ncu smem wavefronts in profiles/)")
 
-    # ---- end to end through the public API from pinned host memory (double-buffered H2D on a side stream)
+    # ---- end to end through the public API from pinned host memory, three-deep pipeline: H2D of step i+1 (copy
+    # stream) | scoring of step i (main stream) | D2H of step i-1's scores + heat maps (drain stream)
+    NB = 3
     xh = x.cpu().pin_memory()
-    sh = torch.empty(B * T, dtype=torch.float32).pin_memory()
-    copy_stream = torch.cuda.Stream()
-    bufs = [torch.empty_like(x) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    copy_stream, drain_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    bufs = [torch.empty_like(x) for _ in range(NB)]
+    sh = [torch.empty(B * T, dtype=torch.float32).pin_memory() for _ in range(NB)]
+    hh = [torch.empty(B * T, H, W, dtype=torch.float32).pin_memory() for _ in range(NB)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    freed = [torch.cuda.Event() for _ in range(NB)]
+    drained = [torch.cuda.Event() for _ in range(NB)]
+    done = [torch.cuda.Event() for _ in range(NB)]
 
     def e2e_run(n):
         main_stream = torch.cuda.current_stream()
         for i in range(n):
-            b = i & 1
+            b = i % NB
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[b])
                 bufs[b].copy_(xh, non_blocking=True)
                 ready[b].record(copy_stream)
             main_stream.wait_event(ready[b])
-            s = model.get_reconstruction_error(bufs[b], per_frame=True) if kind == "video" else \
-                model.get_reconstruction_error(bufs[b])
+            out = model.score_all(bufs[b], want_recon=False, want_heat=True)
             freed[b].record(main_stream)
-            sh.copy_(s.reshape(-1), non_blocking=True)
+            done[b].record(main_stream)
+            with torch.cuda.stream(drain_stream):
+                drain_stream.wait_event(done[b])
+                drained[b].synchronize()                  # the pinned result buffers of step i - NB have been read out
+                sh[b].copy_(out.score, non_blocking=True)
+                hh[b].copy_(out.heat, non_blocking=True)
+                out.score.record_stream(drain_stream)
+                out.heat.record_stream(drain_stream)
+                drained[b].record(drain_stream)
         torch.cuda.synchronize()
 
     e2e_run(3)
@@ -435,59 +508,84 @@ def main():
             dist.destroy_process_group()
         return
     frames = B * T * world * args.steps
-    line = {"metric": "frames/sec scored (recon+heatmap+score)", "value": round(frames / (elapsed_ms * 1e-3), 1),
+    h2d = x.numel() * 4
+    d2h = B * T * 4 + B * T * H * W * 4
+    line = {"metric": METRIC, "value": round(frames / (elapsed_ms * 1e-3), 1),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "model_tflops": round(frames * gflop_per_frame * 1e9 / (elapsed_ms * 1e-3) / 1e12 / world, 2),
             "roofline": roof, "clocks": clocks,
-            "e2e": {"value": round(frames / e2e_s, 1), "unit": "frames/s", "h2d_bytes_per_step": x.numel() * 4,
-                    "d2h_bytes_per_step": B * T * 4, "note": "pinned host -> device copies double-buffered on a side stream"
+            "e2e": {"value": round(frames / e2e_s, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "h2d_gbs_per_gpu": round(h2d * args.steps / e2e_s / 1e9, 1),
+                    "d2h_gbs_per_gpu": round(d2h * args.steps / e2e_s / 1e9, 1),
+                    "note": "model.score_all from pinned host memory: fp32 frames up, per-frame scores + fp32 heat maps "
+                            "down, 3-deep pipeline on copy / compute / drain streams"
                     + (f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else "")},
             "gpu_launches": int(launches)}
-    # extra: the same end-to-end loop fed with the decoder's uint8 HWC frames, normalised on the device
-    # (a quarter of the PCIe bytes of the fp32 tensors the reference callers upload)
-    if world == 1:
-        from runtime import frames as fr
-        u8h = ((xh.reshape(-1, 3, H, W).permute(0, 2, 3, 1) * 0.5 + 0.5).clamp_(0, 1) * 255).to(torch.uint8).contiguous().pin_memory()
-        ubufs = [torch.empty_like(u8h, device=dev) for _ in range(2)]
+    if sharding_check is not None:
+        line["sharding_check"] = sharding_check
 
-        def e2e_u8(n):
-            main_stream = torch.cuda.current_stream()
-            for i in range(n):
-                b = i & 1
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[b])
-                    ubufs[b].copy_(u8h, non_blocking=True)
-                    ready[b].record(copy_stream)
-                main_stream.wait_event(ready[b])
-                xin = fr.normalize_u8(ubufs[b]).view(x.shape)
-                s_ = model.get_reconstruction_error(xin, per_frame=True) if kind == "video" else \
-                    model.get_reconstruction_error(xin)
-                freed[b].record(main_stream)
-                sh.copy_(s_.reshape(-1), non_blocking=True)
+    if not args.no_extras:
+        # apples-to-apples extra: scores only (no heat map written), the one output the reference computes per forward
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        run_model(x, want_heat=False)
+        e0.record()
+        for _ in range(min(args.steps, 10)):
+            run_model(x, want_heat=False)
+        e1.record()
+        torch.cuda.synchronize()
+        line["score_only"] = {"value": round(B * T * min(args.steps, 10) / (e0.elapsed_time(e1) * 1e-3), 1),
+                              "unit": "frames/s", "note": "rank 0, per GPU; heat map not materialised"}
+        # sustained: the same device-resident step back to back for >= 3 s (the power cap settles the clocks)
+        if flush is None:
+            n_sus = max(int(3000.0 / (elapsed_ms / args.steps)) + 1, args.steps)
+            sus = ClockSampler(local_rank)
+            sus.start()
+            e0.record()
+            for _ in range(n_sus):
+                run_model(x)
+            e1.record()
             torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            line["sustained"] = {"value": round(B * T * n_sus / (ms * 1e-3), 1), "unit": "frames/s", "steps": n_sus,
+                                 "seconds": round(ms * 1e-3, 2), "clocks": sus.stop(), "note": "rank 0, per GPU"}
+        # small-batch latency at the reference's real call shapes: one synchronous call (enqueue + kernels + sync)
+        shapes = [("image B=16 (evaluate.py:238-243)", (16, 3, H, W))] if kind == "image" else \
+                 [("video 4x16 (evaluate_video.py:123-128)", (4, 16, 3, min(H, 256), min(W, 256))),
+                  ("stream 1x16 (evaluate_video.py:322-326)", (1, 16, 3, min(H, 256), min(W, 256)))]
+        lat = {}
+        for label, shp in shapes:
+            xs, _ = synth_input(kind, shp[0], shp[1] if kind == "video" else 1, shp[-2], shp[-1], dev, seed=99)
+            for _ in range(5):
+                run_model(xs)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                run_model(xs).score.cpu()
+                ts.append((time.perf_counter() - t0) * 1e3)
+            nat.profile_enable(True)
+            for _ in range(5):
+                run_model(xs)
+            torch.cuda.synchronize()
+            krows = nat.profile_dump()
+            nat.profile_enable(False)
+            lat[label] = {"call_ms_median": round(statistics.median(ts), 4), "call_ms_min": round(min(ts), 4),
+                          "sum_of_kernel_ms": round(sum(ms for _, ms in krows) / 5, 4),
+                          "frames_per_s": round(xs.numel() / (3 * shp[-2] * shp[-1]) / (statistics.median(ts) * 1e-3), 1)}
+        line["small_batch_latency"] = lat
 
-        e2e_u8(3)
-        t0 = time.perf_counter()
-        e2e_u8(args.steps)
-        line["e2e_u8_frames"] = {"value": round(B * T * args.steps / (time.perf_counter() - t0), 1), "unit": "frames/s",
-                                 "h2d_bytes_per_step": u8h.numel(),
-                                 "note": "uint8 HWC frames uploaded, ToTensor+Normalize on the device (runtime/frames.py)"}
-    # apples-to-apples extra: scores only (no heat map written), the one output the reference computes per forward
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    run_model(model, kind, x, want_heat=False)
-    e0.record()
-    for _ in range(min(args.steps, 10)):
-        run_model(model, kind, x, want_heat=False)
-    e1.record()
-    torch.cuda.synchronize()
-    line["score_only"] = {"value": round(B * T * min(args.steps, 10) / (e0.elapsed_time(e1) * 1e-3), 1),
-                          "unit": "frames/s", "note": "rank 0, per GPU; heat map not materialised"}
-    if args.gpu_library_baseline and world == 1:
-        line["gpu_library_baseline"] = gpu_library_baseline(kind, B, T, H, W, dev, x)
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(kind, T, H, W)
+    if world == 1 and not args.no_gpu_library_baseline:
+        g = run_reference_subprocess(args.workload, "reference_cuda", 10, 3)
+        line["gpu_library_baseline"] = {"value": g.get("value"), "unit": "frames/s",
+                                        "kind": "the reference's own classes, torch eager + cuDNN on this GPU",
+                                        "sample": (g.get("cpu_baseline") or {}).get("sample", g.get("error"))}
+    if world == 1 and not args.no_cpu_baseline:
+        c = run_reference_subprocess(args.workload, "reference", 5 if H * W > 256 * 256 else 20, 2)
+        line["cpu_baseline"] = c.get("cpu_baseline") or {"value": None, "unit": "frames/s", "cores": os.cpu_count(),
+                                                         "kind": "reference", "sample": c.get("error", "failed")}
     if stdout_fd is not None:
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
