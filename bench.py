@@ -457,13 +457,20 @@ def main():
                  "per_kernel": per_kernel})
 
     # ---- end to end through the public API from pinned host memory, three-deep pipeline: H2D of step i+1 (copy
-    # stream) | scoring of step i (main stream) | D2H of step i-1's scores + heat maps (drain stream)
+    # stream) | scoring of step i (main stream) | D2H of step i-1's scores + heat maps (drain stream).
+    # The frames are what a decoder hands over — uint8 RGB, HWC (utils/dataset.py:65-70 normalises them on the host; here
+    # `model.score_frames` does it on the device) — and the heat maps come back as create_heatmap's uint8 normalisation
+    # (evaluate_video.py:56-57): every byte that crosses PCIe is one the caller actually needs.
     NB = 3
-    xh = x.cpu().pin_memory()
+    xf = x.reshape(-1, 3, H, W)
+    u8 = ((xf * 0.5 + 0.5).clamp_(0, 1) * 255).round_().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    u8 = u8.view(B, T, H, W, 3) if kind == "video" else u8
+    u8h = u8.cpu().pin_memory()
+    del xf, u8
     copy_stream, drain_stream = torch.cuda.Stream(), torch.cuda.Stream()
-    bufs = [torch.empty_like(x) for _ in range(NB)]
+    bufs = [torch.empty(u8h.shape, dtype=torch.uint8, device=dev) for _ in range(NB)]
     sh = [torch.empty(B * T, dtype=torch.float32).pin_memory() for _ in range(NB)]
-    hh = [torch.empty(B * T, H, W, dtype=torch.float32).pin_memory() for _ in range(NB)]
+    hh = [torch.empty(B * T, H, W, dtype=torch.uint8).pin_memory() for _ in range(NB)]
     ready = [torch.cuda.Event() for _ in range(NB)]
     freed = [torch.cuda.Event() for _ in range(NB)]
     drained = [torch.cuda.Event() for _ in range(NB)]
@@ -475,19 +482,19 @@ def main():
             b = i % NB
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[b])
-                bufs[b].copy_(xh, non_blocking=True)
+                bufs[b].copy_(u8h, non_blocking=True)
                 ready[b].record(copy_stream)
             main_stream.wait_event(ready[b])
-            out = model.score_all(bufs[b], want_recon=False, want_heat=True)
+            out = model.score_frames(bufs[b], want_recon=False, want_heat=False, want_heat_u8=True)
             freed[b].record(main_stream)
             done[b].record(main_stream)
             with torch.cuda.stream(drain_stream):
                 drain_stream.wait_event(done[b])
                 drained[b].synchronize()                  # the pinned result buffers of step i - NB have been read out
                 sh[b].copy_(out.score, non_blocking=True)
-                hh[b].copy_(out.heat, non_blocking=True)
+                hh[b].copy_(out.heat_u8, non_blocking=True)
                 out.score.record_stream(drain_stream)
-                out.heat.record_stream(drain_stream)
+                out.heat_u8.record_stream(drain_stream)
                 drained[b].record(drain_stream)
         torch.cuda.synchronize()
 
@@ -508,8 +515,8 @@ def main():
             dist.destroy_process_group()
         return
     frames = B * T * world * args.steps
-    h2d = x.numel() * 4
-    d2h = B * T * 4 + B * T * H * W * 4
+    h2d = u8h.numel()
+    d2h = B * T * 4 + B * T * H * W
     line = {"metric": METRIC, "value": round(frames / (elapsed_ms * 1e-3), 1),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
@@ -520,8 +527,9 @@ def main():
                     "d2h_bytes_per_step": d2h,
                     "h2d_gbs_per_gpu": round(h2d * args.steps / e2e_s / 1e9, 1),
                     "d2h_gbs_per_gpu": round(d2h * args.steps / e2e_s / 1e9, 1),
-                    "note": "model.score_all from pinned host memory: fp32 frames up, per-frame scores + fp32 heat maps "
-                            "down, 3-deep pipeline on copy / compute / drain streams"
+                    "note": "model.score_frames from pinned host memory: uint8 HWC frames up (normalised on the device), "
+                            "per-frame scores + uint8 heat maps (evaluate_video.py:56-57) down, 3-deep pipeline on copy / "
+                            "compute / drain streams"
                     + (f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else "")},
             "gpu_launches": int(launches)}
     if sharding_check is not None:
@@ -538,6 +546,37 @@ def main():
         torch.cuda.synchronize()
         line["score_only"] = {"value": round(B * T * min(args.steps, 10) / (e0.elapsed_time(e1) * 1e-3), 1),
                               "unit": "frames/s", "note": "rank 0, per GPU; heat map not materialised"}
+        # the reference callers' own shape of the loop (evaluate.py:58-64): fp32 tensors up, scores down, double-buffered
+        if world == 1:
+            xh = x.cpu().pin_memory()
+            fb = [torch.empty_like(x) for _ in range(2)]
+            s32 = torch.empty(B * T, dtype=torch.float32).pin_memory()
+            r2, f2 = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+
+            def e2e_fp32(n):
+                main_stream = torch.cuda.current_stream()
+                for i in range(n):
+                    b = i & 1
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(f2[b])
+                        fb[b].copy_(xh, non_blocking=True)
+                        r2[b].record(copy_stream)
+                    main_stream.wait_event(r2[b])
+                    sc = model.get_reconstruction_error(fb[b], per_frame=True) if kind == "video" else \
+                        model.get_reconstruction_error(fb[b])
+                    f2[b].record(main_stream)
+                    s32.copy_(sc.reshape(-1), non_blocking=True)
+                torch.cuda.synchronize()
+
+            e2e_fp32(2)
+            t0 = time.perf_counter()
+            e2e_fp32(min(args.steps, 10))
+            dt = time.perf_counter() - t0
+            line["e2e_fp32_upload"] = {"value": round(B * T * min(args.steps, 10) / dt, 1), "unit": "frames/s",
+                                       "h2d_bytes_per_step": x.numel() * 4, "d2h_bytes_per_step": B * T * 4,
+                                       "note": "get_reconstruction_error on fp32 tensors uploaded per step, as the "
+                                               "reference callers do (PCIe-bound: 4x the bytes of the uint8 frames)"}
+            del xh, fb
         # sustained: the same device-resident step back to back for >= 3 s (the power cap settles the clocks)
         if flush is None:
             n_sus = max(int(3000.0 / (elapsed_ms / args.steps)) + 1, args.steps)

@@ -244,7 +244,8 @@ enum vad_op {
   VAD_OP_ENCODE = 1,        /* vad_image_forward with only `latent` requested / vad_video_encode */
   VAD_OP_DECODE = 2,        /* vad_image_decode / vad_video_decode */
   VAD_OP_CONVLSTM = 3,      /* vad_convlstm_forward */
-  VAD_OP_SCORE_LATENTS = 4  /* vad_video_score_latents */
+  VAD_OP_SCORE_LATENTS = 4, /* vad_video_score_latents */
+  VAD_OP_FORWARD_U8 = 5     /* vad_image_forward_u8 / vad_video_forward_u8 */
 };
 /* Workspace the given entry point needs for this shape (T ignored by the image model); 0 = invalid arguments. */
 size_t vad_image_workspace_bytes(const vad_image_model* m, int op, int B, int H, int W);
@@ -257,6 +258,13 @@ size_t vad_video_workspace_bytes(const vad_video_model* m, int op, int B, int T,
  * Only `latent` requested: the encoder alone runs (Encoder.forward, :81-86). */
 int vad_image_forward(const vad_image_model* m, const float* x, int B, int H, int W, float* recon, float* latent,
                       float* score, float* minmax, float* heat, void* ws, size_t ws_bytes, vad_stream_t stream);
+/* The same from the decoder's uint8 frames: frames uint8 RGB [B,H,W,3] are normalised on the device exactly like the
+ * reference datasets do on the host (ToTensor + Normalize(.5,.5): utils/dataset.py:65-70), so a caller uploads a quarter
+ * of the bytes; heat_u8 (optional) uint8 [B,H,W] is create_heatmap's per-frame normalisation of the error map
+ * (evaluate_video.py:56-57, bit-exact) — a quarter of the bytes to download.  Other outputs as vad_image_forward. */
+int vad_image_forward_u8(const vad_image_model* m, const uint8_t* frames, int B, int H, int W, float* recon, float* latent,
+                         float* score, float* minmax, float* heat, uint8_t* heat_u8, void* ws, size_t ws_bytes,
+                         vad_stream_t stream);
 /* Decoder.forward — models/autoencoder.py:141-146: z fp32 [B,latent,h,w] -> recon fp32 [B,3,16h,16w]. */
 int vad_image_decode(const vad_image_model* m, const float* z, int B, int h, int w, float* recon, void* ws,
                      size_t ws_bytes, vad_stream_t stream);
@@ -268,6 +276,10 @@ int vad_image_decode(const vad_image_model* m, const float* z, int B, int h, int
  * in resident-size groups of clips. */
 int vad_video_forward(const vad_video_model* m, const float* x, int B, int T, int H, int W, float* recon, float* score,
                       float* minmax, float* heat, void* ws, size_t ws_bytes, vad_stream_t stream);
+/* ... from uint8 frames [B,T,H,W,3] (utils/video_dataset.py:62-66,141-144), optional uint8 heat maps [B*T,H,W]. */
+int vad_video_forward_u8(const vad_video_model* m, const uint8_t* frames, int B, int T, int H, int W, float* recon,
+                         float* score, float* minmax, float* heat, uint8_t* heat_u8, void* ws, size_t ws_bytes,
+                         vad_stream_t stream);
 /* VideoEncoder.forward — :217-231: frames fp32 [F,3,H,W] -> latent fp32 [F,latent,H/16,W/16] and / or the bf16 NHWC
  * [F,H/16,W/16,latent] tensor vad_video_score_latents consumes (either may be NULL). */
 int vad_video_encode(const vad_video_model* m, const float* x, int F, int H, int W, float* latent, void* latent_bf16,

@@ -80,3 +80,37 @@ def test_ssim_loss_matches_reference_golden_and_oracle(cuda_device, name):
     np.testing.assert_allclose(float(comb.mean()), gold[f"{name}_combined"], rtol=1e-4, atol=2e-6)
     ref_map = vad_oracle.ssim_map(p, t)
     assert float((smap.cpu() - ref_map).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("kind", ["image", "video"])
+def test_score_frames_u8_equals_normalised_fp32_path(cuda_device, kind):
+    """`model.score_frames(uint8 frames)` (one C call: device-side ToTensor + Normalize, the forward, uint8 heat maps) ==
+    `model.score_all(host-normalised fp32 frames)` bit for bit; heat_u8 == create_heatmap's numpy normalisation
+    (evaluate_video.py:56-57) of the fp32 map, byte for byte."""
+    from oracle.stress import stress_state_dict
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(5)
+    if kind == "image":
+        from models import ConvAutoencoder
+        m = ConvAutoencoder()
+        u8 = torch.randint(0, 256, (3, 64, 96, 3), generator=g, dtype=torch.uint8)
+        x = (u8.float().div(255).permute(0, 3, 1, 2) - 0.5) / 0.5               # utils/dataset.py:65-70
+    else:
+        from models.video_autoencoder import VideoAutoencoder
+        m = VideoAutoencoder()
+        u8 = torch.randint(0, 256, (2, 3, 48, 64, 3), generator=g, dtype=torch.uint8)
+        x = (u8.float().div(255).permute(0, 1, 4, 2, 3) - 0.5) / 0.5
+    m.load_state_dict(stress_state_dict(m.state_dict(), seed=1))
+    m = m.eval().to(cuda_device)
+    a = m.score_frames(u8.to(cuda_device), want_recon=True, want_heat=True, want_heat_u8=True)
+    b = m.score_all(x.contiguous().to(cuda_device), want_recon=True, want_heat=True)
+    assert torch.equal(a.score, b.score) and torch.equal(a.minmax, b.minmax)
+    assert torch.equal(a.heat, b.heat) and torch.equal(a.recon, b.recon)
+    e = b.heat.cpu().numpy()
+    ref_u8 = np.stack([(((f - f.min()) / (f.max() - f.min() + 1e-8)) * 255).astype(np.uint8) for f in e])
+    assert np.array_equal(a.heat_u8.cpu().numpy(), ref_u8)
+    only8 = m.score_frames(u8.to(cuda_device))                               # defaults: scores + uint8 heat maps only
+    assert only8.heat is None and only8.recon is None
+    assert torch.equal(only8.score, b.score) and torch.equal(only8.heat_u8, a.heat_u8)
+    with pytest.raises(RuntimeError, match="uint8"):
+        m.score_frames(x.to(cuda_device))

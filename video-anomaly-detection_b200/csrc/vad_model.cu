@@ -511,6 +511,34 @@ int video_decode_impl(Ctx& c, const vad_video_model& m, const float* zf, int F, 
   return video_decode_score(c, m, z, 0, F, h, w, s);
 }
 
+// ---- uint8 HWC frames in, (optionally) normalised uint8 heat maps out: the decoder-facing form of the two forwards ----
+// (ToTensor + Normalize on the device: utils/dataset.py:65-70, utils/video_dataset.py:62-66; create_heatmap's
+// normalisation: evaluate_video.py:56-57.)  The fp32 frames / heat maps the kernels work on live in the workspace.
+struct U8Io {
+  float* x = nullptr;     // normalised frames fp32 [F,3,H,W] (workspace)
+  float* heat = nullptr;  // fp32 heat map actually written (caller's, or workspace when only heat_u8 is wanted)
+  float* minmax = nullptr;
+};
+
+int u8_prepare(Ctx& c, const uint8_t* frames, int F, int H, int W, float* heat, float* minmax, uint8_t* heat_u8, U8Io& io) {
+  io.x = static_cast<float*>(c.A.persist(static_cast<size_t>(F) * 3 * H * W * 4));
+  io.heat = heat;
+  io.minmax = minmax;
+  if (heat_u8) {
+    if (!io.heat) io.heat = static_cast<float*>(c.A.persist(static_cast<size_t>(F) * H * W * 4));
+    if (!io.minmax) io.minmax = static_cast<float*>(c.A.persist(static_cast<size_t>(F) * 2 * 4));
+  }
+  if (c.dry()) return VAD_OK;
+  ProfScope p("u8_to_f32", c.stream);
+  return vad_u8_hwc_to_f32_nchw(frames, F, H, W, io.x, c.stream);
+}
+
+int u8_finish(Ctx& c, const U8Io& io, int F, int H, int W, uint8_t* heat_u8) {
+  if (!heat_u8 || c.dry()) return VAD_OK;
+  ProfScope p("heat_u8", c.stream);
+  return vad_heatmap_u8(io.heat, io.minmax, F, H, W, heat_u8, c.stream);
+}
+
 // fp32 NCHW <-> NHWC (ConvLSTM cell state at the sub-module boundary)
 __global__ void f32_nchw_to_nhwc_kernel(const float* __restrict__ src, long long total, int HW, int C,
                                         float* __restrict__ dst) {
@@ -675,6 +703,15 @@ size_t vad_image_workspace_bytes(const vad_image_model* m, int op, int B, int H,
     case VAD_OP_DECODE:  // H, W are the LATENT extent here
       if (!image_model_ok(m, false, true) || H <= 0 || W <= 0) return 0;
       return measure([&](Ctx& c) { return image_decode_impl(c, *m, nullptr, B, H, W, nullptr); });
+    case VAD_OP_FORWARD_U8:
+      if (!image_model_ok(m, true, true) || !hw_ok(H, W)) return 0;
+      return measure([&](Ctx& c) {
+        float dummy;
+        uint8_t dummy8;
+        U8Io io;
+        VAD_TRY(u8_prepare(c, nullptr, B, H, W, nullptr, nullptr, &dummy8, io));  // heat map + min/max in the workspace
+        return image_forward_impl(c, *m, nullptr, B, H, W, &dummy, &dummy, nullptr, &dummy, &dummy);
+      });
     default:
       return 0;
   }
@@ -718,6 +755,14 @@ size_t vad_video_workspace_bytes(const vad_video_model* m, int op, int B, int T,
     case VAD_OP_CONVLSTM:  // H x W = latent extent
       if (!video_model_ok(m, false, true, false) || H <= 0 || W <= 0) return 0;
       return measure([&](Ctx& c) { return convlstm_forward_impl(c, *m, nullptr, B, T, H, W, nullptr, nullptr, nullptr); });
+    case VAD_OP_FORWARD_U8:
+      if (!video_model_ok(m, true, true, true) || !hw_ok(H, W)) return 0;
+      return measure([&](Ctx& c) {
+        uint8_t dummy8;
+        U8Io io;
+        VAD_TRY(u8_prepare(c, nullptr, B * T, H, W, nullptr, nullptr, &dummy8, io));
+        return video_forward_impl(c, *m, nullptr, B, T, H, W, &dummy, nullptr, &dummy, &dummy);
+      });
     case VAD_OP_SCORE_LATENTS:  // H x W = latent extent
       if (!video_model_ok(m, false, true, true) || H <= 0 || W <= 0) return 0;
       return measure([&](Ctx& c) {
@@ -735,6 +780,38 @@ int vad_video_forward(const vad_video_model* m, const float* x, int B, int T, in
   if (!hw_ok(H, W)) return VAD_ERR_SHAPE;
   return run([&](Ctx& c) { return video_forward_impl(c, *m, x, B, T, H, W, recon, score, minmax, heat); }, ws, ws_bytes,
              stream);
+}
+
+int vad_image_forward_u8(const vad_image_model* m, const uint8_t* frames, int B, int H, int W, float* recon, float* latent,
+                         float* score, float* minmax, float* heat, uint8_t* heat_u8, void* ws, size_t ws_bytes,
+                         vad_stream_t stream) {
+  if (!frames || B <= 0 || (!recon && !latent && !score && !minmax && !heat && !heat_u8)) return VAD_ERR_ARG;
+  if (!image_model_ok(m, true, recon || score || minmax || heat || heat_u8)) return VAD_ERR_ARG;
+  if (!hw_ok(H, W)) return VAD_ERR_SHAPE;
+  return run(
+      [&](Ctx& c) {
+        U8Io io;
+        VAD_TRY(u8_prepare(c, frames, B, H, W, heat, minmax, heat_u8, io));
+        VAD_TRY(image_forward_impl(c, *m, io.x, B, H, W, recon, latent, score, io.minmax, io.heat));
+        return u8_finish(c, io, B, H, W, heat_u8);
+      },
+      ws, ws_bytes, stream);
+}
+
+int vad_video_forward_u8(const vad_video_model* m, const uint8_t* frames, int B, int T, int H, int W, float* recon,
+                         float* score, float* minmax, float* heat, uint8_t* heat_u8, void* ws, size_t ws_bytes,
+                         vad_stream_t stream) {
+  if (!frames || B <= 0 || T <= 0 || (!recon && !score && !minmax && !heat && !heat_u8)) return VAD_ERR_ARG;
+  if (!video_model_ok(m, true, true, true)) return VAD_ERR_ARG;
+  if (!hw_ok(H, W)) return VAD_ERR_SHAPE;
+  return run(
+      [&](Ctx& c) {
+        U8Io io;
+        VAD_TRY(u8_prepare(c, frames, B * T, H, W, heat, minmax, heat_u8, io));
+        VAD_TRY(video_forward_impl(c, *m, io.x, B, T, H, W, recon, score, io.minmax, io.heat));
+        return u8_finish(c, io, B * T, H, W, heat_u8);
+      },
+      ws, ws_bytes, stream);
 }
 
 int vad_video_encode(const vad_video_model* m, const float* x, int F, int H, int W, float* latent, void* latent_bf16,

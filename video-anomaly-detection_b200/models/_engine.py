@@ -37,6 +37,7 @@ class ScoreOutputs:
     heat: Optional[torch.Tensor]        # [frames, H, W] fp32 per-pixel channel-mean squared error
     recon: Optional[torch.Tensor]       # [frames, 3, H, W] fp32
     latent: Optional[torch.Tensor] = None  # [frames, latent, H/16, W/16] fp32 (image model, on request)
+    heat_u8: Optional[torch.Tensor] = None  # [frames, H, W] uint8: create_heatmap's per-frame normalisation of `heat`
 
 
 def _require_cuda_input(x: torch.Tensor, ndim: Tuple[int, ...]) -> torch.Tensor:
@@ -48,6 +49,16 @@ def _require_cuda_input(x: torch.Tensor, ndim: Tuple[int, ...]) -> torch.Tensor:
     if x.dtype != torch.float32:
         x = x.float()
     return x.contiguous()
+
+
+def _require_u8_frames(frames: torch.Tensor, ndim: Tuple[int, ...]) -> torch.Tensor:
+    if not frames.is_cuda:
+        raise RuntimeError("vad_b200 scoring path is CUDA-only (sm_100a kernels, no CPU fallback); "
+                           f"got a tensor on {frames.device}")
+    if frames.dtype != torch.uint8 or frames.dim() not in ndim or frames.shape[-1] != 3:
+        raise RuntimeError(f"expected uint8 RGB frames [..., H, W, 3] with {ndim[0]} dimensions, got "
+                           f"{frames.dtype} {tuple(frames.shape)}")
+    return frames.contiguous()
 
 
 def _check_hw(H: int, W: int) -> None:
@@ -150,6 +161,24 @@ class ImageEngine:
                                                  c.ws_bytes, c.stream), "vad_image_forward")
         return ScoreOutputs(score, minmax, heat, recon, latent)
 
+    def run_u8(self, frames: torch.Tensor, want_recon: bool, want_heat: bool, want_heat_u8: bool) -> ScoreOutputs:
+        """uint8 RGB frames [B,H,W,3] (as decoded) -> scores (+ heat maps): normalisation happens on the device."""
+        frames = _require_u8_frames(frames, (4,))
+        B, H, W, _ = frames.shape
+        _check_hw(H, W)
+        dev = frames.device
+        self.m.flags = _flags()
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        minmax = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        heat = torch.empty(B, H, W, dtype=torch.float32, device=dev) if want_heat else None
+        heat8 = torch.empty(B, H, W, dtype=torch.uint8, device=dev) if want_heat_u8 else None
+        recon = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_recon else None
+        with _Call(dev, self._ws(nat.OP_FORWARD_U8, B, H, W), "vad_image_forward_u8") as c:
+            nat.check(self.lib.vad_image_forward_u8(C.byref(self.m), frames.data_ptr(), B, H, W, nat.ptr(recon), None,
+                                                    score.data_ptr(), minmax.data_ptr(), nat.ptr(heat), nat.ptr(heat8),
+                                                    c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_image_forward_u8")
+        return ScoreOutputs(score, minmax, heat, recon, None, heat8)
+
     def latent(self, x: torch.Tensor) -> torch.Tensor:
         """Encoder.forward / get_latent: fp32 [B,3,H,W] -> fp32 [B,latent,H/16,W/16]."""
         x = _require_cuda_input(x, (4,))
@@ -236,6 +265,20 @@ class VideoEngine:
                                                  score.data_ptr(), minmax.data_ptr(), nat.ptr(heat), c.ws.data_ptr(),
                                                  c.ws_bytes, c.stream), "vad_video_forward")
         return ScoreOutputs(score, minmax, heat, recon)
+
+    def run_u8(self, frames: torch.Tensor, want_recon: bool, want_heat: bool, want_heat_u8: bool) -> ScoreOutputs:
+        """uint8 RGB clips [B,T,H,W,3] (as decoded) -> per-frame scores (+ heat maps)."""
+        frames = _require_u8_frames(frames, (5,))
+        B, T, H, W, _ = frames.shape
+        _check_hw(H, W)
+        self.m.flags = _flags()
+        score, minmax, heat, recon = self._outputs(B * T, H, W, want_recon, want_heat, frames.device)
+        heat8 = torch.empty(B * T, H, W, dtype=torch.uint8, device=frames.device) if want_heat_u8 else None
+        with _Call(frames.device, self._ws(nat.OP_FORWARD_U8, B, T, H, W), "vad_video_forward_u8") as c:
+            nat.check(self.lib.vad_video_forward_u8(C.byref(self.m), frames.data_ptr(), B, T, H, W, nat.ptr(recon),
+                                                    score.data_ptr(), minmax.data_ptr(), nat.ptr(heat), nat.ptr(heat8),
+                                                    c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_video_forward_u8")
+        return ScoreOutputs(score, minmax, heat, recon, None, heat8)
 
     def encode(self, x4: torch.Tensor, want_f32: bool = False, want_bf16: bool = True):
         """frames fp32 [F,3,H,W] -> (bf16 NHWC [F,h,w,latent] or None, fp32 NCHW [F,latent,h,w] or None)."""

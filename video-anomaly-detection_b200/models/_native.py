@@ -23,13 +23,13 @@ EXPORTS = (
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8", "vad_u8_hwc_to_f32_nchw", "vad_f32_nchw_to_u8_hwc",
     "vad_heatmap_jet_rgb", "vad_ssim_scratch_bytes", "vad_ssim_loss",
     # model-level entry points (one call per reference method)
-    "vad_image_workspace_bytes", "vad_image_forward", "vad_image_decode", "vad_video_workspace_bytes",
-    "vad_video_forward", "vad_video_encode", "vad_video_score_latents", "vad_video_decode", "vad_convlstm_forward",
+    "vad_image_workspace_bytes", "vad_image_forward", "vad_image_forward_u8", "vad_image_decode",
+    "vad_video_workspace_bytes", "vad_video_forward", "vad_video_forward_u8", "vad_video_encode", "vad_video_score_latents", "vad_video_decode", "vad_convlstm_forward",
     "vad_convlstm_cell_workspace_bytes", "vad_convlstm_cell", "vad_profile_enable", "vad_profile_dump",
 )
 
 FLAG_NO_FUSED_TAIL, FLAG_NO_LSTM_WAVEFRONT = 1, 2
-OP_FORWARD, OP_ENCODE, OP_DECODE, OP_CONVLSTM, OP_SCORE_LATENTS = range(5)
+OP_FORWARD, OP_ENCODE, OP_DECODE, OP_CONVLSTM, OP_SCORE_LATENTS, OP_FORWARD_U8 = range(6)
 MAX_LSTM_LAYERS = 8
 
 
@@ -132,6 +132,8 @@ def load() -> C.CDLL:
     lib.vad_image_workspace_bytes.restype = Z
     lib.vad_image_workspace_bytes.argtypes = [C.POINTER(ImageModel), I, I, I, I]
     lib.vad_image_forward.argtypes = [C.POINTER(ImageModel), P, I, I, I, P, P, P, P, P, P, Z, P]
+    lib.vad_image_forward_u8.argtypes = [C.POINTER(ImageModel), P, I, I, I, P, P, P, P, P, P, P, Z, P]
+    lib.vad_video_forward_u8.argtypes = [C.POINTER(VideoModel), P, I, I, I, I, P, P, P, P, P, P, Z, P]
     lib.vad_image_decode.argtypes = [C.POINTER(ImageModel), P, I, I, I, P, P, Z, P]
     lib.vad_video_workspace_bytes.restype = Z
     lib.vad_video_workspace_bytes.argtypes = [C.POINTER(VideoModel), I, I, I, I, I]

@@ -226,3 +226,12 @@ class ConvAutoencoder(_Prepared):
                   want_latent: bool = False) -> ScoreOutputs:
         """One forward producing score [B], min/max [B,2] and optionally the heat map [B,H,W], recon and latent."""
         return self._get_engine(x.device).run(x, want_recon=want_recon, want_heat=want_heat, want_latent=want_latent)
+
+    @torch.no_grad()
+    def score_frames(self, frames_u8: torch.Tensor, want_recon: bool = False, want_heat: bool = False,
+                     want_heat_u8: bool = True) -> ScoreOutputs:
+        """Score decoded frames directly: uint8 RGB [B,H,W,3] on the GPU.  ToTensor + Normalize(.5,.5) of the reference
+        datasets (utils/dataset.py:65-70) happen on the device, and `heat_u8` is create_heatmap's uint8 normalisation
+        of each error map (evaluate_video.py:56-57) — a caller moves a quarter of the bytes in both directions.
+        Results equal `score_all(normalised fp32 frames)` bit for bit."""
+        return self._get_engine(frames_u8.device).run_u8(frames_u8, want_recon, want_heat, want_heat_u8)

@@ -184,3 +184,11 @@ class VideoAutoencoder(_Prepared):
     @torch.no_grad()
     def score_all(self, x: torch.Tensor, want_recon: bool = True, want_heat: bool = True) -> ScoreOutputs:
         return self._get_engine(x.device).run(x, want_recon=want_recon, want_heat=want_heat)
+
+    @torch.no_grad()
+    def score_frames(self, frames_u8: torch.Tensor, want_recon: bool = False, want_heat: bool = False,
+                     want_heat_u8: bool = True) -> ScoreOutputs:
+        """Score decoded clips directly: uint8 RGB [B,T,H,W,3] on the GPU (normalised on the device like
+        utils/video_dataset.py:62-66 does on the host); `heat_u8` [B*T,H,W] is create_heatmap's uint8 normalisation of
+        each frame's error map (evaluate_video.py:56-57).  Results equal `score_all(normalised fp32 clips)` bit for bit."""
+        return self._get_engine(frames_u8.device).run_u8(frames_u8, want_recon, want_heat, want_heat_u8)
