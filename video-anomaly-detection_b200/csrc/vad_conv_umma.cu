@@ -2576,11 +2576,14 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
 //   ep 1     bias + ReLU, bf16 -> a 16 x 32 pixel PATCH of the intermediate in smem (pixel p = y*32 + x at p*64 B with
 //            the SWIZZLE_64B pattern on absolute address bits; pixels outside the image are written as zeros = the
 //            3x3 conv's padding)
-//   stage 2  five 16 x 8 sub-tiles at patch columns 6s: D2[s][q][kx*3 + co] = sum_ky A(patch + (ky*32 + 6s) px,
-//            row pitch 32 px) · W2[ky]^T — the kx-folded form of conv_kx_kernel (3 x 2 MMAs each, N = 16), into D1's columns
-//   ep 2     out[y][x] = D2[x-1][kx=0] + D2[x][1] + D2[x+1][2] (two lane shuffles), tanh, (x - recon)^2, heat, partials.
+//   stage 2  four sub-tiles of 4 patch rows x 32 columns (128 consecutive patch pixels, dense 8-pixel row groups):
+//            D2[s][p][kx*3 + co] = sum_ky A(patch + (4s + ky) rows) · W2[ky]^T — the kx-folded form of conv_kx_kernel
+//            (3 x 2 MMAs each, N = 16), into D1's columns.  (Round 1 used five 16 x 8 sub-tiles at columns 6s: 30 MMAs
+//            and five epilogue passes with 84 of 128 lanes scoring, strided 6-pixel global accesses.)
+//   ep 2     out[y][x] = D2[x-1][kx=0] + D2[x][1] + D2[x+1][2] (two lane shuffles along the row a warp holds), tanh,
+//            (x - recon)^2, heat, partials: 30 of 32 lanes score, 120-byte contiguous x / heat / recon accesses.
 // Valid outputs of a tile: patch rows 1..14 x columns 1..30 = output rows [14*th - 1, 14*th + 13), columns
-// [30*tw - 1, 30*tw + 29) — tiles overlap by one input pixel, 75-80 % of stage 1 and 66 % of stage 2 is useful work,
+// [30*tw - 1, 30*tw + 29) — tiles overlap by one input pixel, 75-80 % of stage 1 and 82 % of stage 2 is useful work,
 // which is cheap next to the 2.1 GB of HBM traffic saved per batch.
 constexpr int kI2Groups = 4;
 constexpr int kI2Stages = 8;
@@ -2698,7 +2701,7 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
     // ===================================================================== stage-2 MMA issuer (kx-folded 3x3 conv)
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 16);
     const uint32_t a2r0 = smem_addr_once(&a2_ready_bar[0]), d2f0 = smem_addr_once(&d2_full_bar[0]);
-    const uint64_t da_hi = umma_smem_desc(0, 32 * 64, 4u);  // 8-row groups = patch rows, 32 pixels (2048 B) apart
+    const uint64_t da_hi = umma_smem_desc(0, 8 * 64, 4u);  // dense: 8-pixel groups follow each other along the patch rows
     const uint64_t db0 = umma_smem_desc(smem_u32(s_w2), 512, 4u);
     const uint32_t sp16 = (smem_u32(s_p) & 0x3FFFF) >> 4;
     int g = 0, j = 0;
@@ -2709,11 +2712,12 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
       if (elect_one()) {
         const uint32_t p16 = sp16 + static_cast<uint32_t>(g * (kI2PatchBytes >> 4));
 #pragma unroll
-        for (int s = 0; s < 5; ++s) {
+        for (int s = 0; s < 4; ++s) {
+          // sub-tile s = patch rows 4s .. 4s+3, all 32 columns (128 consecutive patch pixels); tap ky starts ky rows down
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128 + s * 16);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint64_t da = da_hi | static_cast<uint64_t>(p16 + (((ky * 32 + 6 * s) * 64) >> 4));
+            const uint64_t da = da_hi | static_cast<uint64_t>(p16 + ((((4 * s + ky) * 32) * 64) >> 4));
             const uint64_t db = db0 + static_cast<uint64_t>((ky * 1024) >> 4);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
@@ -2744,28 +2748,31 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
     const float* b2 = s_bias + 128;
     const bool relu = a.slope == 0.f;     // (the model's case: ReLU folded into the bf16 conversion)
     const int iy = r >> 4, ix = r & 15;   // ep 1: this accumulator row's input pixel inside the 8 x 16 block
-    const int srow = r >> 3, scol = r & 7;  // ep 2: this accumulator row's pixel inside a 16 x 8 sub-tile
+    // ep 2: sub-tile s covers patch rows 4s .. 4s+3 x all 32 columns, so warp quarter q holds row 4s + q and a lane one
+    // column: 30 of 32 lanes score a pixel (the kx fold reaches two lanes to the right) and x / heat / recon accesses
+    // are 120-byte contiguous per warp
     uint32_t ph = 0;
     for (TileIter ti(a, blockIdx.x + g * gridDim.x, G * gridDim.x); ti.tile < a.total_tiles; ti.next(a), ph ^= 1u) {
       const int oy0 = 14 * ti.th - 2, ox0 = 30 * ti.tw - 2;  // output coordinates of patch pixel (0, 0)
       const int fb = ti.tb;
       const int m_tile = (ti.tb * a.tiles_h + ti.th) * a.tiles_w + ti.tw;
-      // the model-input pixels this lane scores in the five sub-tiles (in flight while both GEMM stages run)
+      // the model-input pixels this lane scores in the four sub-tiles (in flight while both GEMM stages run)
       // (one 64-bit pixel offset per tile; everything else is 32-bit index arithmetic from there — the host checks that
-      // a frame's three planes fit an int — and the five validity tests are done once, as a bit mask)
-      const int oy = oy0 + 1 + srow, oxb = ox0 + 1 + scol;  // this lane's output pixel in sub-tile s: (oy, oxb + 6 s)
-      const bool row_ok = scol < 6 && srow < 14 && oy >= 0 && oy < Ho;
-      const long long pix = static_cast<long long>(oy) * Wo + oxb;             // (never dereferenced when !row_ok)
+      // a frame's three planes fit an int — and the validity tests are done once, as a bit mask)
+      const int oy = oy0 + 1 + q, ox = ox0 + 1 + lane;  // this lane's output pixel in sub-tile s: (oy + 4 s, ox)
+      const bool col_ok = lane < 30 && ox >= 0 && ox < Wo;
+      const long long pix = static_cast<long long>(oy) * Wo + ox;             // (never dereferenced when !ok)
       const float* xt = a.x + static_cast<long long>(fb) * 3 * plane + pix;
       uint32_t okmask = 0;
 #pragma unroll
-      for (int s = 0; s < 5; ++s) okmask |= (row_ok && oxb + 6 * s >= 0 && oxb + 6 * s < Wo) ? (1u << s) : 0u;
+      for (int s = 0; s < 4; ++s)
+        okmask |= (col_ok && 4 * s + q < 14 && oy + 4 * s >= 0 && oy + 4 * s < Ho) ? (1u << s) : 0u;
       if (a.dbg & 128) okmask = 0;  // ablation: no x loads (and nothing scored)
-      float xs[5][3];
+      float xs[4][3];
 #pragma unroll
-      for (int s = 0; s < 5; ++s) {
+      for (int s = 0; s < 4; ++s) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) xs[s][ch] = ((okmask >> s) & 1u) ? __ldg(xt + ch * plane_i + 6 * s) : 0.f;
+        for (int ch = 0; ch < 3; ++ch) xs[s][ch] = ((okmask >> s) & 1u) ? __ldg(xt + ch * plane_i + 4 * s * Wo) : 0.f;
       }
 
       // ---- ep 1: transposed conv's bias + ReLU -> bf16 patch (zeros outside the image: the 3x3 conv's padding).
@@ -2824,12 +2831,12 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
       uint32_t wa[16], wb[16];
       tmem_ld_x16(tacc, wa);
 #pragma unroll
-      for (int s = 0; s < 5; ++s) {
+      for (int s = 0; s < 4; ++s) {
         uint32_t (&v)[16] = (s & 1) ? wb : wa;
         uint32_t (&vn)[16] = (s & 1) ? wa : wb;
         tmem_ld_wait();
-        if (s < 4) tmem_ld_x16(tacc + (s + 1) * 16, vn);  // next sub-tile's accumulator in flight during this one's math
-        if (s == 4) {  // the group's TMEM columns are free for the next tile's stage 1
+        if (s < 3) tmem_ld_x16(tacc + (s + 1) * 16, vn);  // next sub-tile's accumulator in flight during this one's math
+        if (s == 3) {  // the group's TMEM columns are free for the next tile's stage 1
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_a(acce);
@@ -2850,9 +2857,9 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
           if (want_recon) {
             float* rt = a.recon + static_cast<long long>(fb) * 3 * plane + pix;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) rt[ch * plane_i + 6 * s] = rec[ch];
+            for (int ch = 0; ch < 3; ++ch) rt[ch * plane_i + 4 * s * Wo] = rec[ch];
           }
-          if (want_heat) a.heat[static_cast<long long>(fb) * plane + pix + 6 * s] = sq * (1.f / 3.f);
+          if (want_heat) a.heat[static_cast<long long>(fb) * plane + pix + 4 * s * Wo] = sq * (1.f / 3.f);
           ssum += sq;
           smin = fminf(smin, sq);
           smax = fmaxf(smax, sq);
