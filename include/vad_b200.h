@@ -154,6 +154,14 @@ int vad_first_conv(const float* x, const float* weight /* fp32 [27][cout], k = (
 int vad_first_conv_tc(const float* x, const void* weight_bf16, const float* bias, float slope, int pool, int B, int H,
                       int W, void* out_bf16_nhwc, vad_stream_t stream);
 
+/* The pooled first layer (video encoder: conv3x3 + BN + LeakyReLU + 2x2 max-pool, models/video_autoencoder.py:193-196)
+ * with the pooling window folded into the GEMM N extent (one accumulator row per POOLED pixel, K = the 4x4x3 input
+ * window): weight_pf is bf16 [128][64], row = pos*32 + co with pos = py*2 + px the output's place in its 2x2 window,
+ * column k = ((py+ky)*4 + (px+kx))*3 + ci holding w[co][ci][ky][kx] (zero elsewhere, columns 48..63 zero).
+ * H, W even; out bf16 NHWC [B,H/2,W/2,32]. */
+int vad_first_conv_pool(const float* x, const void* weight_pf, const float* bias, float slope, int B, int H, int W,
+                        void* out_bf16_nhwc, vad_stream_t stream);
+
 /* ---- scoring reduction ----------------------------------------------------------------------------------------
  * reference models/autoencoder.py:214-221, models/video_autoencoder.py:371-384, evaluate_video.py:56 (min/max) */
 /* finalize the partials of a fused *_SCORE layer (tiles_per_frame = 4 x the frame's tiles: one entry per tile quarter)
@@ -213,6 +221,7 @@ typedef struct vad_gemm_weights {
 typedef struct vad_first_weights {
   const float* w;    /* fp32 [27][cout] (vad_first_conv) */
   const void* w_tc;  /* bf16 [cout][32] (vad_first_conv_tc); NULL: CUDA-core kernel */
+  const void* w_pf;  /* bf16 [128][64] (vad_first_conv_pool, cout = 32): used when the layer is pooled; NULL: w_tc path */
   const float* bias; /* fp32 [cout] */
   int cout;
 } vad_first_weights;

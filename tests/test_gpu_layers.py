@@ -115,15 +115,21 @@ def test_convt2x2(cuda_device, cin, cout, B, H, W):
     _assert_close(out, _nhwc(ref), f"convT {cin}->{cout} B{B} {H}x{W}")
 
 
-@pytest.mark.parametrize("pool", [False, True])
-@pytest.mark.parametrize("B,H,W", [(2, 32, 64), (3, 16, 16), (1, 48, 80)])
+@pytest.mark.parametrize("pool", [False, True, "folded"])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 64), (3, 16, 16), (1, 48, 80), (1, 720, 1280), (5, 128, 128), (2, 16, 48)])
 def test_first_conv(cuda_device, pool, B, H, W):
+    """First layer straight from the fp32 NCHW input: plain (image enc1.0), pooled on the one-row-per-input-pixel kernel
+    (pool=True) and pooled on the kernel that folds the 2x2 window into the GEMM N extent ("folded": the video encoder's
+    default; partial tiles at 16x16 / 16x48 / 720p)."""
     eng, nat, prep = _mods()
     dev = cuda_device
+    folded = pool == "folded"
+    pool = bool(pool)
     g = torch.Generator().manual_seed(5)
     w = torch.randn(32, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
     b = torch.randn(32, generator=g) * 0.1
-    fw = prep.to_device({"w": prep.pack_first_conv(w.double(), b.double())}, dev)["w"]
+    fw = prep.to_device({"w": prep.pack_first_conv(w.double(), b.double(), pooled=folded)}, dev)["w"]
+    assert (fw.w_pf is not None) == folded
     x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     out = torch.full((B, Ho, Wo, 32), float("nan"), dtype=torch.bfloat16, device=dev)

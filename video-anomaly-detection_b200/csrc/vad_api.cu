@@ -1263,6 +1263,61 @@ int vad_first_conv_tc(const float* x, const void* weight, const float* bias, flo
   return launch_conv_first(pool ? VAD_EPI_POOL : VAD_EPI_STORE, a, grid, stream);
 }
 
+int vad_first_conv_pool(const float* x, const void* weight_pf, const float* bias, float slope, int B, int H, int W,
+                        void* out, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !weight_pf || !bias || !out || B <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  if ((H | W) & 1) return VAD_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(weight_pf) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0) return VAD_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || W % 4 != 0) return VAD_ERR_SHAPE;
+  ensure_trap_slot();
+  ConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  const int Hp = H / 2, Wp = W / 2;
+  a.pair = 1;
+  a.n_tiles = 1;
+  a.tiles_w = (Wp + 15) / 16;  // tiles of 8 x 16 POOLED pixels
+  a.tiles_h = (Hp + 7) / 8;
+  a.tiles_b = B;
+  const long long tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * B;
+  if (tiles > 0x7fffffffLL) return VAD_ERR_SHAPE;
+  a.total_tiles = static_cast<int>(tiles);
+  a.B = B; a.H = H; a.W = W;
+  a.bias = bias;
+  a.slope = slope;
+  a.x = x;
+  a.w_first = weight_pf;
+  a.out = out;
+  a.cout = 32;
+  a.dbg = env_int("VAD_DBG", 0);
+  a.pdl = pdl_all_setting() ? 1 : 0;
+  {
+    // fp32 NCHW input as a 4-D map {W, H, 3, B}; box = 40 x 18 x 3 patch starting at column 32*tw - 4 (16-byte aligned
+    // start; columns 3..36 are used), zero fill outside the frame = conv padding
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return VAD_ERR_DRIVER;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+    cuuint64_t st[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+    cuuint32_t box[4] = {40, 18, 3, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (fn(&a.mapA0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, st, box, es,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return VAD_ERR_DRIVER;
+  }
+  {
+    // pooled output bf16 NHWC [B][Hp][Wp][32] as a 5-D map {32, Wp, Hp, 1, B}; one store = one 8 x 16 pixel tile
+    cuuint64_t dims[5] = {32, (cuuint64_t)Wp, (cuuint64_t)Hp, 1, (cuuint64_t)B};
+    cuuint64_t st[4] = {64, (cuuint64_t)Wp * 64, (cuuint64_t)Hp * Wp * 64, (cuuint64_t)Hp * Wp * 64};
+    cuuint32_t box[5] = {32, 16, 8, 1, 1};
+    const int rc = encode_map5(&a.mapOut, out, dims, st, box, 32);
+    if (rc != VAD_OK) return rc;
+    a.tma_store = 1;
+  }
+  const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return launch_conv_first_pool(a, grid, stream);
+}
+
 int vad_score_finalize(const float* partials, int frames, int tiles_per_frame, int H, int W, float* score,
                        float* minmax, vad_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

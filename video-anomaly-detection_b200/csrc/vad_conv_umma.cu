@@ -2276,6 +2276,254 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------- first conv + 2x2 max-pool, folded
+// The video encoder's first layer (reference models/video_autoencoder.py:193-196: Conv2d(3,32,3,padding=1) + BN +
+// LeakyReLU + MaxPool2d(2,2)) with the pooling window folded into the GEMM's N extent: one accumulator ROW is one POOLED
+// output pixel, its 128 COLUMNS are the four conv outputs of the 2x2 window x 32 channels, and its K = 48 operand is the
+// 4 x 4 x 3 input window those four convolutions read (weights zero outside each position's 3x3 sub-window):
+//     D[pooled px][pos*32 + co] = sum_{wy,wx,ci} x[2py - 1 + wy][2px - 1 + wx][ci] * Wpf[pos*32 + co][(wy*4 + wx)*3 + ci]
+//     out[pooled px][co] = act(max_pos D[.][pos*32 + co] + bias[co])
+// Against conv_first_kernel<POOL> (one row per INPUT pixel, pooling by lane shuffles) this is, per 512 input pixels:
+// 3 N=128 MMAs (192 cycles) instead of 8 N=32 ones (320), 6144 im2col values instead of 13824, and an epilogue that takes
+// the maximum of four column groups inside the lane (96 FMNMX, no shuffles / selects) before bias + activation touch a
+// quarter of the values — the SM-side work that bounded the old kernel (0.29 of the HBM peak at 720p) drops ~5x.
+// Tile = 8 x 16 pooled pixels = 16 x 32 input pixels; TMA brings the fp32 patch (3 ch x 18 rows x 40 columns from column
+// 32 tw - 4: 16-byte aligned box start, zero fill outside the frame = conv padding).
+constexpr int kPfStages = 8;   // fp32 patch ring (TMA -> converter): two slots per converter warp hide the load latency
+constexpr int kPfAStages = 4;  // A-tile ring (converter -> MMA): one slot per converter warp
+constexpr int kPfGroups = 4;                  // epilogue groups == accumulator stages (128 TMEM columns each)
+constexpr int kPfConvWarps = 4;               // converter warps; each converts whole tiles (every 4th) and issues their MMAs
+constexpr int kPfConvWarp0 = 4 + 4 * kPfGroups;
+constexpr int kPfThreads = 32 * (kPfConvWarp0 + kPfConvWarps);
+constexpr int kPfPatchW = 40, kPfPatchH = 18, kPfPatchX0 = 4;
+constexpr int kPfPatchBytes = 3 * kPfPatchH * kPfPatchW * 4;  // 8640
+constexpr int kPfPatchPitch = 8704;                           // ring pitch (multiple of 128)
+constexpr int kPfABytes = kTileM * 128;                       // 128 rows x 64 bf16 (48 used), SWIZZLE_128B
+constexpr int kPfWBytes = 128 * 128;                          // [128 n][64 k] bf16
+constexpr int kPfStgBytes = kTileM * 64;                      // one staged output tile: 128 pooled pixels x 32 ch bf16
+constexpr int kPfSmemBytes = 1024 + kPfWBytes + kPfAStages * kPfABytes + kPfGroups * 2 * kPfStgBytes + kPfStages * kPfPatchPitch;
+static_assert(kPfSmemBytes <= kSmemBudget, "conv_first_pool_kernel shared memory");
+static_assert(kPfStages % kPfConvWarps == 0 && kPfStages % 2 == 0 && kPfAStages % kPfConvWarps == 0,
+              "ring slots must map to fixed warps");
+
+__global__ void __launch_bounds__(kPfThreads, 1) conv_first_pool_kernel(const __grid_constant__ ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t patch_full[kPfStages];
+  __shared__ uint64_t patch_empty[kPfStages];
+  __shared__ uint64_t empty_bar[kPfAStages];
+  __shared__ uint64_t acc_full_bar[kPfGroups];
+  __shared__ uint64_t acc_empty_bar[kPfGroups];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[32];
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;                              // [128 n][64 k] bf16, 128B-swizzled
+  uint8_t* s_a = s_w + kPfWBytes;                   // ring of A tiles
+  uint8_t* s_o = s_a + kPfAStages * kPfABytes;       // staged output tiles: two per epilogue group (1024-aligned)
+  uint8_t* s_p = s_o + kPfGroups * 2 * kPfStgBytes;  // ring of fp32 input patches
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kPfStages; ++i) {
+      mbar_init(&patch_full[i], 1);
+      mbar_init(&patch_empty[i], 1);  // one arrive by the converter warp that consumed the patch
+    }
+    for (int i = 0; i < kPfAStages; ++i) mbar_init(&empty_bar[i], 1);  // A slot free: committed by the MMAs that read it
+    for (int i = 0; i < kPfGroups; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  // weights: global bf16 [128][64] row-major -> swizzled smem (16-byte chunks)
+  for (int i = threadIdx.x; i < 128 * 8; i += kPfThreads) {
+    const int n = i >> 3, c16 = i & 7;
+    *reinterpret_cast<uint4*>(s_w + staged_off(n, c16, 64)) = reinterpret_cast<const uint4*>(a.w_first)[i];
+  }
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = a.bias[threadIdx.x];
+  fence_proxy_async_smem();  // s_w is read by the tensor core (async proxy)
+  if (a.pdl) {  // programmatic dependent launch: everything above touched constants only
+    pdl_launch_dependents();
+    pdl_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int Hp = a.H >> 1, Wp = a.W >> 1;
+
+  if (warp == 0 || warp == 2) {
+    // ===================================================================== TMA: fp32 input patches (two producers, alternate tiles)
+    const int pi = warp == 0 ? 0 : 1;
+    const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
+    const uint32_t sp0 = smem_addr_once(s_p);
+    int it = pi;
+    for (TileIter ti(a, blockIdx.x + pi * gridDim.x, 2 * gridDim.x); ti.tile < a.total_tiles; ti.next(a), it += 2) {
+      const int stage = it % kPfStages;
+      const uint32_t phase = (it / kPfStages) & 1;
+      mbar_wait_a(pempty0 + stage * 8, phase ^ 1u, 7);
+      if (elect_one()) {
+        if (a.dbg & 128) {  // ablation: no input loads
+          mbar_arrive_a(pfull0 + stage * 8);
+        } else {
+          mbar_arrive_expect_tx_a(pfull0 + stage * 8, kPfPatchBytes);
+          tma_load_4d_a(sp0 + stage * kPfPatchPitch, &a.mapA0, pfull0 + stage * 8, 32 * ti.tw - kPfPatchX0,
+                        16 * ti.th - 1, 0, ti.tb);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kPfConvWarp0) {
+    // ===================================================================== converters: fp32 patch -> bf16 window rows
+    // A lane owns one pooled column and four pooled rows {hb*2 + (lane >> 4)}: its 4 x 4 x 3 window is 12 rows of six
+    // consecutive floats (three 8-byte loads each; a half-warp reads 32 consecutive floats: conflict-free), packed in K
+    // order k = (wy*4 + wx)*3 + ci into six 16-byte chunks of A row pr*16 + pc (eight consecutive rows per quarter-warp
+    // store: the 128-byte swizzle spreads them over all banks).
+    const int cw = warp - kPfConvWarp0;
+    const int pc = lane & 15, rg = lane >> 4;
+    const uint32_t pfull0 = smem_addr_once(&patch_full[0]), pempty0 = smem_addr_once(&patch_empty[0]);
+    const uint32_t empty0 = smem_addr_once(&empty_bar[0]);
+    const uint32_t accf0 = smem_addr_once(&acc_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 128);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w), 1024, 2u);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 1024, 2u);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & (kPfConvWarps - 1)) != cw) continue;
+      const int stage = it % kPfStages;
+      const uint32_t phase = (it / kPfStages) & 1;
+      const int astage = it % kPfAStages;
+      mbar_wait_a(pfull0 + stage * 8, phase, 6);
+      mbar_wait_a(empty0 + astage * 8, static_cast<uint32_t>(((it / kPfAStages) & 1) ^ 1), 1);
+      uint8_t* sa = s_a + astage * kPfABytes;
+      const float* patch = reinterpret_cast<const float*>(s_p + stage * kPfPatchPitch);
+#pragma unroll 1
+      for (int hb = 0; hb < 4; ++hb) {
+        if (a.dbg & 256) break;  // ablation: no conversion work
+        const int pr = hb * 2 + rg;
+        // window of pooled pixel (pr, pc): patch rows 2pr .. 2pr+3, patch columns 3 + 2pc .. 6 + 2pc
+        const float* pp = patch + (2 * pr) * kPfPatchW + 2 + 2 * pc;
+        float v[48];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int wy = 0; wy < 4; ++wy) {
+            const float2* q2 = reinterpret_cast<const float2*>(pp + ci * (kPfPatchH * kPfPatchW) + wy * kPfPatchW);
+            const float2 f0 = q2[0], f1 = q2[1], f2 = q2[2];
+            v[(wy * 4 + 0) * 3 + ci] = f0.y;
+            v[(wy * 4 + 1) * 3 + ci] = f1.x;
+            v[(wy * 4 + 2) * 3 + ci] = f1.y;
+            v[(wy * 4 + 3) * 3 + ci] = f2.x;
+          }
+        const int r = pr * 16 + pc;
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          sts128(sa + staged_off(r, c, 64),
+                 make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                            pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7])));
+      }
+      fence_proxy_async_smem();  // every lane's A rows -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(pempty0 + stage * 8);  // patch slot may be refilled
+      // the converter issues its tile's three MMAs itself (tile -> converter warp -> accumulator stage -> epilogue group
+      // is a fixed 1:1:1:1 chain, it % 4)
+      const int as = it % kPfGroups;
+      mbar_wait_a(acce0 + as * 8, static_cast<uint32_t>(((it / kPfGroups) & 1) ^ 1), 3);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 128);
+        const uint64_t da = da_base + static_cast<uint64_t>(astage * (kPfABytes >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)  // K = 48: the last 16 columns of the 64-wide rows are never read
+          umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, kk > 0 ? 1u : 0u);
+        umma_commit_a(empty0 + astage * 8);  // A slot free once the MMAs have read it
+        umma_commit_a(accf0 + as * 8);       // accumulator ready for the epilogue group
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue groups: max over the window, bias, act
+    const int g = (warp - kEpiWarp0) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter == warp_id % 4
+    const int r = q * 32 + lane;  // accumulator row = pooled pixel (r >> 4, r & 15) of the tile = staged row
+    const uint32_t accf = smem_addr_once(&acc_full_bar[g]), acce = smem_addr_once(&acc_empty_bar[g]);
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 128);
+    // The pooled tile (128 pixels x 64 B) is staged in swizzled smem and written by ONE TMA store per tile (clipped by
+    // the hardware at partial tiles): direct 16-byte stores at a 64-byte lane stride cost more than the whole rest of
+    // the epilogue (ablation: 0.53 -> 0.34 ms at 720p without them).
+    const bool leader = (q == 0 && lane == 0);
+    const uint32_t bar_id = 1 + g;
+    uint32_t ph = 0;
+    int n = 0;
+    for (TileIter ti(a, blockIdx.x + g * gridDim.x, kPfGroups * gridDim.x); ti.tile < a.total_tiles;
+         ti.next(a), ph ^= 1u, ++n) {
+      uint8_t* stg = s_o + (g * 2 + (n & 1)) * kPfStgBytes;
+      mbar_wait_a(accf, ph, 4);
+      tc_fence_after();
+      if (a.dbg & 32) {  // ablation: no epilogue work at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(acce);
+        continue;
+      }
+      if (leader) bulk_wait_group_read<1>();  // the store that last used this staging buffer has read it
+      named_bar_sync(bar_id, 128);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t m[16], t0[16], t1[16];
+        tmem_ld_x16(tacc + 0 * 32 + half * 16, m);
+        tmem_ld_x16(tacc + 1 * 32 + half * 16, t0);
+        tmem_ld_wait();
+        tmem_ld_x16(tacc + 2 * 32 + half * 16, t1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) m[j] = __float_as_uint(fmaxf(__uint_as_float(m[j]), __uint_as_float(t0[j])));
+        tmem_ld_wait();
+        tmem_ld_x16(tacc + 3 * 32 + half * 16, t0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) m[j] = __float_as_uint(fmaxf(__uint_as_float(m[j]), __uint_as_float(t1[j])));
+        tmem_ld_wait();
+        if (half == 1) {  // every column of this stage has been read: hand it back to the converters
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce);
+        }
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v0 = fmaxf(__uint_as_float(m[2 * j]), __uint_as_float(t0[2 * j])) + s_bias[half * 16 + 2 * j];
+          const float v1 = fmaxf(__uint_as_float(m[2 * j + 1]), __uint_as_float(t0[2 * j + 1])) + s_bias[half * 16 + 2 * j + 1];
+          p[j] = pack_bf16x2(act_fn(v0, a.slope), act_fn(v1, a.slope));
+        }
+        sts128(stg + staged_off(r, half * 2, 32), make_uint4(p[0], p[1], p[2], p[3]));
+        sts128(stg + staged_off(r, half * 2 + 1, 32), make_uint4(p[4], p[5], p[6], p[7]));
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+      named_bar_sync(bar_id, 128);
+      if (leader && !(a.dbg & 64)) {  // (ablation bit 64: no output store)
+        tma_store_5d(&a.mapOut, stg, 0, 16 * ti.tw, 8 * ti.th, 0, ti.tb);
+        bulk_commit_group();
+      }
+    }
+    if (leader) bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------- ConvT -> ConvT + tanh + score, fused
 // The last two layers of the video decoder (reference models/video_autoencoder.py:252-259: ConvTranspose2d(64,32,2,2) +
 // BN + ReLU, ConvTranspose2d(32,3,2,2) + Tanh) and the error reduction (:371-384) in ONE kernel.  A k2s2 transposed
@@ -2974,6 +3222,12 @@ int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream) {
   static SmemConfig cfg;
   if (int e = ensure_smem(convt_conv_score_kernel, cfg, kI2SmemBytes)) return e;
   return launch_conv_kernel(convt_conv_score_kernel, a, grid, kI2Threads, kI2SmemBytes, stream);
+}
+
+int launch_conv_first_pool(const ConvArgs& a, int grid, cudaStream_t stream) {
+  static SmemConfig cfg;
+  if (int e = ensure_smem(conv_first_pool_kernel, cfg, kPfSmemBytes)) return e;
+  return launch_conv_kernel(conv_first_pool_kernel, a, grid, kPfThreads, kPfSmemBytes, stream);
 }
 
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {

@@ -150,6 +150,7 @@ int convt(Ctx& c, const char* name, const vad_gemm_weights& w, const void* src, 
 int first_conv(Ctx& c, const vad_first_weights& w, const float* x, int B, int H, int W, bool pool, void* out) {
   if (c.dry()) return VAD_OK;
   ProfScope p("first_conv", c.stream);
+  if (pool && w.w_pf && w.cout == 32) return vad_first_conv_pool(x, w.w_pf, w.bias, kLeaky, B, H, W, out, c.stream);
   if (w.w_tc && w.cout == 32) return vad_first_conv_tc(x, w.w_tc, w.bias, kLeaky, pool ? 1 : 0, B, H, W, out, c.stream);
   return vad_first_conv(x, w.w, w.bias, w.cout, kLeaky, pool ? 1 : 0, B, H, W, out, c.stream);
 }

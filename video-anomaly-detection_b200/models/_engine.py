@@ -28,6 +28,9 @@ FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
 # VAD_FIRST_TC=0: CUDA-core first conv (fp32 operands) instead of the tensor-core one
 FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
+# VAD_FIRST_PF=0: the video encoder's pooled first conv on the one-row-per-input-pixel kernel (vad_first_conv_tc)
+# instead of the pool-folded one (vad_first_conv_pool)
+FIRST_CONV_POOL_FOLD = os.environ.get("VAD_FIRST_PF", "1") != "0"
 
 
 @dataclass
@@ -78,6 +81,7 @@ def _first_struct(w: FirstConvWeights) -> "nat.FirstW":
     f = nat.FirstW()
     f.w, f.bias, f.cout = w.w.data_ptr(), w.bias.data_ptr(), w.cout
     f.w_tc = nat.ptr(w.w_tc) if FIRST_CONV_TC else None
+    f.w_pf = nat.ptr(w.w_pf) if (FIRST_CONV_TC and FIRST_CONV_POOL_FOLD) else None
     return f
 
 

@@ -151,7 +151,16 @@ FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
 
 
+# the pooled first conv on the pool-folded kernel (vad_first_conv_pool) when its weights were prepared; tests flip this
+FIRST_CONV_POOL_FOLD = os.environ.get("VAD_FIRST_PF", "1") != "0"
+
+
 def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, pool: bool, out: torch.Tensor) -> None:
+    if FIRST_CONV_TC and FIRST_CONV_POOL_FOLD and pool and w.cout == 32 and w.w_pf is not None:
+        _timed("first_conv", lambda: nat.check(
+            nat.load().vad_first_conv_pool(x.data_ptr(), w.w_pf.data_ptr(), w.bias.data_ptr(), LEAKY, B, H, W,
+                                           out.data_ptr(), nat.stream_ptr()), "vad_first_conv_pool"))
+        return
     if FIRST_CONV_TC and w.cout == 32 and w.w_tc is not None:
         _timed("first_conv", lambda: nat.check(
             nat.load().vad_first_conv_tc(x.data_ptr(), w.w_tc.data_ptr(), w.bias.data_ptr(), LEAKY, 1 if pool else 0,

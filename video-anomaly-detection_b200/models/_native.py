@@ -18,7 +18,7 @@ EPI_STORE, EPI_POOL, EPI_CONVT, EPI_LSTM, EPI_TANH_SCORE, EPI_CONVT_TANH_SCORE =
 
 # every symbol include/vad_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convt2_score", "vad_convt2_score_tiles", "vad_convt_conv_score", "vad_convt_conv_score_tiles", "vad_convlstm_sequence", "vad_convlstm2_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc",
+    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convt2_score", "vad_convt2_score_tiles", "vad_convt_conv_score", "vad_convt_conv_score_tiles", "vad_convlstm_sequence", "vad_convlstm2_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc", "vad_first_conv_pool",
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8", "vad_u8_hwc_to_f32_nchw", "vad_f32_nchw_to_u8_hwc",
     "vad_heatmap_jet_rgb", "vad_ssim_scratch_bytes", "vad_ssim_loss",
@@ -63,7 +63,7 @@ class GemmW(C.Structure):
 
 class FirstW(C.Structure):
     """Mirror of `struct vad_first_weights`."""
-    _fields_ = [("w", C.c_void_p), ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("cout", C.c_int)]
+    _fields_ = [("w", C.c_void_p), ("w_tc", C.c_void_p), ("w_pf", C.c_void_p), ("bias", C.c_void_p), ("cout", C.c_int)]
 
 
 class ImageModel(C.Structure):
@@ -112,6 +112,8 @@ def load() -> C.CDLL:
                                    C.c_int, C.c_void_p, C.c_void_p]
     lib.vad_first_conv_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]
+    lib.vad_first_conv_pool.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]
     lib.vad_score_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     lib.vad_score_scratch_bytes.restype = C.c_size_t

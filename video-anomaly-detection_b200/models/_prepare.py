@@ -39,6 +39,9 @@ class FirstConvWeights:
     bias: torch.Tensor
     cout: int
     w_tc: Optional[torch.Tensor] = None
+    # pooled layer only: bf16 [4*cout, 64] for the kernel that folds the 2x2 pooling window into the GEMM N extent
+    # (include/vad_b200.h `vad_first_conv_pool`): row = (py*2+px)*cout + co, column = ((py+ky)*4 + (px+kx))*3 + ci
+    w_pf: Optional[torch.Tensor] = None
 
 
 def bn_scale_shift(sd: Mapping[str, torch.Tensor], bn: Optional[str], cout: int, ref: torch.Tensor
@@ -133,13 +136,27 @@ def pack_lstm(w: torch.Tensor, b: torch.Tensor, hid: int) -> GemmWeights:
     return g
 
 
-def pack_first_conv(w: torch.Tensor, b: torch.Tensor) -> FirstConvWeights:
+def pack_first_conv_pool_folded(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,3,3,3] -> bf16 [4*Cout, 64]: the four conv outputs of a 2x2 pooling window as one GEMM row over the 4x4x3
+    input window (zeros outside each output position's 3x3 sub-window; K = 48 padded to 64)."""
+    cout = w.shape[0]
+    out = torch.zeros(4, cout, 4, 4, 3, dtype=torch.float64, device=w.device)  # [pos][co][wy][wx][ci]
+    for py in range(2):
+        for px in range(2):
+            out[py * 2 + px, :, py:py + 3, px:px + 3, :] = w.permute(0, 2, 3, 1)  # [co][ky][kx][ci]
+    flat = torch.zeros(4 * cout, 64, dtype=torch.float64, device=w.device)
+    flat[:, :48] = out.reshape(4 * cout, 48)
+    return flat.to(torch.bfloat16).contiguous()
+
+
+def pack_first_conv(w: torch.Tensor, b: torch.Tensor, pooled: bool = False) -> FirstConvWeights:
     cout = w.shape[0]
     wk = w.permute(2, 3, 1, 0).reshape(27, cout)  # [ky,kx,ci,co]
     w_tc = torch.zeros(cout, 32, dtype=torch.float64, device=w.device)
     w_tc[:, :27] = wk.t()
     return FirstConvWeights(wk.float().contiguous(), b.float().contiguous(), cout,
-                            w_tc.to(torch.bfloat16).contiguous())
+                            w_tc.to(torch.bfloat16).contiguous(),
+                            pack_first_conv_pool_folded(w) if (pooled and cout == 32) else None)
 
 
 def prepare_image_encoder(sd: Mapping[str, torch.Tensor], prefix: str = "encoder.") -> Dict[str, object]:
@@ -173,7 +190,7 @@ def prepare_image(sd: Mapping[str, torch.Tensor]) -> Dict[str, object]:
 
 def prepare_video_encoder(sd: Mapping[str, torch.Tensor], prefix: str = "encoder.encoder.") -> Dict[str, object]:
     out: Dict[str, object] = {}
-    out["enc.0"] = pack_first_conv(*fold_conv(sd, f"{prefix}0", f"{prefix}1"))
+    out["enc.0"] = pack_first_conv(*fold_conv(sd, f"{prefix}0", f"{prefix}1"), pooled=True)
     for i in (4, 8, 12):
         out[f"enc.{i}"] = pack_conv3x3(*fold_conv(sd, f"{prefix}{i}", f"{prefix}{i + 1}"))
     return out
@@ -222,6 +239,8 @@ def to_device(packed: Dict[str, object], device) -> Dict[str, object]:
             v.bias = v.bias.to(device)
             if isinstance(v, FirstConvWeights) and v.w_tc is not None:
                 v.w_tc = v.w_tc.to(device)
+            if isinstance(v, FirstConvWeights) and v.w_pf is not None:
+                v.w_pf = v.w_pf.to(device)
             if isinstance(v, GemmWeights) and v.w_kx is not None:
                 v.w_kx = v.w_kx.to(device)
         res[k] = v
