@@ -104,6 +104,15 @@ typedef struct vad_conv_desc {
    * counters of the persistent kernels live there (zeroed by the library on `stream`; must not be shared by two calls
    * in flight).  NULL: a slot of the library's own rotating pool is used. */
   void* scratch;
+  /* Pixel-pair folding of a narrow 3x3 layer (Cin = 32; STORE or POOL epilogue).  A tcgen05.mma with N = 32 is bound
+   * by streaming its A operand, not by math, so such a layer can be described on the PAIR view of its tensors instead:
+   * input bf16 NHWC [B,H,W,32] seen as [B,H,W/2,64] (c0 = 64, W = W/2), n_total = 2*Cout with column p*Cout + co =
+   * output pixel 2Q+p, channel co, and `weight` the 3x3 "pair" kernel [2*Cout][9*64] that holds w[co][ci][ky][kx] at
+   * row p_out*Cout + co, column (ky*3 + kxp)*64 + p_in*32 + ci, kx = 2*(kxp-1) + p_in - p_out + 1 (zero where kx is
+   * not in 0..2); bias repeated for both pixels.  STORE then writes [B,H,W/2,2*Cout] = the ordinary NHWC output;
+   * POOL writes [B,H/2,W/2,Cout] (out_cpitch = Cout) with the horizontal half of the 2x2 window taken inside the
+   * accumulator row.  pair_fold = 1 tells the kernel which K steps are structurally zero (skipped). */
+  int pair_fold;
 } vad_conv_desc;
 
 int vad_conv_layer(const vad_conv_desc* d, vad_stream_t stream);
@@ -216,6 +225,10 @@ typedef struct vad_gemm_weights {
   const void* w_kx;  /* optional kx-folded layout of a narrow 3x3 layer (vad_conv_desc.weight_kx) */
   const float* bias; /* fp32 [n_total] */
   int ntaps, ctap, n_total, cout;
+  /* optional pixel-pair folded form of a 3x3 layer with 32 input channels (vad_conv_desc.pair_fold): bf16
+   * [2*n_total][9*64] and fp32 [2*n_total]; NULL: the layer runs on the ordinary view */
+  const void* w_pair;
+  const float* bias_pair;
 } vad_gemm_weights;
 
 typedef struct vad_first_weights {

@@ -49,6 +49,8 @@ def _dev(packed, dev):
     packed.w, packed.bias = packed.w.to(dev), packed.bias.to(dev)
     if getattr(packed, "w_kx", None) is not None:
         packed.w_kx = packed.w_kx.to(dev)
+    if getattr(packed, "w_pair", None) is not None:
+        packed.w_pair, packed.bias_pair = packed.w_pair.to(dev), packed.bias_pair.to(dev)
     return packed
 
 
@@ -96,6 +98,45 @@ def test_conv3x3(cuda_device, cin, cout, B, H, W, pool, kx):
     if pool:
         ref = F.max_pool2d(ref, 2, 2)
     _assert_close(out, _nhwc(ref), f"conv3x3 {cin}->{cout} B{B} {H}x{W} pool={pool}")
+
+
+@pytest.mark.parametrize("cout,B,H,W", [(32, 2, 32, 32), (64, 2, 16, 48), (32, 1, 48, 80), (64, 1, 360, 640),
+                                        (32, 3, 256, 256), (32, 2, 16, 32)])
+@pytest.mark.parametrize("pool", [False, True])
+def test_pixel_pair_folded_conv_equals_ordinary_view(cuda_device, cout, B, H, W, pool):
+    """The 32-input-channel 3x3 layers run on the pixel-PAIR view by default (N = 2*Cout instead of the A-stream-bound
+    N = 32: include/vad_b200.h `pair_fold`).  Same products, different fp32 summation order: the bf16 outputs agree
+    with the ordinary view up to rare 1-ulp flips, and both agree with torch."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(cout + H)
+    w = torch.randn(cout, 32, 3, 3, generator=g) * (2.0 / 288) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    packed = _dev(prep.pack_conv3x3(w.double(), b.double()), dev)
+    assert packed.w_pair is not None
+    x = _rand_nhwc(B, H, W, 32, dev, seed=H + W)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    outs = {}
+    prev = nat.load().vad_debug_set_kx(0)
+    try:
+        for pair in (True, False):
+            out = torch.full((B, Ho, Wo, cout), float("nan"), dtype=torch.bfloat16, device=dev)
+            eng.PAIR_FOLD = pair
+            n0 = nat.launch_count()
+            eng._conv(packed, x, B, H, W, out, 0.2, pool=pool, what="test conv")
+            assert nat.launch_count() - n0 == 1
+            torch.cuda.synchronize()
+            outs[pair] = out
+    finally:
+        eng.PAIR_FOLD = True
+        nat.load().vad_debug_set_kx(-1)
+    ref = F.leaky_relu(F.conv2d(_nchw(x), w.to(torch.bfloat16).float().to(dev), b.to(dev), padding=1), 0.2)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    _assert_close(outs[True], _nhwc(ref), f"pair-folded conv3x3 32->{cout} B{B} {H}x{W} pool={pool}")
+    _assert_close(outs[False], _nhwc(ref), f"ordinary conv3x3 32->{cout} B{B} {H}x{W} pool={pool}")
+    diff = (outs[True].float() - outs[False].float()).abs()
+    assert float((diff > 0).float().mean()) < 0.02 and float(diff.max()) <= 0.0625 * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("cin,cout,B,H,W", [(256, 128, 2, 16, 16), (128, 64, 2, 8, 24), (64, 32, 3, 16, 16),

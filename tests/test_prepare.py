@@ -191,3 +191,29 @@ def test_kx_merged_gemm_reproduces_conv():
     out = D[:, :, 0:W, 0:3] + D[:, :, 1:W + 1, 3:6] + D[:, :, 2:W + 2, 6:9]
     ref = F.conv2d(x.permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), padding=1).permute(0, 2, 3, 1)
     assert torch.allclose(out, ref, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("cout", [32, 64])
+def test_pixel_pair_folded_weights_are_the_same_convolution(cout):
+    """pack_conv3x3_pair: the 3x3 conv on pairs of horizontally adjacent pixels (input [B,H,W/2,2*32], output
+    [B,H,W/2,2*Cout]) equals the original conv, and a third of the pair matrix is structurally zero (the K steps the
+    kernel skips: left-neighbour pair x first pixel, right-neighbour pair x second pixel)."""
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(cout, 32, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 32, 6, 10, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, b, padding=1)
+    saved = prep  # (bf16 rounding aside: rebuild the pair matrix in fp64 with the same index formula)
+    wp, bp = saved.pack_conv3x3_pair(w.to(torch.bfloat16).double(), b)
+    w4 = wp.double().reshape(2 * cout, 3, 3, 64).permute(0, 3, 1, 2)          # [n][p_in*32+ci][ky][kxp]
+    xp = x.reshape(2, 32, 6, 5, 2).permute(0, 4, 1, 2, 3).reshape(2, 64, 6, 5)   # channels p_in*32 + ci, W/2 pairs
+    yp = F.conv2d(xp, w4, bp.double(), padding=1)                                 # [B][p_out*cout+co][H][W/2]
+    y = yp.reshape(2, 2, cout, 6, 5).permute(0, 2, 3, 4, 1).reshape(2, cout, 6, 10)
+    ref_bf = F.conv2d(x, w.to(torch.bfloat16).double(), b.float().double(), padding=1)   # (the packed bias is fp32)
+    assert torch.allclose(y, ref_bf, rtol=0, atol=1e-12)
+    assert (ref - ref_bf).abs().max() < 0.2
+    k = wp.reshape(2 * cout, 3, 3, 2, 32)                                          # [n][ky][kxp][p_in][ci]
+    assert float(k[:, :, 0, 0].abs().max()) == 0.0 and float(k[:, :, 2, 1].abs().max()) == 0.0
+    gw = prep.pack_conv3x3(w, b)
+    assert gw.w_pair is not None and tuple(gw.w_pair.shape) == (2 * cout, 576) and tuple(gw.bias_pair.shape) == (2 * cout,)
+    assert prep.pack_conv3x3(torch.randn(64, 64, 3, 3, dtype=torch.float64), torch.zeros(64, dtype=torch.float64)).w_pair is None

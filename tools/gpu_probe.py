@@ -66,7 +66,7 @@ def run_stage(stage):
         for (B, H, W) in ((1, 8, 16), (2, 16, 16)):
             w = torch.randn(cout, cin, 1, 1, generator=g) * 0.2
             b = torch.randn(cout, generator=g) * 0.1
-            pk = prep.pack_conv1x1(w.double(), b.double()); pk.w, pk.bias = pk.w.to(dev), pk.bias.to(dev); pk.w_kx = pk.w_kx.to(dev) if pk.w_kx is not None else None
+            pk = prep.pack_conv1x1(w.double(), b.double()); pk = prep.to_device({"pk": pk}, dev)["pk"]
             x = rnd_nhwc(B, H, W, cin)
             out = torch.full((B, H, W, cout), float("nan"), dtype=torch.bfloat16, device=dev)
             eng._conv(pk, x, B, H, W, out, 1.0)
@@ -87,7 +87,7 @@ def run_stage(stage):
         for cin, cout, B, H, W, pool in cases:
             w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
             b = torch.randn(cout, generator=g) * 0.1
-            pk = prep.pack_conv3x3(w.double(), b.double()); pk.w, pk.bias = pk.w.to(dev), pk.bias.to(dev); pk.w_kx = pk.w_kx.to(dev) if pk.w_kx is not None else None
+            pk = prep.pack_conv3x3(w.double(), b.double()); pk = prep.to_device({"pk": pk}, dev)["pk"]
             x = rnd_nhwc(B, H, W, cin)
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
             out = torch.full((B, Ho, Wo, cout), float("nan"), dtype=torch.bfloat16, device=dev)

@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 w = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
 b = torch.zeros(cout)
-pk = prep.pack_conv3x3(w.double(), b.double()); pk.w, pk.bias = pk.w.to(dev), pk.bias.to(dev); pk.w_kx = pk.w_kx.to(dev) if pk.w_kx is not None else None
+pk = prep.pack_conv3x3(w.double(), b.double()); pk = prep.to_device({"pk": pk}, dev)["pk"]
 x = torch.randn(B, H, W, cin, generator=g).to(torch.bfloat16).to(dev)
 out = torch.empty(B, H // 2 if pool else H, W // 2 if pool else W, cout, dtype=torch.bfloat16, device=dev)
 buf = torch.zeros(4, 64, 16, dtype=torch.int64, device=dev)

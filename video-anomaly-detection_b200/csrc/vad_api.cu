@@ -701,7 +701,10 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
       BN = d->n_total >= 256 && d->n_total % 256 == 0 ? 256 : d->n_total % 128 == 0 ? 128 : d->n_total % 64 == 0 ? 64 : 32;
       if (CK == 32 && BN > 64) BN = 64;
       if (!d->out) return VAD_ERR_ARG;
-      if (epi == VAD_EPI_POOL && ((d->H | d->W) & 1)) return VAD_ERR_SHAPE;
+      if (epi == VAD_EPI_POOL && ((d->H | (d->pair_fold ? 0 : d->W)) & 1)) return VAD_ERR_SHAPE;
+      if (d->pair_fold && (d->ntaps != 9 || d->c0 != 64 || d->c1 != 0 || d->n_total > 128 || d->H < 16 || d->W < 16 ||
+                           (d->T0 > 1)))
+        return VAD_ERR_UNSUPPORTED;  // (pair view: 2 x 32 input channels, halo kernel shapes only)
       break;
     case VAD_EPI_CONVT:
       if (d->n_total % 128 != 0 || d->cout * 4 != d->n_total || d->cout % 32 != 0) return VAD_ERR_SHAPE;
@@ -756,7 +759,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   }
 
   // ---- patch + streamed-weights kernel for wide 3x3 layers: pairs of 8x16 tiles, N tiles of 128
-  bool use_hs = hs_setting() != 0 && d->ntaps == 9 && d->c1 == 0 && d->c0 % 64 == 0 &&
+  bool use_hs = !d->pair_fold && hs_setting() != 0 && d->ntaps == 9 && d->c1 == 0 && d->c0 % 64 == 0 &&
                 (d->c0 >= 128 || hs_setting() >= 2 || epi == VAD_EPI_STORE) && d->n_total % 128 == 0 && (d->T0 <= 1) &&
                 d->H >= 8 &&
                 d->W % 16 == 0 && (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL) && hs_patch_stages(epi) >= 2;
@@ -855,6 +858,8 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   a.c_state = d->c_state;
   a.lstm_first = d->lstm_first;
   a.x = d->x; a.recon = d->recon; a.heat = d->heat; a.partials = d->partials;
+  a.pair_fold = d->pair_fold ? 1 : 0;
+  if (d->pair_fold && !use_halo) return VAD_ERR_UNSUPPORTED;  // only the resident-weights patch kernel skips the zero K steps
 
   // ---- output tensor map: the epilogue stages each bf16 chunk in swizzled smem and TMA-stores it
   if (tma_store_setting() && (epi == VAD_EPI_STORE || epi == VAD_EPI_POOL || epi == VAD_EPI_CONVT || epi == VAD_EPI_LSTM)) {
@@ -875,7 +880,7 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
                           (cuuint64_t)d->out_frame_stride * 2};
       cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1, (cuuint32_t)TN};
       a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, 32) == VAD_OK;
-    } else if (aligned && epi == VAD_EPI_POOL && TW >= 2 && TH >= 2 && !pool_direct_setting()) {
+    } else if (aligned && epi == VAD_EPI_POOL && TW >= 2 && TH >= 2 && !pool_direct_setting() && !d->pair_fold) {
       a.out_chunk = (BN % 64 == 0) ? 64 : 32;
       const int Wo = d->W / 2, Ho = d->H / 2;
       cuuint64_t dims[5] = {(cuuint64_t)d->n_total, (cuuint64_t)Wo, (cuuint64_t)Ho, 1, (cuuint64_t)d->B};

@@ -387,7 +387,39 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
       // straight from registers, no staging buffer, no group barrier, no proxy fence, no TMA store.  STORE / CONVT: the
       // fallback for tile shapes the output tensor map cannot express.
       __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
-      if constexpr (EPI == VAD_EPI_POOL) {
+      if (EPI == VAD_EPI_POOL && KX == 1 && a.pair_fold) {
+        // pixel-pair folded layer: columns [0, BN/2) are the pair's left pixel, [BN/2, BN) its right pixel, so the
+        // horizontal half of the 2x2 window is a max inside the lane; the vertical half is one exchange with the row
+        // neighbour (reduce-scatter: each lane keeps 8 of every 16 channels).  a.W counts pairs = pooled columns.
+        constexpr int CO = BN / 2;
+        const bool up2 = (hh & 1) != 0;
+        __nv_bfloat16* dst0 = outp + fb * a.out_fs + (static_cast<long long>(h >> 1) * a.W + w) * a.out_cp + (up2 ? 8 : 0);
+#pragma unroll 1
+        for (int c = 0; c < CO / 16; ++c) {
+          uint32_t v0[16], v1[16];
+          tmem_ld_x16(tacc + c * 16, v0);
+          tmem_ld_x16(tacc + CO + c * 16, v1);
+          tmem_ld_wait();
+          if (c == CO / 16 - 1) release_acc();
+          float g[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
+          float m[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float recv = __shfl_xor_sync(0xffffffffu, up2 ? g[j] : g[j + 8], L.my);
+            m[j] = fmaxf(up2 ? g[j + 8] : g[j], recv);
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 16 + (up2 ? 8 : 0));
+          const float4 b0 = b4[0], b1 = b4[1];
+          if (valid)
+            *reinterpret_cast<uint4*>(dst0 + c * 16) = make_uint4(
+                pack_bf16x2(act_fn(m[0] + b0.x, a.slope), act_fn(m[1] + b0.y, a.slope)),
+                pack_bf16x2(act_fn(m[2] + b0.z, a.slope), act_fn(m[3] + b0.w, a.slope)),
+                pack_bf16x2(act_fn(m[4] + b1.x, a.slope), act_fn(m[5] + b1.y, a.slope)),
+                pack_bf16x2(act_fn(m[6] + b1.z, a.slope), act_fn(m[7] + b1.w, a.slope)));
+        }
+      } else if constexpr (EPI == VAD_EPI_POOL) {
         const bool up1 = (ww & 1) != 0, up2 = (hh & 1) != 0;
         const int part = (up1 ? 2 : 0) + (up2 ? 1 : 0);
         __nv_bfloat16* dst0 = outp + fb * a.out_fs +
@@ -960,15 +992,22 @@ __global__ void __launch_bounds__(block_threads(BN), 1) conv_halo_kernel(const _
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
           const uint64_t da0 = da_hi + static_cast<uint64_t>(sa16_0 + stage * stage16);
+          // Pixel-pair folding (a.pair_fold: rows = pairs of horizontally adjacent pixels, CK = 2 x 32 channels,
+          // N = 2 x Cout): the left neighbour pair only feeds the tap through its SECOND pixel (K columns 32..63) and
+          // the right one through its FIRST (0..31) — the other half of their weight slabs is zero and is not issued:
+          // 24 MMAs per 256 pixels instead of 36.
+          uint32_t acc = 0u;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if ((a.dbg & 16) && tap > 0) break;  // ablation: one tap only
             const uint64_t da = da0 + static_cast<uint64_t>(tap_off[tap]);
             const uint64_t db = db0 + static_cast<uint64_t>((tap * kBBytes) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < CK / 16; ++kk)
-              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                        (tap > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < CK / 16; ++kk) {
+              if (CK == 64 && a.pair_fold && ((tap % 3 == 0 && kk < 2) || (tap % 3 == 2 && kk >= 2))) continue;
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, acc);
+              acc = 1u;
+            }
           }
           umma_commit_a(empty0 + stage * 8);
           umma_commit_a(accf0 + as * 8);
@@ -2359,7 +2398,6 @@ __global__ void __launch_bounds__(kPfThreads, 1) conv_first_pool_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const int Hp = a.H >> 1, Wp = a.W >> 1;
 
   if (warp == 0 || warp == 2) {
     // ===================================================================== TMA: fp32 input patches (two producers, alternate tiles)

@@ -47,6 +47,7 @@ struct alignas(64) ConvArgs {
   int token;            // 1: the two issuers pass a token (strict tile order on the tensor pipe)
   long long* timeline;  // optional [role 0..3][64 tiles][8 events] clock64 stamps of CTA 0 (vad_debug_set_timeline)
   const void* w_first;  // first conv: bf16 [32 n][32 k] weights, k = (ky*3+kx)*3+ci (27 real + 5 zero)
+  int pair_fold;        // halo kernel: pixel-pair folded 3x3 layer (vad_conv_desc.pair_fold)
   // epilogue staging / TMA store
   int tma_store;  // 1: stage the bf16 tile in swizzled smem and store it with TMA (coalesced, clipped by hardware)
   int out_chunk;  // channels per staged chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)

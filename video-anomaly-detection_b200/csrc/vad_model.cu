@@ -133,6 +133,22 @@ int conv(Ctx& c, const char* name, const vad_gemm_weights& w, const void* src, i
   d.out_frame_stride = static_cast<long long>(Ho) * Wo * w.n_total;
   d.out_cpitch = w.n_total;
   ProfScope p(name, c.stream);
+  if (w.w_pair && w.bias_pair && w.ntaps == 9 && w.ctap == 32 && w.n_total <= 64 && W % 2 == 0 && W >= 32 && H >= 16) {
+    // pixel-pair view (include/vad_b200.h `pair_fold`): N = 2*Cout lifts the layer off the N = 32 A-operand ceiling
+    vad_conv_desc dp = d;
+    dp.c0 = 64;
+    dp.W = W / 2;
+    dp.weight = w.w_pair;
+    dp.weight_kx = nullptr;
+    dp.bias = w.bias_pair;
+    dp.w_ctap = 64;
+    dp.n_total = 2 * w.n_total;
+    dp.cout = 2 * w.n_total;
+    dp.pair_fold = 1;
+    dp.out_cpitch = pool ? w.n_total : 2 * w.n_total;
+    const int rc = vad_conv_layer(&dp, c.stream);
+    if (rc != VAD_ERR_UNSUPPORTED) return rc;
+  }
   return vad_conv_layer(&d, c.stream);
 }
 

@@ -28,6 +28,8 @@ FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
 # VAD_FIRST_TC=0: CUDA-core first conv (fp32 operands) instead of the tensor-core one
 FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
+# VAD_PAIR_FOLD=0: the 3x3 layers with 32 input channels on the ordinary view instead of the pixel-pair folded one
+PAIR_FOLD = os.environ.get("VAD_PAIR_FOLD", "1") != "0"
 # VAD_FIRST_PF=0: the video encoder's pooled first conv on the one-row-per-input-pixel kernel (vad_first_conv_tc)
 # instead of the pool-folded one (vad_first_conv_pool)
 FIRST_CONV_POOL_FOLD = os.environ.get("VAD_FIRST_PF", "1") != "0"
@@ -74,6 +76,8 @@ def _gemm_struct(w: GemmWeights) -> "nat.GemmW":
     g = nat.GemmW()
     g.w, g.w_kx, g.bias = w.w.data_ptr(), nat.ptr(w.w_kx), w.bias.data_ptr()
     g.ntaps, g.ctap, g.n_total, g.cout = w.ntaps, w.ctap, w.n_total, w.cout
+    if PAIR_FOLD and w.w_pair is not None:
+        g.w_pair, g.bias_pair = w.w_pair.data_ptr(), w.bias_pair.data_ptr()
     return g
 
 

@@ -171,8 +171,29 @@ def _first_conv(w: FirstConvWeights, x: torch.Tensor, B: int, H: int, W: int, po
                                   B, H, W, out.data_ptr(), nat.stream_ptr()), "vad_first_conv"))
 
 
+# 3x3 layers with 32 input channels on the pixel-pair view (include/vad_b200.h `pair_fold`) when prepared; tests flip this
+PAIR_FOLD = os.environ.get("VAD_PAIR_FOLD", "1") != "0"
+
+
 def _conv(w: GemmWeights, src, B, H, W, out, slope, pool=False, what=""):
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    if PAIR_FOLD and w.w_pair is not None and w.ntaps == 9 and w.ctap == 32 and w.n_total <= 64 and W % 2 == 0 and \
+            W >= 32 and H >= 16:
+        d = _gemm_desc(w, src, B, H, W // 2, nat.EPI_POOL if pool else nat.EPI_STORE, slope, out, c0=64,
+                       out_frame_stride=Ho * Wo * w.n_total, out_cpitch=w.n_total if pool else 2 * w.n_total)
+        d.weight, d.weight_kx, d.bias = w.w_pair.data_ptr(), None, w.bias_pair.data_ptr()
+        d.w_ctap, d.n_total, d.cout, d.pair_fold = 64, 2 * w.n_total, 2 * w.n_total, 1
+        rc = [0]
+
+        def run():
+            rc[0] = nat.load().vad_conv_layer(C.byref(d), nat.stream_ptr())
+            if rc[0] != nat.ERR_UNSUPPORTED:
+                nat.check(rc[0], what or "vad_conv_layer(pair)")
+        _timed(what or "vad_conv_layer", run)
+        if rc[0] == 0:
+            return
+        if PROFILE is not None:
+            PROFILE.pop()
     _gemm_layer(w, src, B, H, W, nat.EPI_POOL if pool else nat.EPI_STORE, slope, out,
                 out_frame_stride=Ho * Wo * w.n_total, out_cpitch=w.n_total, what=what)
 

@@ -52,13 +52,15 @@ class ConvDesc(C.Structure):
         ("x", C.c_void_p), ("recon", C.c_void_p), ("heat", C.c_void_p), ("partials", C.c_void_p),
         ("weight_kx", C.c_void_p),
         ("scratch", C.c_void_p),
+        ("pair_fold", C.c_int),
     ]
 
 
 class GemmW(C.Structure):
     """Mirror of `struct vad_gemm_weights`."""
     _fields_ = [("w", C.c_void_p), ("w_kx", C.c_void_p), ("bias", C.c_void_p),
-                ("ntaps", C.c_int), ("ctap", C.c_int), ("n_total", C.c_int), ("cout", C.c_int)]
+                ("ntaps", C.c_int), ("ctap", C.c_int), ("n_total", C.c_int), ("cout", C.c_int),
+                ("w_pair", C.c_void_p), ("bias_pair", C.c_void_p)]
 
 
 class FirstW(C.Structure):

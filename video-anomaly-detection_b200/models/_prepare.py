@@ -29,6 +29,10 @@ class GemmWeights:
     # narrow 3x3 layers only: the same weights as [kx*Cout + co (zero rows up to a multiple of 16)][ky*Cin + ci], the
     # layout of the kernel that folds the horizontal taps into the GEMM N extent (include/vad_b200.h `weight_kx`)
     w_kx: Optional[torch.Tensor] = None
+    # 3x3 layers with 32 input channels only: the pixel-pair folded form (include/vad_b200.h `pair_fold`):
+    # `w_pair` bf16 [2*n_total, 9*64], `bias_pair` fp32 [2*n_total]
+    w_pair: Optional[torch.Tensor] = None
+    bias_pair: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -85,7 +89,25 @@ def pack_conv3x3(w: torch.Tensor, b: torch.Tensor, pad_n_to: int = 0) -> GemmWei
     gw = GemmWeights(wk.to(torch.bfloat16).contiguous(), b.float().contiguous(), 9, cin, n_total, cout)
     if cout <= 64 and cin in (32, 64):
         gw.w_kx = pack_conv3x3_kx(w)
+    if cin == 32 and n_total == cout and cout in (32, 64):
+        gw.w_pair, gw.bias_pair = pack_conv3x3_pair(w, b)
     return gw
+
+
+def pack_conv3x3_pair(w: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[Cout,32,3,3] -> the same convolution on PAIRS of horizontally adjacent pixels: bf16 [2*Cout, 9*64] with row
+    p_out*Cout + co and column (ky*3 + kxp)*64 + p_in*32 + ci holding w[co][ci][ky][kx], kx = 2*(kxp-1) + p_in - p_out + 1
+    (zero where that is outside 0..2: a third of the matrix), and the bias repeated for both pixels."""
+    cout, cin = w.shape[0], w.shape[1]
+    wp = torch.zeros(2, cout, 3, 3, 2, cin, dtype=w.dtype, device=w.device)  # [p_out][co][ky][kxp][p_in][ci]
+    for p_out in range(2):
+        for kxp in range(3):
+            for p_in in range(2):
+                kx = 2 * (kxp - 1) + p_in - p_out + 1
+                if 0 <= kx <= 2:
+                    wp[p_out, :, :, kxp, p_in, :] = w[:, :, :, kx].permute(0, 2, 1)  # [co][ky][ci]
+    return (wp.reshape(2 * cout, 9 * 2 * cin).to(torch.bfloat16).contiguous(),
+            torch.cat([b, b]).float().contiguous())
 
 
 def pack_conv3x3_kx(w: torch.Tensor) -> torch.Tensor:
@@ -243,5 +265,7 @@ def to_device(packed: Dict[str, object], device) -> Dict[str, object]:
                 v.w_pf = v.w_pf.to(device)
             if isinstance(v, GemmWeights) and v.w_kx is not None:
                 v.w_kx = v.w_kx.to(device)
+            if isinstance(v, GemmWeights) and v.w_pair is not None:
+                v.w_pair, v.bias_pair = v.w_pair.to(device), v.bias_pair.to(device)
         res[k] = v
     return res
