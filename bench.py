@@ -166,6 +166,9 @@ def layer_cost(kind, name, B, T, H, W):
         m = F * (H // 4) * (W // 4)
         flops = 2.0 * m * (4 * 32 * 64 + 16 * 3 * 32)
         return flops, m * 64 * 2 + 16 * m * (12 + 4) + F * 12
+    if name == "enc1.0+1.3":  # fused first block: reads the fp32 input, writes the pooled 32-channel tensor
+        m = F * H * W
+        return 2.0 * m * 32 * (27 + 288), m * 3 * 4 + (m // 4) * 32 * 2
     if name == "dec4.0+4.3+score":  # fused tail: reads the 32-ch half-resolution tensor and x, writes the heat map
         m = F * (H // 2) * (W // 2)
         flops = 2.0 * m * (4 * 32 * 32 + 4 * 3 * 9 * 32)

@@ -171,6 +171,14 @@ int vad_first_conv_tc(const float* x, const void* weight_bf16, const float* bias
 int vad_first_conv_pool(const float* x, const void* weight_pf, const float* bias, float slope, int B, int H, int W,
                         void* out_bf16_nhwc, vad_stream_t stream);
 
+/* The first block of the image encoder in one kernel (models/autoencoder.py:38-45: conv3x3(3->32)+BN+LeakyReLU,
+ * conv3x3(32->32)+BN+LeakyReLU, MaxPool2d(2,2)): the 32-channel full-resolution tensor between the two convolutions
+ * stays in shared memory.  w_first: bf16 [32][32] as vad_first_conv_tc; w_pair / bias2: the pixel-pair folded second
+ * conv, bf16 [64][9*64] / fp32 [>= 32] (vad_conv_desc.pair_fold; pack_conv3x3_pair).  H, W multiples of 16;
+ * out bf16 NHWC [B,H/2,W/2,32].  Bit-identical to vad_first_conv_tc followed by the pair-folded VAD_EPI_POOL layer. */
+int vad_enc1_fused(const float* x, const void* w_first, const float* bias1, const void* w_pair, const float* bias2,
+                   float slope, int B, int H, int W, void* out_bf16_nhwc, vad_stream_t stream);
+
 /* ---- scoring reduction ----------------------------------------------------------------------------------------
  * reference models/autoencoder.py:214-221, models/video_autoencoder.py:371-384, evaluate_video.py:56 (min/max) */
 /* finalize the partials of a fused *_SCORE layer (tiles_per_frame = 4 x the frame's tiles: one entry per tile quarter)
@@ -200,6 +208,13 @@ int vad_f32_nchw_to_u8_hwc(const float* src, int frames, int H, int W, uint8_t* 
 /* per-frame normalised error map -> JET-coloured RGB uint8 [N,H,W,3]: `create_heatmap` — evaluate_video.py:52-66 */
 int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int H, int W, uint8_t* out,
                         vad_stream_t stream);
+
+/* the side-by-side panel of the reference's video output: np.hstack([denormalize(frame), denormalize(reconstruction),
+ * create_heatmap(error_map)]) — evaluate_video.py:279-286,355-364 — as uint8 RGB [N,H,3W,3], byte-exact for frames of the
+ * size create_heatmap resizes to (its cv2.resize is then the identity; other sizes stay with cv2 on the host).
+ * x, recon fp32 [N,3,H,W]; heat fp32 [N,H,W]; minmax fp32 [N][2] (all from one vad_*_forward call). */
+int vad_compose_panel(const float* x, const float* recon, const float* heat, const float* minmax, int frames, int H,
+                      int W, uint8_t* out, vad_stream_t stream);
 
 /* ---- SSIM as an alternative anomaly score ----------------------------------------------------- */
 /* SSIMLoss.forward — utils/losses.py:51-93 — per frame: loss[f] = 1 - mean over (3,H,W) of the SSIM map between
@@ -241,6 +256,7 @@ typedef struct vad_first_weights {
 
 #define VAD_FLAG_NO_FUSED_TAIL 1     /* run the decoder's last two layers one by one (test / tuning aid) */
 #define VAD_FLAG_NO_LSTM_WAVEFRONT 2 /* one launch per ConvLSTM layer instead of the two-layer wavefront kernel */
+#define VAD_FLAG_NO_FUSED_ENC1 4     /* image encoder: enc1.0 and enc1.3 as two launches instead of vad_enc1_fused */
 
 /* ConvAutoencoder — reference models/autoencoder.py:24-221 */
 typedef struct vad_image_model {

@@ -114,3 +114,32 @@ def test_score_frames_u8_equals_normalised_fp32_path(cuda_device, kind):
     assert torch.equal(only8.score, b.score) and torch.equal(only8.heat_u8, a.heat_u8)
     with pytest.raises(RuntimeError, match="uint8"):
         m.score_frames(x.to(cuda_device))
+
+
+def test_compose_panels_matches_reference_hstack(cuda_device):
+    """runtime.frames.compose_panels == np.hstack([denormalize(frame), denormalize(recon), create_heatmap(err)]) of the
+    reference (evaluate_video.py:40-66, 355-364), byte for byte, on the outputs of one score_all call (256x256 frames: the
+    size create_heatmap resizes to, so its cv2.resize is the identity)."""
+    from models.video_autoencoder import VideoAutoencoder
+    from oracle.stress import stress_state_dict
+    from runtime import frames
+    torch.manual_seed(0)
+    m = VideoAutoencoder()
+    m.load_state_dict(stress_state_dict(m.state_dict(), seed=1))
+    m = m.eval().to(cuda_device)
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(1, 3, 3, 256, 256, generator=g) * 2.4 - 1.2).to(cuda_device)       # (some values beyond [-1, 1]: clamp)
+    out = m.score_all(x, want_recon=True, want_heat=True)
+    panels = frames.compose_panels(x.view(3, 3, 256, 256), out.recon, out.heat, out.minmax).cpu().numpy()
+    lut = np.load(os.path.join(GOLDEN, "jet_lut_rgb.npy"))
+
+    def denorm(t):                                                  # evaluate_video.py:40-49
+        t = torch.clamp(t * 0.5 + 0.5, 0, 1)
+        return (t.permute(1, 2, 0).cpu().numpy() * 255).astype(np.uint8)
+    for f in range(3):
+        e = out.heat[f].cpu().numpy()
+        norm = (e - e.min()) / (e.max() - e.min() + 1e-8)           # evaluate_video.py:56-57
+        heatmap = lut[(norm * 255).astype(np.uint8)]                # applyColorMap(JET) + BGR2RGB; resize(256,256) = identity
+        ref = np.hstack([denorm(x[0, f]), denorm(out.recon[f]), heatmap])
+        assert panels[f].shape == ref.shape == (256, 768, 3)
+        assert np.array_equal(panels[f], ref)

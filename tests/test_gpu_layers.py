@@ -485,3 +485,43 @@ def test_layout_round_trip(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(nhwc, x.permute(0, 2, 3, 1).to(torch.bfloat16))
     assert torch.equal(back, x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (1, 16, 16), (3, 48, 80), (2, 256, 256), (1, 16, 64)])
+def test_fused_enc1_equals_two_layers(cuda_device, B, H, W):
+    """vad_enc1_fused (image encoder block 1: conv3x3 3->32 + LeakyReLU, conv3x3 32->32 + LeakyReLU, max-pool, with the
+    32-channel full-resolution tensor kept in shared memory) against the two single-layer kernels it replaces — bit for
+    bit (same MMAs in the same order, same bf16 rounding point) — and against torch."""
+    eng, nat, prep = _mods()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(H + W)
+    w1 = torch.randn(32, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    b1 = torch.randn(32, generator=g) * 0.1
+    w2 = torch.randn(32, 32, 3, 3, generator=g) * (2.0 / 288) ** 0.5
+    b2 = torch.randn(32, generator=g) * 0.1
+    fw = prep.to_device({"w": prep.pack_first_conv(w1.double(), b1.double())}, dev)["w"]
+    pk = _dev(prep.pack_conv3x3(w2.double(), b2.double()), dev)
+    x = (torch.rand(B, 3, H, W, generator=g) * 2 - 1).to(dev)
+    fused = torch.full((B, H // 2, W // 2, 32), float("nan"), dtype=torch.bfloat16, device=dev)
+    n0 = nat.launch_count()
+    nat.check(nat.load().vad_enc1_fused(x.data_ptr(), fw.w_tc.data_ptr(), fw.bias.data_ptr(), pk.w_pair.data_ptr(),
+                                        pk.bias_pair.data_ptr(), 0.2, B, H, W, fused.data_ptr(), nat.stream_ptr()),
+              "vad_enc1_fused")
+    assert nat.launch_count() - n0 == 1
+    torch.cuda.synchronize()
+    mid = torch.empty(B, H, W, 32, dtype=torch.bfloat16, device=dev)
+    two = torch.full_like(fused, float("nan"))
+    eng._first_conv(fw, x, B, H, W, False, mid)
+    prev = nat.load().vad_debug_set_kx(0)
+    try:
+        eng._conv(pk, mid, B, H, W, two, 0.2, pool=True, what="enc1.3")
+    finally:
+        nat.load().vad_debug_set_kx(-1)
+    torch.cuda.synchronize()
+    if W >= 32 and H >= 16:                      # (narrower frames: the two-layer path uses the ordinary view of enc1.3)
+        assert torch.equal(fused, two)
+    m = F.leaky_relu(F.conv2d(x.to(torch.bfloat16).float(), w1.to(torch.bfloat16).float().to(dev), b1.to(dev), padding=1), 0.2)
+    m = m.to(torch.bfloat16).float()
+    ref = F.max_pool2d(F.leaky_relu(F.conv2d(m, w2.to(torch.bfloat16).float().to(dev), b2.to(dev), padding=1), 0.2), 2, 2)
+    _assert_close(fused, _nhwc(ref), f"fused enc1 B{B} {H}x{W}")
+    _assert_close(two, _nhwc(ref), f"two-layer enc1 B{B} {H}x{W}")

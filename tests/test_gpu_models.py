@@ -245,6 +245,27 @@ def test_image_fused_decoder_tail_equals_layerwise(cuda_device, shape):
     torch.testing.assert_close(a_score, b.score, rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("shape", [(3, 64, 64), (2, 256, 256), (2, 48, 80), (1, 16, 16)])
+def test_image_fused_enc1_equals_layerwise(cuda_device, shape):
+    """The fused enc1.0 + enc1.3 + pool kernel (default) and the two-launch schedule (VAD_FUSE_ENC1=0) give the same
+    latent, reconstruction, heat map and scores bit for bit."""
+    from models import _engine as eng
+    m = make_image_model(cuda_device, stress=True)
+    x = image_input(55, *shape).to(cuda_device)
+    assert eng.FUSE_ENC1
+    a = m.score_all(x, want_recon=True, want_heat=True, want_latent=True)
+    eng.FUSE_ENC1 = False
+    try:
+        b = m.score_all(x, want_recon=True, want_heat=True, want_latent=True)
+    finally:
+        eng.FUSE_ENC1 = True
+    if shape[2] >= 32:   # (16-pixel-wide frames: the two-launch schedule runs enc1.3 on the ordinary view, 1-ulp flips)
+        assert torch.equal(a.latent, b.latent) and torch.equal(a.recon, b.recon)
+        assert torch.equal(a.heat, b.heat) and torch.equal(a.score, b.score)
+    else:
+        torch.testing.assert_close(a.score, b.score, rtol=1e-3, atol=0)
+
+
 def test_full_size_properties_cfg2(cuda_device):
     """BASELINE cfg2 (batch 256 of 256x256): determinism, batch-partition invariance, map/score consistency."""
     m = make_image_model(cuda_device, stress=True)

@@ -522,6 +522,36 @@ __global__ void __launch_bounds__(256) heatmap_jet_kernel(const float* __restric
   out[i * 3 + 2] = static_cast<uint8_t>(c >> 16);
 }
 
+// Side-by-side panel of the reference's video output (evaluate_video.py:355-364, generate_visualizations :279-286):
+// np.hstack([denormalize(frame), denormalize(reconstruction), create_heatmap(error_map)]) -> uint8 [F][H][3W][3].
+// (create_heatmap's cv2.resize to (256, 256) is the identity at the reference's image size; other sizes stay with cv2.)
+__global__ void __launch_bounds__(256) compose_panel_kernel(const float* __restrict__ x, const float* __restrict__ recon,
+                                                            const float* __restrict__ heat,
+                                                            const float* __restrict__ minmax, int W, long long plane,
+                                                            long long total_px, uint8_t* __restrict__ out) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;  // pixel index over F * plane
+  if (i >= total_px) return;
+  const long long n = i / plane, p = i - n * plane;
+  const long long row = p / W;
+  const int col = static_cast<int>(p - row * W);
+  uint8_t* o = out + ((n * (plane / W) + row) * 3LL * W + col) * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = __fadd_rn(__fmul_rn(__ldg(x + (n * 3 + ch) * plane + p), 0.5f), 0.5f);   // denormalize: evaluate_video.py:40-49
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    o[ch] = static_cast<uint8_t>(__fmul_rn(v, 255.f));
+    float r = __fadd_rn(__fmul_rn(__ldg(recon + (n * 3 + ch) * plane + p), 0.5f), 0.5f);
+    r = fminf(fmaxf(r, 0.f), 1.f);
+    o[3 * W + ch] = static_cast<uint8_t>(__fmul_rn(r, 255.f));
+  }
+  const float mn = minmax[2 * n], mx = minmax[2 * n + 1];
+  const float norm = __fdiv_rn(__fsub_rn(heat[i], mn), __fadd_rn(__fsub_rn(mx, mn), 1e-8f));  // as heatmap_u8_kernel
+  const uint32_t c = c_jet_rgb[static_cast<uint8_t>(__fmul_rn(norm, 255.f))];
+  o[6 * W + 0] = static_cast<uint8_t>(c);
+  o[6 * W + 1] = static_cast<uint8_t>(c >> 8);
+  o[6 * W + 2] = static_cast<uint8_t>(c >> 16);
+}
+
 // ------------------------------------------------------------------------------------------------ SSIM
 // SSIMLoss.forward of the reference (utils/losses.py:51-93): Gaussian-weighted (11x11, sigma 1.5, zero padding) local
 // means / variances / covariance per channel, ssim = (2 mu_p mu_t + C1)(2 s_pt + C2) / ((mu_p^2 + mu_t^2 + C1)(s_pp +
@@ -1323,6 +1353,57 @@ int vad_first_conv_pool(const float* x, const void* weight_pf, const float* bias
   return launch_conv_first_pool(a, grid, stream);
 }
 
+int vad_enc1_fused(const float* x, const void* w_first, const float* bias1, const void* w_pair, const float* bias2,
+                   float slope, int B, int H, int W, void* out, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w_first || !bias1 || !w_pair || !bias2 || !out || B <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  if (H % 16 != 0 || W % 16 != 0) return VAD_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(w_first) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(x) % 16 != 0)
+    return VAD_ERR_ARG;
+  ensure_trap_slot();
+  ConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.pair = 1;
+  a.n_tiles = 1;
+  a.tiles_w = W / 16;  // tiles of 16 x 16 output pixels of the second conv (8 x 8 pooled pixels)
+  a.tiles_h = H / 16;
+  a.tiles_b = B;
+  const long long tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * B;
+  if (tiles > 0x7fffffffLL) return VAD_ERR_SHAPE;
+  a.total_tiles = static_cast<int>(tiles);
+  a.B = B; a.H = H; a.W = W;
+  a.bias = bias1;
+  a.bias2 = bias2;
+  a.slope = slope;
+  a.x = x;
+  a.w_first = w_first;
+  a.out = out;
+  a.cout = 32;
+  a.pair_fold = 1;
+  a.dbg = env_int("VAD_DBG", 0);
+  a.pdl = pdl_all_setting() ? 1 : 0;
+  {
+    // fp32 NCHW input as a 4-D map {W, H, 3, B}; box = 28 x 20 x 3 patch from (16*th - 2, 16*tw - 4): the 16 x 16 tile
+    // plus the halos of both convolutions (24 columns used; 28 keeps the converter's reads bank-conflict free), 16-byte
+    // aligned start, zero fill outside the frame = the first conv's padding
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return VAD_ERR_DRIVER;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+    cuuint64_t st[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+    cuuint32_t box[4] = {28, 20, 3, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (fn(&a.mapA0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, st, box, es,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return VAD_ERR_DRIVER;
+  }
+  const int rc = encode_weight_map(&a.mapB, w_pair, 9 * 64, 64, 64, 64);  // nine [64 n][64 k] slabs of the pair kernel
+  if (rc != VAD_OK) return rc;
+  const int grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
+  return launch_enc1_fused(a, grid, stream);
+}
+
 int vad_score_finalize(const float* partials, int frames, int tiles_per_frame, int H, int W, float* score,
                        float* minmax, vad_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1425,6 +1506,18 @@ int vad_heatmap_jet_rgb(const float* heat, const float* minmax, int frames, int 
   const long long plane = static_cast<long long>(H) * W;
   const long long total = plane * frames;
   heatmap_jet_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(heat, minmax, plane, total, out);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vad_compose_panel(const float* x, const float* recon, const float* heat, const float* minmax, int frames, int H,
+                      int W, uint8_t* out, vad_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !recon || !heat || !minmax || !out || frames <= 0 || H <= 0 || W <= 0) return VAD_ERR_ARG;
+  const long long plane = static_cast<long long>(H) * W;
+  const long long total = plane * frames;
+  compose_panel_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, recon, heat, minmax, W, plane,
+                                                                                      total, out);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

@@ -2562,6 +2562,359 @@ __global__ void __launch_bounds__(kPfThreads, 1) conv_first_pool_kernel(const __
   }
 }
 
+// ---------------------------------------------------------------------- enc1.0 -> enc1.3 (+ pool), fused (image encoder)
+// The first block of the image encoder (reference models/autoencoder.py:38-45: Conv2d(3,32,3,p=1) + BN + LeakyReLU,
+// Conv2d(32,32,3,p=1) + BN + LeakyReLU, MaxPool2d(2,2)) in ONE kernel: the 32-channel full-resolution tensor between
+// the two convolutions (1.07 GB at batch 256, written by enc1.0 and read back by enc1.3) stays in shared memory.
+// Per tile = 16 x 16 output pixels of enc1.3 (8 x 8 pooled pixels):
+//   TMA      fp32 input patch, 3 ch x 20 rows x 24 columns from (16 th - 2, 16 tw - 4), zero fill outside the frame
+//   convert  four warps write the bf16 im2col rows of the 18 x 20 = 360 pixels enc1.3 needs from enc1.0 (its 1-pixel
+//            halo included): three [128 px][32 k] operands, K order k = (ky*3 + kx)*3 + ci as conv_first_kernel
+//   stage A  D1[j][128 px][32 ch] = A1[j] · W1^T                                   (3 x 2 MMAs, N = 32)
+//   ep A     bias + LeakyReLU, bf16 -> the PIXEL-PAIR patch of enc1.3's input in smem: 18 rows x 10 pairs x 128 B with
+//            the SWIZZLE_128B pattern on absolute address bits; pixels outside the image are written as zeros (enc1.3's
+//            padding)
+//   stage B  the pixel-pair folded 3x3 conv of conv_halo_kernel<64, 64> (pair_fold): D2[16 rows x 8 pairs][2 x 32] from
+//            nine row-shifted views of the patch against the resident pair weights, 24 MMAs (N = 64), into D1's columns
+//   ep B     2x2 max-pool (horizontal half inside the lane, vertical half with the row-neighbour lane), bias,
+//            LeakyReLU, 16-byte stores of the pooled bf16 NHWC tile.
+// Both GEMM stages issue the same MMAs in the same order as the two single-layer kernels, and the intermediate is
+// rounded to bf16 exactly where enc1.0 would have stored it: outputs are bit-identical to the two-layer path (tested).
+constexpr int kE1Groups = 3;                       // pipeline stages: TMEM accumulator stage + pair patch per tile in flight
+constexpr int kE1XStages = 4;                      // fp32 input patch ring
+constexpr int kE1AStages = 2;                      // im2col operand ring (three A1 tiles per slot)
+constexpr int kE1ConvWarps = 4;
+// warps: 0 TMA, 1 stage-A issuer, 2 TMEM, 3 stage-B issuer | 4..15 epilogue A: set j = (warp - 4) / 4 reads operand j's
+// accumulator of EVERY tile | 16..19 epilogue B of every tile | 20..23 converters.  (Fixed roles instead of one group
+// of four warps walking a tile through both epilogues: a single warp runs such serial code at ~0.3 instructions per
+// clock, so the group's chain A -> ep A (3 x 128 rows) -> B -> ep B took ~5000 cycles and three groups could not keep
+// the tensor pipe busy.)
+constexpr int kE1EpiBWarp0 = 4 + 12;
+constexpr int kE1ConvWarp0 = kE1EpiBWarp0 + 4;
+constexpr int kE1Threads = 32 * (kE1ConvWarp0 + kE1ConvWarps);
+constexpr int kE1XW = 28, kE1XH = 20;              // (24 columns are used; 28 makes three patch rows 84 = 20 mod 32 floats,
+                                                   //  so that the two row bands a converter warp reads hit disjoint banks)
+constexpr int kE1XBytes = 3 * kE1XH * kE1XW * 4;   // 6720
+constexpr int kE1XPitch = 6784;                    // multiple of 128
+constexpr int kE1PatchW = 20, kE1PatchH = 18, kE1PatchPx = kE1PatchW * kE1PatchH;  // enc1.0 outputs per tile: 360
+constexpr int kE1A1Bytes = 3 * kTileM * 64;        // three [128][32] bf16 tiles, SWIZZLE_64B: 24 KB
+constexpr int kE1W1Bytes = 32 * 64;                // [32 n][32 k] bf16
+constexpr int kE1W2Bytes = 9 * 64 * 128;           // nine [64 n][64 k] bf16 slabs, SWIZZLE_128B: 72 KB
+constexpr int kE1PatchBytes = 23 * 1024;           // 18 x 10 pair rows x 128 B = 23040 -> 1024-aligned pitch
+constexpr int kE1SmemBytes = 1024 + kE1W2Bytes + kE1W1Bytes + kE1AStages * kE1A1Bytes + kE1Groups * kE1PatchBytes +
+                             kE1XStages * kE1XPitch;
+static_assert(kE1SmemBytes <= kSmemBudget, "enc1_fused_kernel shared memory");
+
+__global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int G = kE1Groups;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_bar;
+  __shared__ uint64_t x_full[kE1XStages];
+  __shared__ uint64_t x_empty[kE1XStages];
+  __shared__ uint64_t a1_full[kE1AStages];
+  __shared__ uint64_t a1_empty[kE1AStages];
+  __shared__ uint64_t d1_full_bar[G];
+  __shared__ uint64_t a2_ready_bar[G];
+  __shared__ uint64_t d2_full_bar[G];
+  __shared__ uint64_t acc_empty_bar[G];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[64];  // [0,32) enc1.0, [32,64) enc1.3
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w2 = smem;                                  // pair weights, resident
+  uint8_t* s_w1 = s_w2 + kE1W2Bytes;                     // first-conv weights [32][32], 64B-swizzled
+  uint8_t* s_a1 = s_w1 + kE1W1Bytes;                     // im2col ring (1024-aligned: 72 KB + 2 KB)
+  uint8_t* s_p = s_a1 + kE1AStages * kE1A1Bytes;         // pair patches, one per epilogue group (1024-aligned)
+  uint8_t* s_x = s_p + G * kE1PatchBytes;                // fp32 input patch ring
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.mapA0);
+    tma_prefetch_desc(&a.mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&w_bar, 1);
+    for (int i = 0; i < kE1XStages; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], kE1ConvWarps);
+    }
+    for (int i = 0; i < kE1AStages; ++i) {
+      mbar_init(&a1_full[i], kE1ConvWarps);
+      mbar_init(&a1_empty[i], 1);
+    }
+    for (int i = 0; i < G; ++i) {
+      mbar_init(&d1_full_bar[i], 1);
+      mbar_init(&a2_ready_bar[i], 12);  // every epilogue-A warp has written its rows of the patch
+      mbar_init(&d2_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 4);  // the four epilogue-B warps have read the stage
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 128) {  // first-conv weights: global bf16 [32][32] row-major -> swizzled smem (16-byte chunks)
+    const int n = threadIdx.x >> 2, c16 = threadIdx.x & 3;
+    *reinterpret_cast<uint4*>(s_w1 + staged_off(n, c16, 32)) = reinterpret_cast<const uint4*>(a.w_first)[threadIdx.x];
+  }
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = threadIdx.x < 32 ? a.bias[threadIdx.x] : a.bias2[threadIdx.x - 32];
+  fence_proxy_async_smem();  // s_w1 is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 0 && elect_one()) {  // pair weights: nine [64 x 64] slabs, once (constants: may be fetched before the PDL wait)
+    mbar_arrive_expect_tx(&w_bar, static_cast<uint32_t>(kE1W2Bytes));
+    for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_w2 + tap * (64 * 128), &a.mapB, &w_bar, tap * 64, 0);
+  }
+  if (a.pdl) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer: fp32 input patches
+    const uint32_t xf0 = smem_addr_once(&x_full[0]), xe0 = smem_addr_once(&x_empty[0]);
+    const uint32_t sx0 = smem_addr_once(s_x);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      mbar_wait_a(xe0 + stage * 8, phase ^ 1u, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(xf0 + stage * 8, kE1XBytes);
+        tma_load_4d_a(sx0 + stage * kE1XPitch, &a.mapA0, xf0 + stage * 8, 16 * ti.tw - 4, 16 * ti.th - 2, 0, ti.tb);
+      }
+      __syncwarp();
+      if (++stage == kE1XStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp >= kE1ConvWarp0) {
+    // ===================================================================== converters: fp32 patch -> bf16 im2col rows
+    // Converter thread L = cw*32 + lane < 120 owns patch column c = L % 20 and the three patch rows 3*(L / 20) .. +2:
+    // 5 input rows x 3 columns x 3 channels = 45 shared loads (explicit LDS) for its three im2col rows instead of 81.
+    // Patch pixel (r, c) is image pixel (16 th - 1 + r, 16 tw - 2 + c); its tap (ky, kx) reads input patch element
+    // (r + ky, c + 1 + kx); it becomes row p % 128 of operand p / 128, p = r*20 + c.  A warp's lanes read consecutive
+    // floats of at most two row bands 84 floats apart: conflict-free; they write consecutive A rows: conflict-free.
+    const int cw = warp - kE1ConvWarp0;
+    const int cl = cw * 32 + lane;
+    const int band = cl / kE1PatchW, cc0 = cl - band * kE1PatchW;
+    const bool conv_on = cl < 6 * kE1PatchW;
+    const uint32_t xf0 = smem_addr_once(&x_full[0]), xe0 = smem_addr_once(&x_empty[0]);
+    const uint32_t af0 = smem_addr_once(&a1_full[0]), ae0 = smem_addr_once(&a1_empty[0]);
+    const uint32_t sx_lane = smem_addr_once(s_x) + static_cast<uint32_t>((3 * band * kE1XW + cc0 + 1) * 4);
+    int xs = 0, as = 0;
+    uint32_t xph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(xf0 + xs * 8, xph, 6);
+      mbar_wait_a(ae0 + as * 8, aph ^ 1u, 1);
+      uint8_t* sa = s_a1 + as * kE1A1Bytes;
+      if (conv_on && !(a.dbg & 256)) {
+        const uint32_t xa = sx_lane + static_cast<uint32_t>(xs * kE1XPitch);
+        float f[3][5][3];  // [ci][input row][kx]
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ir = 0; ir < 5; ++ir)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              f[ci][ir][kx] = lds_f32(xa + static_cast<uint32_t>((ci * (kE1XH * kE1XW) + ir * kE1XW + kx) * 4));
+#pragma unroll
+        for (int jr = 0; jr < 3; ++jr) {
+          const int p = (3 * band + jr) * kE1PatchW + cc0;
+          const int m = p & 127;
+          uint8_t* st = sa + (p >> 7) * (kTileM * 64);
+          float v[28];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = f[ci][jr + ky][kx];
+          v[27] = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc)
+            sts128(st + staged_off(m, cc, 32),
+                   make_uint4(pack_bf16x2(v[8 * cc], v[8 * cc + 1]), pack_bf16x2(v[8 * cc + 2], v[8 * cc + 3]),
+                              pack_bf16x2(v[8 * cc + 4], v[8 * cc + 5]), pack_bf16x2(v[8 * cc + 6], v[8 * cc + 7])));
+          sts128(st + staged_off(m, 3, 32), make_uint4(pack_bf16x2(v[24], v[25]), pack_bf16x2(v[26], 0.f), 0u, 0u));
+        }
+      }
+      fence_proxy_async_smem();  // every lane's A rows -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_a(af0 + as * 8);  // this warp's quarter of the three operands is in place
+        mbar_arrive_a(xe0 + xs * 8);  // ... and it is done with the input patch
+      }
+      if (++xs == kE1XStages) { xs = 0; xph ^= 1u; }
+      if (++as == kE1AStages) { as = 0; aph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== stage-A MMA issuer (enc1.0)
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 32);
+    const uint32_t af0 = smem_addr_once(&a1_full[0]), ae0 = smem_addr_once(&a1_empty[0]);
+    const uint32_t d1f0 = smem_addr_once(&d1_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint64_t da_base = umma_smem_desc(smem_u32(s_a1), 512, 4u);
+    const uint64_t db = umma_smem_desc(smem_u32(s_w1), 512, 4u);
+    int as = 0, g = 0, jg = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(acce0 + g * 8, static_cast<uint32_t>(jg & 1) ^ 1u, 3);
+      mbar_wait_a(af0 + as * 8, aph, 2);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint64_t da = da_base + static_cast<uint64_t>((as * kE1A1Bytes + j * (kTileM * 64)) >> 4);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128 + j * 32);
+          umma_bf16(d_tmem, da, db, idesc, 0u);
+          umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+        }
+        umma_commit_a(ae0 + as * 8);
+        umma_commit_a(d1f0 + g * 8);
+      }
+      __syncwarp();
+      if (++as == kE1AStages) { as = 0; aph ^= 1u; }
+      if (++g == G) { g = 0; ++jg; }
+    }
+  } else if (warp == 3) {
+    // ===================================================================== stage-B MMA issuer (pair-folded enc1.3)
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, 64);
+    const uint32_t a2r0 = smem_addr_once(&a2_ready_bar[0]), d2f0 = smem_addr_once(&d2_full_bar[0]);
+    const uint64_t da_hi = umma_smem_desc(0, 10 * 128, 2u);  // 8-pair row groups, 10 pair rows (one patch row) apart
+    const uint64_t db0 = umma_smem_desc(smem_u32(s_w2), 1024, 2u);
+    const uint32_t sp16 = (smem_u32(s_p) & 0x3FFFF) >> 4;
+    int g = 0, jg = 0;
+    mbar_wait(&w_bar, 0, 5);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait_a(a2r0 + g * 8, static_cast<uint32_t>(jg & 1), 6);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p16 = sp16 + static_cast<uint32_t>(g * (kE1PatchBytes >> 4));
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * 128);
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if ((a.dbg & 16) && tap > 0) break;  // ablation: one tap only
+          const uint64_t da = da_hi | static_cast<uint64_t>(p16 + ((((tap / 3) * 10 + tap % 3) * 128) >> 4));
+          const uint64_t db = db0 + static_cast<uint64_t>((tap * 64 * 128) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if ((tap % 3 == 0 && kk < 2) || (tap % 3 == 2 && kk >= 2)) continue;  // structurally zero K steps
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, acc);
+            acc = 1u;
+          }
+        }
+        umma_commit_a(d2f0 + g * 8);
+      }
+      __syncwarp();
+      if (++g == G) { g = 0; ++jg; }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kE1EpiBWarp0) {
+    // ===================================================================== epilogue A: enc1.0's bias + LeakyReLU -> pair patch
+    const int j = (warp - kEpiWarp0) >> 2;  // which of the three [128 px][32 ch] accumulators this warp set reads
+    const int q = warp & 3;                 // TMEM lane quarter == warp_id % 4
+    const int p = j * 128 + q * 32 + lane;  // patch pixel of this thread (tile-invariant)
+    const bool p_ok = p < kE1PatchPx;
+    const int pr = p / kE1PatchW, pc = p - pr * kE1PatchW;
+    const uint32_t poff0 = staged_off(pr * 10 + (pc >> 1), (pc & 1) * 4, 64);  // chunk 0 of this pixel's half pair row
+    const int prow7 = (pr * 10 + (pc >> 1)) & 7;
+    const uint32_t d1f0 = smem_addr_once(&d1_full_bar[0]), a2r0 = smem_addr_once(&a2_ready_bar[0]);
+    const uint32_t tacc0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j * 32);
+    float bias[32];
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) bias[jj] = s_bias[jj];
+    int g = 0;
+    uint32_t ph = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      const int gy = 16 * ti.th - 1 + pr, gx = 16 * ti.tw - 2 + pc;  // image coordinates of this thread's patch pixel
+      const bool inside = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+      uint8_t* patch = s_p + g * kE1PatchBytes;
+      mbar_wait_a(d1f0 + g * 8, ph, 4);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_x32(tacc0 + static_cast<uint32_t>(g * 128), v);  // (warp-collective: also the lanes past pixel 359)
+      tmem_ld_wait();
+      if (p_ok && !(a.dbg & 32)) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          pk[jj] = pack_bf16x2(act_fn(__uint_as_float(v[2 * jj]) + bias[2 * jj], a.slope),
+                               act_fn(__uint_as_float(v[2 * jj + 1]) + bias[2 * jj + 1], a.slope));
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          // chunk (pc & 1) * 4 + jj of the pair row, 128-byte swizzle: XOR the chunk index with the row's low three bits
+          const uint32_t off = (poff0 & ~0x70u) | (((((pc & 1) * 4 + jj) ^ prow7) & 7) << 4);
+          sts128(patch + off, inside ? make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3])
+                                     : make_uint4(0u, 0u, 0u, 0u));  // zeros outside the image: enc1.3's padding
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a2r0 + g * 8);
+      if (++g == G) { g = 0; ph ^= 1u; }
+    }
+  } else if (warp >= kE1EpiBWarp0 && warp < kE1ConvWarp0) {
+    // ===================================================================== epilogue B: 2x2 max-pool, bias, LeakyReLU, store
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int hh = r >> 3, ww = r & 7;  // this accumulator row's (row, pixel pair) inside the 16 x 8 tile
+    const bool up2 = (hh & 1) != 0;
+    const uint32_t d2f0 = smem_addr_once(&d2_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
+    const uint32_t tacc0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int Hp = a.H >> 1, Wp = a.W >> 1;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
+    int g = 0;
+    uint32_t ph = 0;
+    for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
+      const uint32_t tacc = tacc0 + static_cast<uint32_t>(g * 128);
+      const int oh = 8 * ti.th + (hh >> 1), ow = 8 * ti.tw + ww;
+      const bool ok = oh < Hp && ow < Wp && !(a.dbg & 64);
+      __nv_bfloat16* dst0 = outp + ((static_cast<long long>(ti.tb) * Hp + oh) * Wp + ow) * 32 + (up2 ? 8 : 0);
+      mbar_wait_a(d2f0 + g * 8, ph, 7);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v0[16], v1[16];
+        tmem_ld_x16(tacc + c * 16, v0);
+        tmem_ld_x16(tacc + 32 + c * 16, v1);
+        tmem_ld_wait();
+        if (c == 1) {  // the stage's TMEM columns (and its patch) are free for a later tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(acce0 + g * 8);
+        }
+        float gmax[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) gmax[jj] = fmaxf(__uint_as_float(v0[jj]), __uint_as_float(v1[jj]));
+        float mm[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float recv = __shfl_xor_sync(0xffffffffu, up2 ? gmax[jj] : gmax[jj + 8], 8);
+          mm[jj] = fmaxf(up2 ? gmax[jj + 8] : gmax[jj], recv);
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + 32 + c * 16 + (up2 ? 8 : 0));
+        const float4 b0 = b4[0], b1 = b4[1];
+        if (ok)
+          *reinterpret_cast<uint4*>(dst0 + c * 16) = make_uint4(
+              pack_bf16x2(act_fn(mm[0] + b0.x, a.slope), act_fn(mm[1] + b0.y, a.slope)),
+              pack_bf16x2(act_fn(mm[2] + b0.z, a.slope), act_fn(mm[3] + b0.w, a.slope)),
+              pack_bf16x2(act_fn(mm[4] + b1.x, a.slope), act_fn(mm[5] + b1.y, a.slope)),
+              pack_bf16x2(act_fn(mm[6] + b1.z, a.slope), act_fn(mm[7] + b1.w, a.slope)));
+      }
+      if (++g == G) { g = 0; ph ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------- ConvT -> ConvT + tanh + score, fused
 // The last two layers of the video decoder (reference models/video_autoencoder.py:252-259: ConvTranspose2d(64,32,2,2) +
 // BN + ReLU, ConvTranspose2d(32,3,2,2) + Tanh) and the error reduction (:371-384) in ONE kernel.  A k2s2 transposed
@@ -3266,6 +3619,12 @@ int launch_conv_first_pool(const ConvArgs& a, int grid, cudaStream_t stream) {
   static SmemConfig cfg;
   if (int e = ensure_smem(conv_first_pool_kernel, cfg, kPfSmemBytes)) return e;
   return launch_conv_kernel(conv_first_pool_kernel, a, grid, kPfThreads, kPfSmemBytes, stream);
+}
+
+int launch_enc1_fused(const ConvArgs& a, int grid, cudaStream_t stream) {
+  static SmemConfig cfg;
+  if (int e = ensure_smem(enc1_fused_kernel, cfg, kE1SmemBytes)) return e;
+  return launch_conv_kernel(enc1_fused_kernel, a, grid, kE1Threads, kE1SmemBytes, stream);
 }
 
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream) {

@@ -86,6 +86,7 @@ int launch_convlstm2_patch(const ConvArgs& a1, const ConvArgs& a2, int T, int gr
                            cudaStream_t stream);
 int launch_conv_first(int EPI, const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_conv_first_pool(const ConvArgs& a, int grid, cudaStream_t stream);
+int launch_enc1_fused(const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt2_score(const ConvArgs& a, int grid, cudaStream_t stream);
 int launch_convt_conv_score(const ConvArgs& a, int grid, cudaStream_t stream);
 // dynamic shared memory the halo kernel needs for `stages` ring slots (0 if the configuration is not instantiated)

@@ -222,10 +222,27 @@ int score_layer(Ctx& c, const char* name, const vad_gemm_weights& w, const void*
 int image_encode(Ctx& c, const vad_image_model& m, const float* x, int B, int H, int W, void** z, int* which_out) {
   static const char* names[7] = {"enc1.3", "enc2.0", "enc2.3", "enc3.0", "enc3.3", "enc4.0", "enc4.3"};
   int which = 0;
-  void* cur = c.A.ping(which, static_cast<size_t>(B) * H * W * 32 * 2);
-  VAD_TRY(first_conv(c, m.enc1_0, x, B, H, W, false, cur));
   int h = H, w = W;
-  for (int blk = 0; blk < 4; ++blk) {
+  void* cur = nullptr;
+  int first_blk = 0;
+  const vad_gemm_weights& w13 = m.enc[0];
+  const bool fuse1 = !(m.flags & VAD_FLAG_NO_FUSED_ENC1) && m.enc1_0.w_tc && m.enc1_0.cout == 32 && w13.w_pair &&
+                     w13.bias_pair && w13.ntaps == 9 && w13.ctap == 32 && w13.n_total == 32;
+  if (fuse1) {
+    // enc1.0 + enc1.3 + pool in one kernel: the 32-channel full-resolution tensor never reaches HBM
+    cur = c.A.ping(which, static_cast<size_t>(B) * (H / 2) * (W / 2) * 32 * 2);
+    if (!c.dry()) {
+      ProfScope p("enc1.0+1.3", c.stream);
+      VAD_TRY(vad_enc1_fused(x, m.enc1_0.w_tc, m.enc1_0.bias, w13.w_pair, w13.bias_pair, kLeaky, B, H, W, cur, c.stream));
+    }
+    h /= 2;
+    w /= 2;
+    first_blk = 1;
+  } else {
+    cur = c.A.ping(which, static_cast<size_t>(B) * H * W * 32 * 2);
+    VAD_TRY(first_conv(c, m.enc1_0, x, B, H, W, false, cur));
+  }
+  for (int blk = first_blk; blk < 4; ++blk) {
     if (blk > 0) {
       const vad_gemm_weights& w0 = m.enc[2 * blk - 1];
       void* nxt = c.A.ping(which ^ 1, static_cast<size_t>(B) * h * w * w0.n_total * 2);

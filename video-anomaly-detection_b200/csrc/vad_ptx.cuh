@@ -315,6 +315,14 @@ __device__ __forceinline__ void sts128(void* generic_smem_ptr, uint4 v) {
                : "memory");
 }
 
+// explicit shared-space 4-byte load (a generic pointer into dynamic smem otherwise becomes LD.E: slower, and it keeps
+// the LSU pipe busy for longer than LDS)
+__device__ __forceinline__ float lds_f32(uint32_t smem_addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+  return v;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

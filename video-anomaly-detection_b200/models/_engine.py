@@ -28,6 +28,8 @@ FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
 # VAD_FIRST_TC=0: CUDA-core first conv (fp32 operands) instead of the tensor-core one
 FIRST_CONV_TC = os.environ.get("VAD_FIRST_TC", "1") != "0"
+# VAD_FUSE_ENC1=0: image enc1.0 and enc1.3 as two launches instead of the fused kernel (vad_enc1_fused)
+FUSE_ENC1 = os.environ.get("VAD_FUSE_ENC1", "1") != "0"
 # VAD_PAIR_FOLD=0: the 3x3 layers with 32 input channels on the ordinary view instead of the pixel-pair folded one
 PAIR_FOLD = os.environ.get("VAD_PAIR_FOLD", "1") != "0"
 # VAD_FIRST_PF=0: the video encoder's pooled first conv on the one-row-per-input-pixel kernel (vad_first_conv_tc)
@@ -90,7 +92,8 @@ def _first_struct(w: FirstConvWeights) -> "nat.FirstW":
 
 
 def _flags() -> int:
-    return (0 if FUSE_DEC_TAIL else nat.FLAG_NO_FUSED_TAIL) | (0 if FUSE_LSTM_LAYERS else nat.FLAG_NO_LSTM_WAVEFRONT)
+    return (0 if FUSE_DEC_TAIL else nat.FLAG_NO_FUSED_TAIL) | (0 if FUSE_LSTM_LAYERS else nat.FLAG_NO_LSTM_WAVEFRONT) | \
+        (0 if FUSE_ENC1 else nat.FLAG_NO_FUSED_ENC1)
 
 
 def _packed_device(packed: Dict[str, object]) -> torch.device:
@@ -195,6 +198,7 @@ class ImageEngine:
             raise RuntimeError(f"expected 3 input channels, got {cin}")
         _check_hw(H, W)
         out = torch.empty(B, self.latent_dim, H // 16, W // 16, dtype=torch.float32, device=x.device)
+        self.m.flags = _flags()
         with _Call(x.device, self._ws(nat.OP_ENCODE, B, H, W), "vad_image_forward(latent)") as c:
             nat.check(self.lib.vad_image_forward(C.byref(self.m), x.data_ptr(), B, H, W, None, out.data_ptr(), None, None,
                                                  None, c.ws.data_ptr(), c.ws_bytes, c.stream), "vad_image_forward")

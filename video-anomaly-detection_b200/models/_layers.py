@@ -151,6 +151,8 @@ FUSE_DEC_TAIL = os.environ.get("VAD_FUSE_DEC", "1") != "0"
 FUSE_LSTM_LAYERS = os.environ.get("VAD_LSTM2", "1") != "0"
 
 
+# image enc1.0 + enc1.3 + pool as one kernel (vad_enc1_fused); tests flip this
+FUSE_ENC1 = os.environ.get("VAD_FUSE_ENC1", "1") != "0"
 # the pooled first conv on the pool-folded kernel (vad_first_conv_pool) when its weights were prepared; tests flip this
 FIRST_CONV_POOL_FOLD = os.environ.get("VAD_FIRST_PF", "1") != "0"
 
@@ -224,10 +226,22 @@ class ImageEngine:
         B, _, H, W = x.shape
         _check_hw(H, W)
         g = lambda name, shape: self.bufs.get(name, shape, torch.bfloat16, dev)
-        a = g("e1a", (B, H, W, 32))
-        _first_conv(p["enc1.0"], x, B, H, W, False, a)
-        h, w, cur = H, W, a
-        for blk in ("enc1", "enc2", "enc3", "enc4"):
+        w10, w13 = p["enc1.0"], p["enc1.3"]
+        blocks = ("enc1", "enc2", "enc3", "enc4")
+        if FUSE_ENC1 and FIRST_CONV_TC and PAIR_FOLD and w10.w_tc is not None and w10.cout == 32 and \
+                w13.w_pair is not None and w13.n_total == 32:
+            cur = g("enc1b", (B, H // 2, W // 2, 32))
+            _timed("enc1.0+1.3", lambda: nat.check(
+                nat.load().vad_enc1_fused(x.data_ptr(), w10.w_tc.data_ptr(), w10.bias.data_ptr(), w13.w_pair.data_ptr(),
+                                          w13.bias_pair.data_ptr(), LEAKY, B, H, W, cur.data_ptr(), nat.stream_ptr()),
+                "vad_enc1_fused"))
+            h, w = H // 2, W // 2
+            blocks = blocks[1:]
+        else:
+            a = g("e1a", (B, H, W, 32))
+            _first_conv(w10, x, B, H, W, False, a)
+            h, w, cur = H, W, a
+        for blk in blocks:
             if blk != "enc1":
                 w0: GemmWeights = p[f"{blk}.0"]
                 nxt = g(f"{blk}a", (B, h, w, w0.n_total))

@@ -18,17 +18,17 @@ EPI_STORE, EPI_POOL, EPI_CONVT, EPI_LSTM, EPI_TANH_SCORE, EPI_CONVT_TANH_SCORE =
 
 # every symbol include/vad_b200.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convt2_score", "vad_convt2_score_tiles", "vad_convt_conv_score", "vad_convt_conv_score_tiles", "vad_convlstm_sequence", "vad_convlstm2_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc", "vad_first_conv_pool",
+    "vad_error_string", "vad_version", "vad_launch_count", "vad_debug_last_trap", "vad_debug_set_timeline", "vad_debug_set_kx", "vad_debug_set_lstm_mode", "vad_conv_layer", "vad_conv_layer_tiles", "vad_convt2_score", "vad_convt2_score_tiles", "vad_convt_conv_score", "vad_convt_conv_score_tiles", "vad_convlstm_sequence", "vad_convlstm2_sequence", "vad_conv_m_tiles", "vad_first_conv", "vad_first_conv_tc", "vad_first_conv_pool", "vad_enc1_fused",
     "vad_score_finalize", "vad_score_scratch_bytes", "vad_score", "vad_nhwc_bf16_to_nchw_f32",
     "vad_nchw_f32_to_nhwc_bf16", "vad_heatmap_u8", "vad_u8_hwc_to_f32_nchw", "vad_f32_nchw_to_u8_hwc",
-    "vad_heatmap_jet_rgb", "vad_ssim_scratch_bytes", "vad_ssim_loss",
+    "vad_heatmap_jet_rgb", "vad_compose_panel", "vad_ssim_scratch_bytes", "vad_ssim_loss",
     # model-level entry points (one call per reference method)
     "vad_image_workspace_bytes", "vad_image_forward", "vad_image_forward_u8", "vad_image_decode",
     "vad_video_workspace_bytes", "vad_video_forward", "vad_video_forward_u8", "vad_video_encode", "vad_video_score_latents", "vad_video_decode", "vad_convlstm_forward",
     "vad_convlstm_cell_workspace_bytes", "vad_convlstm_cell", "vad_profile_enable", "vad_profile_dump",
 )
 
-FLAG_NO_FUSED_TAIL, FLAG_NO_LSTM_WAVEFRONT = 1, 2
+FLAG_NO_FUSED_TAIL, FLAG_NO_LSTM_WAVEFRONT, FLAG_NO_FUSED_ENC1 = 1, 2, 4
 OP_FORWARD, OP_ENCODE, OP_DECODE, OP_CONVLSTM, OP_SCORE_LATENTS, OP_FORWARD_U8 = range(6)
 MAX_LSTM_LAYERS = 8
 
@@ -116,6 +116,8 @@ def load() -> C.CDLL:
                                       C.c_void_p, C.c_void_p]
     lib.vad_first_conv_pool.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p]
+    lib.vad_enc1_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_void_p]
     lib.vad_score_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     lib.vad_score_scratch_bytes.restype = C.c_size_t
@@ -128,6 +130,8 @@ def load() -> C.CDLL:
     lib.vad_u8_hwc_to_f32_nchw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.vad_f32_nchw_to_u8_hwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.vad_heatmap_jet_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.vad_compose_panel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p]
     lib.vad_ssim_scratch_bytes.restype = C.c_size_t
     lib.vad_ssim_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.vad_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -20,8 +20,9 @@ def normalize_u8(frames_u8: torch.Tensor) -> torch.Tensor:
     lead, (H, W) = x.shape[:-3], x.shape[-3:-1]
     n = int(torch.tensor(lead).prod()) if len(lead) else 1
     out = torch.empty(*lead, 3, H, W, dtype=torch.float32, device=x.device)
-    nat.check(nat.load().vad_u8_hwc_to_f32_nchw(x.data_ptr(), n, H, W, out.data_ptr(), nat.stream_ptr()),
-              "vad_u8_hwc_to_f32_nchw")
+    with torch.cuda.device(x.device):  # the library works on the current device: make it the tensors' one
+        nat.check(nat.load().vad_u8_hwc_to_f32_nchw(x.data_ptr(), n, H, W, out.data_ptr(), nat.stream_ptr(x.device)),
+                  "vad_u8_hwc_to_f32_nchw")
     return out
 
 
@@ -33,8 +34,9 @@ def denormalize_u8(x: torch.Tensor) -> torch.Tensor:
     lead, (H, W) = x.shape[:-3], x.shape[-2:]
     n = int(torch.tensor(lead).prod()) if len(lead) else 1
     out = torch.empty(*lead, H, W, 3, dtype=torch.uint8, device=x.device)
-    nat.check(nat.load().vad_f32_nchw_to_u8_hwc(x.data_ptr(), n, H, W, out.data_ptr(), nat.stream_ptr()),
-              "vad_f32_nchw_to_u8_hwc")
+    with torch.cuda.device(x.device):
+        nat.check(nat.load().vad_f32_nchw_to_u8_hwc(x.data_ptr(), n, H, W, out.data_ptr(), nat.stream_ptr(x.device)),
+                  "vad_f32_nchw_to_u8_hwc")
     return out
 
 
@@ -46,6 +48,25 @@ def render_heatmap(heat: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     heat, minmax = heat.contiguous(), minmax.contiguous().float()
     F, H, W = heat.shape
     out = torch.empty(F, H, W, 3, dtype=torch.uint8, device=heat.device)
-    nat.check(nat.load().vad_heatmap_jet_rgb(heat.data_ptr(), minmax.data_ptr(), F, H, W, out.data_ptr(),
-                                             nat.stream_ptr()), "vad_heatmap_jet_rgb")
+    with torch.cuda.device(heat.device):
+        nat.check(nat.load().vad_heatmap_jet_rgb(heat.data_ptr(), minmax.data_ptr(), F, H, W, out.data_ptr(),
+                                                 nat.stream_ptr(heat.device)), "vad_heatmap_jet_rgb")
+    return out
+
+
+def compose_panels(x: torch.Tensor, recon: torch.Tensor, heat: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
+    """The reference's side-by-side frames, `np.hstack([denormalize(frame), denormalize(recon), create_heatmap(err)])`
+    (evaluate_video.py:279-286, 355-364), for all frames of one `score_all(x, want_recon=True)` call at once:
+    x, recon fp32 [F,3,H,W], heat fp32 [F,H,W], minmax [F,2] -> uint8 RGB [F, H, 3W, 3] (byte-exact when the frames have
+    the size create_heatmap resizes to; the score bar / text / VideoWriter stay with cv2 on the host)."""
+    if not (x.is_cuda and recon.is_cuda and heat.is_cuda) or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+        raise RuntimeError("compose_panels expects CUDA fp32 tensors x, recon [F,3,H,W], heat [F,H,W], minmax [F,2]")
+    x, recon, heat, minmax = x.contiguous(), recon.contiguous().float(), heat.contiguous().float(), minmax.contiguous().float()
+    F, _, H, W = x.shape
+    if tuple(recon.shape) != (F, 3, H, W) or tuple(heat.shape) != (F, H, W) or tuple(minmax.shape) != (F, 2):
+        raise RuntimeError("compose_panels: shapes of x, recon, heat, minmax do not belong together")
+    out = torch.empty(F, H, 3 * W, 3, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        nat.check(nat.load().vad_compose_panel(x.data_ptr(), recon.data_ptr(), heat.data_ptr(), minmax.data_ptr(), F, H, W,
+                                               out.data_ptr(), nat.stream_ptr(x.device)), "vad_compose_panel")
     return out

@@ -27,8 +27,9 @@ def ssim_loss(pred: torch.Tensor, target: torch.Tensor, want_map: bool = False
     loss = torch.empty(n, dtype=torch.float32, device=p.device)
     smap = torch.empty_like(p) if want_map else None
     scratch = torch.empty(lib.vad_ssim_scratch_bytes(n, H, W), dtype=torch.uint8, device=p.device)
-    nat.check(lib.vad_ssim_loss(p.data_ptr(), t.data_ptr(), n, H, W, loss.data_ptr(), nat.ptr(smap), scratch.data_ptr(),
-                                nat.stream_ptr()), "vad_ssim_loss")
+    with torch.cuda.device(p.device):  # the library works on the current device: make it the tensors' one
+        nat.check(lib.vad_ssim_loss(p.data_ptr(), t.data_ptr(), n, H, W, loss.data_ptr(), nat.ptr(smap),
+                                    scratch.data_ptr(), nat.stream_ptr(p.device)), "vad_ssim_loss")
     return loss.view(lead) if lead else loss.view(()), smap
 
 
