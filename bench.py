@@ -517,6 +517,18 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    # third roof of the narrow (N <= 64) image layers: the shared-memory port.  A tcgen05.mma streams its 128 x 32 B
+    # A slab and its B slab from shared memory at 128 B/clk whatever N is, and TMA writes, LDS and STS use the same
+    # port; bytes per tile as counted in DESIGN.md section 3 / finding 18, clock = the median sampled under load.
+    if kind == "image" and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        for k, (tile_px, tile_bytes) in {"enc1.0+1.3": (256, 252576), "enc2.3": (128, 244224)}.items():
+            if k in roof["per_kernel"]:
+                div = 1 if k.startswith("enc1") else 2
+                tiles = B * T * (-(-(H // div) // 16)) * (-(-(W // div) // (tile_px // 16)))
+                cyc = roof["per_kernel"][k]["ms"] * 1e-3 * clocks["sm_mhz"] * 1e6 / (tiles / sms)
+                roof["per_kernel"][k]["smem_port"] = {"bytes_per_tile": tile_bytes, "cycles_per_tile": round(cyc),
+                                                      "frac": round(tile_bytes / 128.0 / cyc, 3)}
     frames = B * T * world * args.steps
     h2d = u8h.numel()
     d2h = B * T * 4 + B * T * H * W

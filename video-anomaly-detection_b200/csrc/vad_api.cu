@@ -666,7 +666,7 @@ int vad_version(void) { return 100; }
 unsigned long long vad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static long long* g_timeline = nullptr;
-int vad_debug_set_timeline(long long* device_buf) {  // 4 roles x 64 tiles x 8 events; NULL disables
+int vad_debug_set_timeline(long long* device_buf) {  // up to 5 roles x 64 tiles x 16 events; NULL disables
   g_timeline = device_buf;
   return VAD_OK;
 }
@@ -1381,6 +1381,7 @@ int vad_enc1_fused(const float* x, const void* w_first, const float* bias1, cons
   a.out = out;
   a.cout = 32;
   a.pair_fold = 1;
+  a.timeline = g_timeline;
   a.dbg = env_int("VAD_DBG", 0);
   a.pdl = pdl_all_setting() ? 1 : 0;
   {

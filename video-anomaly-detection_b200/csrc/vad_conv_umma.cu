@@ -2607,6 +2607,14 @@ static_assert(kE1SmemBytes <= kSmemBudget, "enc1_fused_kernel shared memory");
 
 __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int G = kE1Groups;
+#ifdef VAD_TIMELINE
+  int tl_n = 0;  // tiles this role has walked (timeline row; tools/timeline_enc1.py)
+#define E1_STAMP(role, ev, cond) do { if (cond) tl_stamp(a, role, tl_n, ev); } while (0)
+#define E1_NEXT() (++tl_n)
+#else
+#define E1_STAMP(role, ev, cond) do { } while (0)
+#define E1_NEXT() do { } while (0)
+#endif
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_bar;
   __shared__ uint64_t x_full[kE1XStages];
@@ -2706,8 +2714,11 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
     int xs = 0, as = 0;
     uint32_t xph = 0, aph = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      E1_STAMP(0, 0, cl == 0);
       mbar_wait_a(xf0 + xs * 8, xph, 6);
+      E1_STAMP(0, 1, cl == 0);
       mbar_wait_a(ae0 + as * 8, aph ^ 1u, 1);
+      E1_STAMP(0, 2, cl == 0);
       uint8_t* sa = s_a1 + as * kE1A1Bytes;
       if (conv_on && !(a.dbg & 256)) {
         const uint32_t xa = sx_lane + static_cast<uint32_t>(xs * kE1XPitch);
@@ -2746,6 +2757,8 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
         mbar_arrive_a(af0 + as * 8);  // this warp's quarter of the three operands is in place
         mbar_arrive_a(xe0 + xs * 8);  // ... and it is done with the input patch
       }
+      E1_STAMP(0, 3, cl == 0);
+      E1_NEXT();
       if (++xs == kE1XStages) { xs = 0; xph ^= 1u; }
       if (++as == kE1AStages) { as = 0; aph ^= 1u; }
     }
@@ -2759,8 +2772,11 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
     int as = 0, g = 0, jg = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      E1_STAMP(1, 0, lane == 0);
       mbar_wait_a(acce0 + g * 8, static_cast<uint32_t>(jg & 1) ^ 1u, 3);
+      E1_STAMP(1, 1, lane == 0);
       mbar_wait_a(af0 + as * 8, aph, 2);
+      E1_STAMP(1, 2, lane == 0);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -2774,6 +2790,8 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
         umma_commit_a(d1f0 + g * 8);
       }
       __syncwarp();
+      E1_STAMP(1, 3, lane == 0);
+      E1_NEXT();
       if (++as == kE1AStages) { as = 0; aph ^= 1u; }
       if (++g == G) { g = 0; ++jg; }
     }
@@ -2787,7 +2805,9 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
     int g = 0, jg = 0;
     mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      E1_STAMP(3, 0, lane == 0);
       mbar_wait_a(a2r0 + g * 8, static_cast<uint32_t>(jg & 1), 6);
+      E1_STAMP(3, 1, lane == 0);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t p16 = sp16 + static_cast<uint32_t>(g * (kE1PatchBytes >> 4));
@@ -2808,6 +2828,8 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
         umma_commit_a(d2f0 + g * 8);
       }
       __syncwarp();
+      E1_STAMP(3, 2, lane == 0);
+      E1_NEXT();
       if (++g == G) { g = 0; ++jg; }
     }
   } else if (warp >= kEpiWarp0 && warp < kE1EpiBWarp0) {
@@ -2830,11 +2852,14 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
       const int gy = 16 * ti.th - 1 + pr, gx = 16 * ti.tw - 2 + pc;  // image coordinates of this thread's patch pixel
       const bool inside = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
       uint8_t* patch = s_p + g * kE1PatchBytes;
+      E1_STAMP(2, 0, warp == kEpiWarp0 && lane == 0);
       mbar_wait_a(d1f0 + g * 8, ph, 4);
+      E1_STAMP(2, 1, warp == kEpiWarp0 && lane == 0);
       tc_fence_after();
       uint32_t v[32];
       tmem_ld_x32(tacc0 + static_cast<uint32_t>(g * 128), v);  // (warp-collective: also the lanes past pixel 359)
       tmem_ld_wait();
+      E1_STAMP(2, 2, warp == kEpiWarp0 && lane == 0);
       if (p_ok && !(a.dbg & 32)) {
         uint32_t pk[16];
 #pragma unroll
@@ -2853,6 +2878,8 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(a2r0 + g * 8);
+      E1_STAMP(2, 3, warp == kEpiWarp0 && lane == 0);
+      E1_NEXT();
       if (++g == G) { g = 0; ph ^= 1u; }
     }
   } else if (warp >= kE1EpiBWarp0 && warp < kE1ConvWarp0) {
@@ -2872,7 +2899,9 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
       const int oh = 8 * ti.th + (hh >> 1), ow = 8 * ti.tw + ww;
       const bool ok = oh < Hp && ow < Wp && !(a.dbg & 64);
       __nv_bfloat16* dst0 = outp + ((static_cast<long long>(ti.tb) * Hp + oh) * Wp + ow) * 32 + (up2 ? 8 : 0);
+      E1_STAMP(4, 0, r == 0);
       mbar_wait_a(d2f0 + g * 8, ph, 7);
+      E1_STAMP(4, 1, r == 0);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -2884,6 +2913,7 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_a(acce0 + g * 8);
+          E1_STAMP(4, 2, r == 0);
         }
         float gmax[16];
 #pragma unroll
@@ -2903,6 +2933,8 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
               pack_bf16x2(act_fn(mm[4] + b1.x, a.slope), act_fn(mm[5] + b1.y, a.slope)),
               pack_bf16x2(act_fn(mm[6] + b1.z, a.slope), act_fn(mm[7] + b1.w, a.slope)));
       }
+      E1_STAMP(4, 3, r == 0);
+      E1_NEXT();
       if (++g == G) { g = 0; ph ^= 1u; }
     }
   }
@@ -2914,6 +2946,8 @@ __global__ void __launch_bounds__(kE1Threads, 1) enc1_fused_kernel(const __grid_
     tmem_dealloc<512>(tmem_base);
   }
 }
+#undef E1_STAMP
+#undef E1_NEXT
 
 // ------------------------------------------------------------------------------- ConvT -> ConvT + tanh + score, fused
 // The last two layers of the video decoder (reference models/video_autoencoder.py:252-259: ConvTranspose2d(64,32,2,2) +
