@@ -517,18 +517,21 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    # third roof of the narrow (N <= 64) image layers: the shared-memory port.  A tcgen05.mma streams its 128 x 32 B
-    # A slab and its B slab from shared memory at 128 B/clk whatever N is, and TMA writes, LDS and STS use the same
-    # port; bytes per tile as counted in DESIGN.md section 3 / finding 18, clock = the median sampled under load.
+    # third roof of the narrow (N <= 64) image layers: the tensor core's operand stream out of shared memory.  A
+    # tcgen05.mma (M = 128, K = 16) reads its 4 KB A slab and its N x 32 B slab at 128 B/clk whatever N is (ncu:
+    # l1tex__data_pipe_tc_wavefronts_mem_shared = exactly these bytes / 128), so MMAs x bytes per tile / 128 is a floor in
+    # cycles (DESIGN.md finding 18); clock = the median sampled under load.
     if kind == "image" and clocks and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        for k, (tile_px, tile_bytes) in {"enc1.0+1.3": (256, 252576), "enc2.3": (128, 244224)}.items():
+        for k, (tile_px, tc_bytes) in {"enc1.0+1.3": (256, 6 * 5120 + 24 * 6144), "enc2.3": (128, 36 * 6144)}.items():
             if k in roof["per_kernel"]:
                 div = 1 if k.startswith("enc1") else 2
                 tiles = B * T * (-(-(H // div) // 16)) * (-(-(W // div) // (tile_px // 16)))
                 cyc = roof["per_kernel"][k]["ms"] * 1e-3 * clocks["sm_mhz"] * 1e6 / (tiles / sms)
-                roof["per_kernel"][k]["smem_port"] = {"bytes_per_tile": tile_bytes, "cycles_per_tile": round(cyc),
-                                                      "frac": round(tile_bytes / 128.0 / cyc, 3)}
+                roof["per_kernel"][k]["tc_smem_stream"] = {"bytes_per_tile": tc_bytes, "cycles_per_tile": round(cyc),
+                                                           "frac": round(tc_bytes / 128.0 / cyc, 3),
+                                                           "clock_mhz": clocks["sm_mhz"]}  # (nvidia-smi median: an upper
+                # bound of the clock the power-capped step really ran at, so `frac` is a lower bound; ncu: 0.72 / 0.89)
     frames = B * T * world * args.steps
     h2d = u8h.numel()
     d2h = B * T * 4 + B * T * H * W
@@ -542,6 +545,8 @@ def main():
                     "d2h_bytes_per_step": d2h,
                     "h2d_gbs_per_gpu": round(h2d * args.steps / e2e_s / 1e9, 1),
                     "d2h_gbs_per_gpu": round(d2h * args.steps / e2e_s / 1e9, 1),
+                    "h2d_gbs_all_gpus": round(world * h2d * args.steps / e2e_s / 1e9, 1),  # what the host had to feed
+                    "d2h_gbs_all_gpus": round(world * d2h * args.steps / e2e_s / 1e9, 1),
                     "note": "model.score_frames from pinned host memory: uint8 HWC frames up (normalised on the device), "
                             "per-frame scores + uint8 heat maps (evaluate_video.py:56-57) down, 3-deep pipeline on copy / "
                             "compute / drain streams"

@@ -71,8 +71,9 @@ def test_model_entry_points_reject_bad_arguments(lib):
 
 def test_workspace_query_matches_the_schedule(lib):
     """vad_*_workspace_bytes on real (CPU-resident) prepared weights: pointers are only stored, nothing is launched.
-    cfg2: two ping-pong regions (1.07 GB for enc1.0's output + 0.27 GB) and the score partials — not the sum of all
-    layer outputs (2.9 GB)."""
+    cfg2: two ping-pong regions and the score partials — not the sum of all layer outputs (2.9 GB); with the fused first
+    block (default) the largest activation is enc1's pooled output (0.27 GB) + the 0.54 GB enc2.0 output, without it
+    enc1.0's 1.07 GB full-resolution output."""
     import torch
     from models import _engine as eng, _native as nat, _prepare as prep
     from models import ConvAutoencoder
@@ -80,7 +81,15 @@ def test_workspace_query_matches_the_schedule(lib):
     torch.manual_seed(0)
     ie = eng.ImageEngine(prep.prepare_image(ConvAutoencoder().state_dict()))
     full = ie._ws(nat.OP_FORWARD, 256, 256, 256)
-    assert 1.3e9 < full < 1.45e9, full
+    assert 0.8e9 < full < 0.9e9, full
+    assert eng.FUSE_ENC1
+    eng.FUSE_ENC1 = False
+    try:
+        ie.m.flags = eng._flags()   # (run() refreshes the flags on every call; the bare workspace query does not)
+        assert 1.3e9 < ie._ws(nat.OP_FORWARD, 256, 256, 256) < 1.45e9
+    finally:
+        eng.FUSE_ENC1 = True
+        ie.m.flags = eng._flags()
     assert ie._ws(nat.OP_ENCODE, 256, 256, 256) <= full
     assert ie._ws(nat.OP_FORWARD, 1, 40, 64) == 0                                               # H not a multiple of 16
     small = ie._ws(nat.OP_FORWARD, 2, 32, 32)
