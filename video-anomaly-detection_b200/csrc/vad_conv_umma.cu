@@ -2969,9 +2969,12 @@ constexpr int kC2Stages = 6;
 constexpr int kC2Threads = 128 + 128 * kC2Groups;
 constexpr int kC2W1Bytes = 128 * 128;     // [4 taps x 32 ch][64 k] bf16, SWIZZLE_128B
 constexpr int kC2W2Bytes = 1024;          // [4 taps x 3 ch -> 16 rows][32 k] bf16, SWIZZLE_64B
+constexpr int kC2BiasBytes = 4096 + 1024 + 1024;  // the first ConvT's bias as a GEMM operand (convt_conv_score_kernel's
+                                                  // scheme) + padding that keeps the input ring 1024-byte aligned
 constexpr int kC2ABytes = kTileM * 128;   // one input tile: 128 pixels x 64 channels
 constexpr int kC2TapBytes = kTileM * 64;  // one stage-2 operand: 128 pixels x 32 channels
-constexpr int kC2SmemBytes = 1024 + kC2W1Bytes + kC2W2Bytes + kC2Stages * kC2ABytes + kC2Groups * 4 * kC2TapBytes;
+constexpr int kC2SmemBytes = 1024 + kC2W1Bytes + kC2W2Bytes + kC2BiasBytes + kC2Stages * kC2ABytes + kC2Groups * 4 * kC2TapBytes;
+static_assert((kC2W1Bytes + kC2W2Bytes + kC2BiasBytes) % 1024 == 0, "1024-byte aligned operands");
 static_assert(kC2SmemBytes <= kSmemBudget, "convt2_score_kernel shared memory");
 
 __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __grid_constant__ ConvArgs a) {
@@ -2992,7 +2995,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w1 = smem;
   uint8_t* s_w2 = s_w1 + kC2W1Bytes;
-  uint8_t* s_a = s_w2 + kC2W2Bytes;
+  uint8_t* s_bb = s_w2 + kC2W2Bytes;   // bias operand B: [2][128][16 B]
+  uint8_t* s_ba = s_bb + 4096;         // bias operand A: [2][8][16 B]
+  uint8_t* s_a = s_w2 + kC2W2Bytes + kC2BiasBytes;
   uint8_t* s_a2 = s_a + kC2Stages * kC2ABytes;
   const int rows_valid = 1 << (a.lgTW + a.lgTH + a.lgTN);  // <= 128
   const uint32_t tx_bytes = static_cast<uint32_t>(rows_valid * 128);
@@ -3021,6 +3026,17 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < 128 + 16; i += kC2Threads) s_bias[i] = i < 128 ? a.bias[i] : a.bias2[i - 128];
+  if (threadIdx.x < 128) {  // D1 += ones · bias^T as one more K step of stage 1 (see convt_conv_score_kernel)
+    const float b = a.bias[threadIdx.x];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    const uint32_t w = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+    *reinterpret_cast<uint4*>(s_bb + threadIdx.x * 16) = make_uint4(w, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s_bb + 2048 + threadIdx.x * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < 16)
+      *reinterpret_cast<uint4*>(s_ba + threadIdx.x * 16) = make_uint4(threadIdx.x < 8 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();  // the bias operands are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -3058,6 +3074,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
     const uint32_t d1f0 = smem_addr_once(&d1_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
     const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 1024, 2u);
     const uint64_t db = umma_smem_desc(smem_u32(s_w1), 1024, 2u);
+    const uint64_t da_bias = umma_smem_desc_noswz(smem_u32(s_ba), 128, 0);     // every 8-row group: the same core matrix
+    const uint64_t db_bias = umma_smem_desc_noswz(smem_u32(s_bb), 2048, 128);
     int stage = 0, g = 0, j = 0;
     uint32_t phase = 0;
     mbar_wait(&w_bar, 0, 5);
@@ -3072,6 +3090,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, kk > 0 ? 1u : 0u);
         umma_commit_a(empty0 + stage * 8);
+        umma_bf16(d_tmem, da_bias, db_bias, idesc, 1u);  // + bias (constants only: after the input slot's release)
         umma_commit_a(d1f0 + g * 8);
       }
       __syncwarp();
@@ -3141,24 +3160,15 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
         uint32_t v[32];
         tmem_ld_x32(tacc + tap * 32, v);
         tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + tap * 32);
-        uint32_t p[16];
+        uint32_t p[16];  // (bias: added by the GEMM)
         if (relu) {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float4 bv = b4[jj];
-            p[2 * jj] = pack_bf16x2_relu(__uint_as_float(v[4 * jj]) + bv.x, __uint_as_float(v[4 * jj + 1]) + bv.y);
-            p[2 * jj + 1] = pack_bf16x2_relu(__uint_as_float(v[4 * jj + 2]) + bv.z, __uint_as_float(v[4 * jj + 3]) + bv.w);
-          }
+          for (int jj = 0; jj < 16; ++jj)
+            p[jj] = pack_bf16x2_relu(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
         } else {
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float4 bv = b4[jj];
-            p[2 * jj] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj]) + bv.x, a.slope),
-                                    act_fn(__uint_as_float(v[4 * jj + 1]) + bv.y, a.slope));
-            p[2 * jj + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj + 2]) + bv.z, a.slope),
-                                        act_fn(__uint_as_float(v[4 * jj + 3]) + bv.w, a.slope));
-          }
+          for (int jj = 0; jj < 16; ++jj)
+            p[jj] = pack_bf16x2(act_fn(__uint_as_float(v[2 * jj]), a.slope), act_fn(__uint_as_float(v[2 * jj + 1]), a.slope));
         }
         uint8_t* buf = my_a2 + tap * kC2TapBytes;
 #pragma unroll
@@ -3259,15 +3269,18 @@ __global__ void __launch_bounds__(kC2Threads, 1) convt2_score_kernel(const __gri
 // [30*tw - 1, 30*tw + 29) — tiles overlap by one input pixel, 75-80 % of stage 1 and 82 % of stage 2 is useful work,
 // which is cheap next to the 2.1 GB of HBM traffic saved per batch.
 constexpr int kI2Groups = 4;
-constexpr int kI2Stages = 8;
+constexpr int kI2Stages = 7;                  // input-tile ring (8 until the bias operands took 5 KB)
 constexpr int kI2Threads = 128 + 128 * kI2Groups;
 constexpr int kI2W1Bytes = 128 * 64;          // [4 taps x 32 ch][32 k] bf16, SWIZZLE_64B
 constexpr int kI2W2Bytes = 3 * 1024;          // three [16][32] slabs (ky), SWIZZLE_64B
+constexpr int kI2BiasBytes = 4096 + 1024;     // the transposed conv's bias as a GEMM operand (no swizzle): B = [2 K
+                                              // chunks][128 n][16 B] with k0 / k1 = bias hi / lo (bf16), A = one 8-row
+                                              // core matrix of {1, 1, 0, ...} + a zero one, shared by all rows (SBO = 0)
 constexpr int kI2ABytes = kTileM * 64;        // one input tile: 8 x 16 pixels x 32 channels
 constexpr int kI2PatchBytes = 18 * 32 * 64;   // 16 patch rows + 2 rows only ever read into discarded accumulator rows
-constexpr int kI2SmemBytes = 1024 + kI2W1Bytes + kI2W2Bytes + kI2Stages * kI2ABytes + kI2Groups * kI2PatchBytes;
+constexpr int kI2SmemBytes = 1024 + kI2W1Bytes + kI2W2Bytes + kI2BiasBytes + kI2Stages * kI2ABytes + kI2Groups * kI2PatchBytes;
 static_assert(kI2SmemBytes <= kSmemBudget, "convt_conv_score_kernel shared memory");
-static_assert((kI2W1Bytes + kI2W2Bytes) % 1024 == 0 && kI2PatchBytes % 1024 == 0, "1024-byte aligned operands");
+static_assert((kI2W1Bytes + kI2W2Bytes + kI2BiasBytes) % 1024 == 0 && kI2PatchBytes % 1024 == 0, "1024-byte aligned operands");
 
 __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int G = kI2Groups;
@@ -3287,7 +3300,9 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w1 = smem;
   uint8_t* s_w2 = s_w1 + kI2W1Bytes;
-  uint8_t* s_a = s_w2 + kI2W2Bytes;
+  uint8_t* s_bb = s_w2 + kI2W2Bytes;   // bias operand B: [2][128][16 B]
+  uint8_t* s_ba = s_bb + 4096;         // bias operand A: [2][8][16 B]
+  uint8_t* s_a = s_ba + 1024;
   uint8_t* s_p = s_a + kI2Stages * kI2ABytes;
 
   if (warp == 0 && lane == 0) {
@@ -3314,6 +3329,19 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < 128 + 16; i += kI2Threads) s_bias[i] = i < 128 ? a.bias[i] : a.bias2[i - 128];
+  if (threadIdx.x < 128) {
+    // D1 += ones · bias^T as a third K step of stage 1: bias[n] = hi + lo in bf16 (exact to 2^-17 relative) against two
+    // columns of ones — epilogue 1 loses its 128 FADDs and 32 bias loads per lane (it is instruction-issue-bound)
+    const float b = a.bias[threadIdx.x];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+    const uint32_t w = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+    *reinterpret_cast<uint4*>(s_bb + threadIdx.x * 16) = make_uint4(w, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s_bb + 2048 + threadIdx.x * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < 16)
+      *reinterpret_cast<uint4*>(s_ba + threadIdx.x * 16) = make_uint4(threadIdx.x < 8 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();  // the bias operands are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -3350,6 +3378,8 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
     const uint32_t d1f0 = smem_addr_once(&d1_full_bar[0]), acce0 = smem_addr_once(&acc_empty_bar[0]);
     const uint64_t da_base = umma_smem_desc(smem_u32(s_a), 512, 4u);
     const uint64_t db = umma_smem_desc(smem_u32(s_w1), 512, 4u);
+    const uint64_t da_bias = umma_smem_desc_noswz(smem_u32(s_ba), 128, 0);     // every 8-row group: the same core matrix
+    const uint64_t db_bias = umma_smem_desc_noswz(smem_u32(s_bb), 2048, 128);
     int stage = 0, g = 0, j = 0;
     uint32_t phase = 0;
     mbar_wait(&w_bar, 0, 5);
@@ -3364,6 +3394,7 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
         for (int kk = 0; kk < 2; ++kk)
           umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, kk > 0 ? 1u : 0u);
         umma_commit_a(empty0 + stage * 8);
+        umma_bf16(d_tmem, da_bias, db_bias, idesc, 1u);  // + bias (reads constants only: after the input slot's release)
         umma_commit_a(d1f0 + g * 8);
       }
       __syncwarp();
@@ -3465,24 +3496,15 @@ __global__ void __launch_bounds__(kI2Threads, 1) convt_conv_score_kernel(const _
           const int py = 2 * iy + (tap >> 1), px = 2 * ix + (tap & 1);
           const int gy = oy0 + py, gx = ox0 + px;
           const bool inside = gy >= 0 && gy < Ho && gx >= 0 && gx < Wo;
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + hp * 16);
-          uint32_t p[8];
+          uint32_t p[8];  // (bias: added by the GEMM)
           if (relu) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float4 bv = b4[jj];
-              p[2 * jj] = pack_bf16x2_relu(__uint_as_float(v[4 * jj]) + bv.x, __uint_as_float(v[4 * jj + 1]) + bv.y);
-              p[2 * jj + 1] = pack_bf16x2_relu(__uint_as_float(v[4 * jj + 2]) + bv.z, __uint_as_float(v[4 * jj + 3]) + bv.w);
-            }
+            for (int jj = 0; jj < 8; ++jj)
+              p[jj] = pack_bf16x2_relu(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1]));
           } else {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float4 bv = b4[jj];
-              p[2 * jj] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj]) + bv.x, a.slope),
-                                      act_fn(__uint_as_float(v[4 * jj + 1]) + bv.y, a.slope));
-              p[2 * jj + 1] = pack_bf16x2(act_fn(__uint_as_float(v[4 * jj + 2]) + bv.z, a.slope),
-                                          act_fn(__uint_as_float(v[4 * jj + 3]) + bv.w, a.slope));
-            }
+            for (int jj = 0; jj < 8; ++jj)
+              p[jj] = pack_bf16x2(act_fn(__uint_as_float(v[2 * jj]), a.slope), act_fn(__uint_as_float(v[2 * jj + 1]), a.slope));
           }
           const int pp = py * 32 + px;
           if (a.dbg & 32) continue;  // ablation: no patch writes

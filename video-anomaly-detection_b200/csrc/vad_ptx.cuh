@@ -264,6 +264,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(layout_type & 7) << 61;
   return d;
 }
+// K-major operand WITHOUT swizzle (layout type 0): 8-row x 16-byte core matrices; the rows of a core matrix are 16 bytes
+// apart, the next K chunk (8 more bf16 of every row) lbo_bytes further, the next 8 rows sbo_bytes further.  The strides
+// are plain address arithmetic: chunks of different rows may overlap (DESIGN.md finding 19) and sbo = 0 makes every
+// 8-row group read the same 128 bytes (a constant operand, e.g. the column of ones that adds a bias inside the GEMM).
+__device__ __forceinline__ uint64_t umma_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
 // Instruction descriptor: c=f32 ([4,6)=1), a=b=bf16 ([7,10)=1,[10,13)=1), K-major both, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
