@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-2 final measurement campaign on one B200 (run under gpurun): GPU test log, bench lines for cfg1-4, the reference
-# arm, and an ncu --set full capture of one cfg2 step.  Outputs under gpurun_out/ with the given tag.
+# arm; with a second argument "ncu" also ncu --set full captures of one cfg2 and one cfg4 step.  Outputs under
+# gpurun_out/ with the given tag.
 TAG=${1:-r02f}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -s > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -1 gpurun_out/${TAG}_pytest_gpu.log
@@ -19,6 +20,11 @@ except Exception as e:
     print(sys.argv[1], "unreadable", e)
 PY
 done
-timeout 900 ncu --set full --clock-control none -k "regex:conv|finalize|enc1_fused" -s 45 -c 31 -f -o gpurun_out/${TAG}_prof_cfg2 \
+if [ "$2" = "ncu" ]; then  # (two reports of one step each: gpurun brings back at most 64 MiB)
+timeout 900 ncu --set full --clock-control none -k "regex:conv|finalize|enc1_fused" -s 45 -c 16 -f -o gpurun_out/${TAG}_prof_cfg2 \
   python bench.py --steps 1 --warmup 1 --no-extras --no-cpu-baseline --no-gpu-library-baseline > gpurun_out/${TAG}_ncu_cfg2.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_cfg2.log | cut -c1-200
+timeout 900 ncu --set full --clock-control none -k "regex:conv|finalize|enc1_fused" -s 27 -c 10 -f -o gpurun_out/${TAG}_prof_cfg4 \
+  python bench.py --steps 1 --warmup 1 --no-extras --no-cpu-baseline --no-gpu-library-baseline --workload cfg4 > gpurun_out/${TAG}_ncu_cfg4.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu_cfg4.log | cut -c1-200
+fi
