@@ -114,6 +114,13 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.vad_score_scratch_bytes(4, 256, 256) == 4 * 8 * 16
     assert lib.vad_first_conv(None, None, None, 32, 0.2, 0, 1, 16, 16, None, None) == -1
     assert lib.vad_score(None, None, 1, 16, 16, None, None, None, None, None) == -1
+    # the fused first encoder block: null pointers, then the shape rule (H, W multiples of 16), before any CUDA call
+    assert lib.vad_enc1_fused(None, None, None, None, None, 0.2, 1, 16, 16, None, None) == -1
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf) // 16 * 16 + 16
+    assert lib.vad_enc1_fused(p, p, p, p, p, 0.2, 1, 24, 16, p, None) == -2
+    assert lib.vad_enc1_fused(p, p, p, p, p, 0.2, 1, 16, 40, p, None) == -2
+    assert lib.vad_compose_panel(None, None, None, None, 1, 16, 16, None, None) == -1
 
 
 def test_fused_tail_entry_points_validate_on_the_host(lib):
