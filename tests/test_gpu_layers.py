@@ -140,7 +140,10 @@ def test_pixel_pair_folded_conv_equals_ordinary_view(cuda_device, cout, B, H, W,
 
 
 @pytest.mark.parametrize("cin,cout,B,H,W", [(256, 128, 2, 16, 16), (128, 64, 2, 8, 24), (64, 32, 3, 16, 16),
-                                           (32, 32, 2, 32, 32), (128, 128, 3, 4, 4)])
+                                           (32, 32, 2, 32, 32), (128, 128, 3, 4, 4),
+                                           # heights that are not a multiple of the 16-row tile (720p: 45 and 90 rows):
+                                           # the pixel shuffle goes through the two split output maps, rows clipped
+                                           (128, 64, 2, 45, 80), (128, 128, 1, 90, 160), (64, 32, 3, 22, 40)])
 def test_convt2x2(cuda_device, cin, cout, B, H, W):
     eng, nat, prep = _mods()
     dev = cuda_device

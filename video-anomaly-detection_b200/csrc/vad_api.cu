@@ -930,6 +930,20 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
                             (cuuint64_t)4 * d->W * cp * 2};
         cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, 1, (cuuint32_t)TW, 1, (cuuint32_t)(TH * TN)};
         a.tma_store = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK;
+      } else if (TN == 1) {
+        // frame heights that are not a multiple of the tile height (720p: 90 and 45 rows against 16-row tiles): the merged
+        // (b, h) dimension would let a tile's overhanging rows land in the next frame, and the direct-store fallback costs
+        // 30-40 % of these HBM-bound layers.  Two maps instead, one per output row parity di, with h and b as separate
+        // dimensions: {co, dj, w, h, b}, base = out + di * (one output row).
+        a.out_chunk = (d->cout % 64 == 0) ? 64 : 32;
+        cuuint64_t dims[5] = {(cuuint64_t)d->cout, 2, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+        cuuint64_t st[4] = {(cuuint64_t)cp * 2, (cuuint64_t)2 * cp * 2, (cuuint64_t)4 * d->W * cp * 2,
+                            (cuuint64_t)d->out_frame_stride * 2};
+        cuuint32_t box[5] = {(cuuint32_t)a.out_chunk, 1, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        const __nv_bfloat16* row1 = static_cast<const __nv_bfloat16*>(d->out) + 2LL * d->W * cp;
+        a.convt_split = encode_map5(&a.mapOut, d->out, dims, st, box, a.out_chunk) == VAD_OK &&
+                        encode_map5(&a.mapOut2, row1, dims, st, box, a.out_chunk) == VAD_OK;
+        a.tma_store = a.convt_split;
       }
     }
   }
@@ -947,6 +961,16 @@ int build_conv(const vad_conv_desc* d, ConvLaunch& L) {
   L.use_halo = use_halo;
   L.grid = a.total_tiles < sm_count() ? a.total_tiles : sm_count();
   if (use_hs) L.grid = (a.total_tiles >> 1) < sm_count() ? (a.total_tiles >> 1) : sm_count();
+  // Transposed convolutions on the streaming kernel keep their weight tiles resident (see conv_umma_kernel): needs one
+  // tap, one source, a k loop that fits the ring (5 slots of 32 KB for CK = 64, BN = 128) and a grid that is a multiple
+  // of n_tiles, so that every tile of a CTA has the same n0.  VAD_CONVT_RESIDENT=0 switches it off.
+  a.b_resident = 0;
+  static const int resident_env = env_int("VAD_CONVT_RESIDENT", 1);
+  if (resident_env && !use_hs && !use_kx && !use_halo && epi == VAD_EPI_CONVT && d->ntaps == 1 && a.chunks1 == 0 && CK == 64 &&
+      BN == 128 && a.ntaps * a.chunks0 <= 4 && L.grid >= a.n_tiles && a.n_tiles <= 8) {
+    L.grid = (L.grid / a.n_tiles) * a.n_tiles;
+    a.b_resident = 1;
+  }
   return VAD_OK;
 }
 }  // namespace

@@ -375,7 +375,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const TileCoord
             tma_store_5d(&a.mapOut, buf, col, t.w0 >> 1, t.h0 >> 1, 0, t.b0);
           } else {  // ConvT pixel shuffle: map dims {co, dj, w, di, b*H + h}
             const int quad = (col >= a.cout) + (col >= 2 * a.cout) + (col >= 3 * a.cout);
-            tma_store_5d(&a.mapOut, buf, col - quad * a.cout, quad & 1, t.w0, quad >> 1, t.b0 * a.H + t.h0);
+            if (a.convt_split)  // one map per output row parity, {co, dj, w, h, b}: rows past the frame are clipped
+              tma_store_5d((quad >> 1) ? &a.mapOut2 : &a.mapOut, buf, col - quad * a.cout, quad & 1, t.w0, t.h0, t.b0);
+            else
+              tma_store_5d(&a.mapOut, buf, col - quad * a.cout, quad & 1, t.w0, quad >> 1, t.b0 * a.H + t.h0);
           }
           bulk_commit_group();
         }
@@ -704,11 +707,12 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
   using C = Cfg<CK, BN, EPI>;
   constexpr int kAS = acc_stages_for(epi_groups(BN, EPI));
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[C::kStages];
-  __shared__ uint64_t empty_bar[C::kStages];
+  __shared__ uint64_t full_bar[2 * C::kStages];   // (b_resident: up to 2 * kStages - k_iters activation slots)
+  __shared__ uint64_t empty_bar[2 * C::kStages];
   __shared__ uint64_t acc_full_bar[kMaxAccStages];
   __shared__ uint64_t acc_empty_bar[kMaxAccStages];
   __shared__ uint64_t turn_bar[2];  // MMA issuer ping-pong token
+  __shared__ uint64_t w_bar;        // b_resident: this CTA's weight tiles have landed
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_smem[kMaxAccStages][4][3];
   __shared__ __align__(16) float s_bias[kMaxBiasStream];
@@ -722,20 +726,31 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
   const uint32_t tx_bytes = static_cast<uint32_t>(rows_valid * C::kRowBytes + C::kBBytes);
   const int chunks = a.chunks0 + a.chunks1;
   const int k_iters = a.ntaps * chunks;
+  // Ring slots.  Normally slot s = [A tile | B tile] at s * kStageBytes.  With resident weights (b_resident) weight tile
+  // k sits in the B half of slot k for the whole launch and EVERY other half carries an activation tile: the A halves of
+  // all kStages slots plus the B halves of slots k_iters .. kStages-1 — twice the bytes in flight per SM, which is
+  // what a latency-bound streaming layer needs (the 720p transposed convolutions: nothing but loads on the critical
+  // path — ablating the whole epilogue and the stores changes nothing).
+  const int ns = a.b_resident ? 2 * C::kStages - k_iters : C::kStages;
+  auto slot_off = [&](int sl) -> uint32_t {
+    return static_cast<uint32_t>(sl < C::kStages ? sl * C::kStageBytes : (k_iters + sl - C::kStages) * C::kStageBytes + C::kABytes);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.mapA0);
     if (a.chunks1 > 0) tma_prefetch_desc(&a.mapA1);
     tma_prefetch_desc(&a.mapB);
     if (a.tma_store) tma_prefetch_desc(&a.mapOut);
+    if (a.convt_split) tma_prefetch_desc(&a.mapOut2);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < 2 * C::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&turn_bar[0], 1);
     mbar_init(&turn_bar[1], 1);
+    mbar_init(&w_bar, 1);
     for (int i = 0; i < kMaxAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       mbar_init(&acc_empty_bar[i], 4);  // one arrive per warp of the owning epilogue group
@@ -770,6 +785,21 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
     // addressed explicitly, so any order is valid, and this one puts everything that does not depend on the previous
     // ConvLSTM step first
     bool waited = a.pdl != 2;
+    // Resident weights (transposed convolutions: one tap, k_iters <= ring depth, grid a multiple of n_tiles so that this
+    // CTA's tiles all have the same n0): weight tile k lives in the B half of ring slot k for the whole launch and the
+    // ring's A halves carry the activations — half the L2 -> shared-memory traffic and half the TMA issues per tile
+    // (the 720p video decoder's transposed convolutions ran at 0.35-0.45 of the HBM peak with L2 70 % busy).
+    const uint32_t a_bytes = static_cast<uint32_t>(rows_valid * C::kRowBytes);
+    if (a.b_resident && blockIdx.x < a.total_tiles) {
+      TileIter t0(a, blockIdx.x, gridDim.x);
+      const int n0 = t0.coord(a, BN).n0;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&w_bar, static_cast<uint32_t>(k_iters * C::kBBytes));
+        for (int kq = 0; kq < k_iters; ++kq)
+          tma_load_2d(smem + kq * C::kStageBytes + C::kABytes, &a.mapB, &w_bar, kq * CK, n0);
+      }
+      __syncwarp();
+    }
     for (TileIter ti(a, blockIdx.x, gridDim.x); ti.tile < a.total_tiles; ti.next(a)) {
       const TileCoord t = ti.coord(a, BN);
       for (int src = 0; src < 2; ++src) {
@@ -782,18 +812,18 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
           for (int c = c_lo; c < c_hi; ++c) {
             mbar_wait_a(empty0 + stage * 8, phase ^ 1u, 1);
             if (elect_one()) {
-              const uint32_t sa = smem0 + stage * C::kStageBytes;
+              const uint32_t sa = smem0 + slot_off(stage);
               const uint32_t fb = full0 + stage * 8;
-              mbar_arrive_expect_tx_a(fb, tx_bytes);
+              mbar_arrive_expect_tx_a(fb, a.b_resident ? a_bytes : tx_bytes);
               if (src == 0)
                 tma_load_5d_a(sa, &a.mapA0, fb, c * CK, t.w0 + dx, t.h0 + dy, a.tA0, t.b0);
               else
                 tma_load_5d_a(sa, &a.mapA1, fb, (c - a.chunks0) * CK, t.w0 + dx, t.h0 + dy, a.tA1, t.b0);
-              tma_load_2d_a(sa + C::kABytes, &a.mapB, fb, kcol, t.n0);
+              if (!a.b_resident) tma_load_2d_a(sa + C::kABytes, &a.mapB, fb, kcol, t.n0);
             }
             __syncwarp();
             kcol += CK;
-            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            if (++stage == ns) { stage = 0; phase ^= 1u; }
           }
           if (++dx == 2) { dx = -1; ++dy; }  // next tap (3x3: row-major over (dy, dx) in -1..1)
         }
@@ -804,7 +834,7 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
     // Two issuers are only safe while a tile's k-loop is SHORTER than the operand ring: the issuer that runs ahead
     // then never waits on a slot a full ring revolution early (mbarrier phase parity would alias and let it through
     // on stale data).  Long k-loops use warp 1 alone.
-    const bool dual = a.dual_mma && k_iters < C::kStages;
+    const bool dual = a.dual_mma && k_iters < ns;
     const int mi = warp == 1 ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
     const uint32_t full0 = smem_addr_once(&full_bar[0]), empty0 = smem_addr_once(&empty_bar[0]);
@@ -814,12 +844,13 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (a.b_resident && blockIdx.x < a.total_tiles && (dual || mi == 0)) mbar_wait(&w_bar, 0, 5);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       if (!dual && mi == 1) break;
       if (dual && (it & 1) != mi) {  // the other issuer's tile: only keep the ring position in step
-        stage += k_iters % C::kStages;
-        phase ^= static_cast<uint32_t>((k_iters / C::kStages) & 1);
-        if (stage >= C::kStages) { stage -= C::kStages; phase ^= 1u; }
+        stage += k_iters % ns;
+        phase ^= static_cast<uint32_t>((k_iters / ns) & 1);
+        if (stage >= ns) { stage -= ns; phase ^= 1u; }
         continue;
       }
       const int as = it % kAS;
@@ -830,9 +861,9 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
         mbar_wait_a(full0 + stage * 8, phase, 2);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t soff = static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+          const uint64_t soff = static_cast<uint64_t>(slot_off(stage) >> 4);
           const uint64_t da = da_base + soff;
-          const uint64_t db = db_base + soff;
+          const uint64_t db = a.b_resident ? db_base + static_cast<uint64_t>(k * (C::kStageBytes >> 4)) : db_base + soff;
 #pragma unroll
           for (int kk = 0; kk < CK / 16; ++kk) {
             // advance 16 bf16 = 32 B inside the swizzle span: +2 in the (addr >> 4) field
@@ -843,7 +874,7 @@ __global__ void __launch_bounds__(block_threads(BN, EPI), 1) conv_umma_kernel(co
           if (k == k_iters - 1) umma_commit_a(accf0 + as * 8);      // accumulator ready for the epilogue
         }
         __syncwarp();
-        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        if (++stage == ns) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= kEpiWarp0) {

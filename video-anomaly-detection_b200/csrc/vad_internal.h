@@ -15,6 +15,7 @@ struct alignas(64) ConvArgs {
   CUtensorMap mapA1;   // optional source 1 (ConvLSTM hidden state)
   CUtensorMap mapB;    // bf16 [n_total][K] weights, box {CK, BN}
   CUtensorMap mapOut;  // bf16 output, used when tma_store != 0 (box = one staged chunk of the output tile)
+  CUtensorMap mapOut2;  // transposed conv with convt_split: the map of output rows 2h + 1 (mapOut: rows 2h)
   int chunks0, chunks1;  // CK-wide channel chunks per source
   int ntaps;
   int w_ctap;  // weight columns per tap
@@ -48,6 +49,10 @@ struct alignas(64) ConvArgs {
   long long* timeline;  // optional [role 0..3][64 tiles][8 events] clock64 stamps of CTA 0 (vad_debug_set_timeline)
   const void* w_first;  // first conv: bf16 [32 n][32 k] weights, k = (ky*3+kx)*3+ci (27 real + 5 zero)
   int pair_fold;        // halo kernel: pixel-pair folded 3x3 layer (vad_conv_desc.pair_fold)
+  int convt_split;      // ConvT TMA store through two maps {co, dj, w, h, b} (di folded into the base address): h and b stay
+                        // separate dimensions, so tiles that overhang the frame's last rows are clipped by the hardware
+  int b_resident;       // streaming kernel, single-tap layers: this CTA's weight tiles stay in shared memory (the grid is
+                        // a multiple of n_tiles, so a CTA only ever sees one n tile); the ring carries activations only
   // epilogue staging / TMA store
   int tma_store;  // 1: stage the bf16 tile in swizzled smem and store it with TMA (coalesced, clipped by hardware)
   int out_chunk;  // channels per staged chunk: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
